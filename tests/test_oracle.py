@@ -1,0 +1,141 @@
+"""CPU tests: the NumPy oracle (oracle/icem_np.py) against fixtures recorded from the UNMODIFIED
+reference controller (tests/golden/*.npz, made by oracle/make_golden.py), plus a live re-check
+when /root/reference is present."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cases, costs_np, ref_loader
+from oracle.icem_np import ICemConfig, ICemOracle, population_schedule, trajectories_per_plan_step
+from oracle.shims import colorednoise as cn
+
+COSTS = {"halfcheetah": costs_np.halfcheetah_cost, "humanoid_standup": costs_np.humanoid_standup_cost}
+
+
+def run_oracle_case(case, record_actions=False):
+    model = case["model"]()
+    cfg = ICemConfig(**cases.controller_config(case))
+    if case["cost"] == "halfcheetah":
+        cost = lambda o, a: costs_np.halfcheetah_cost(o, a, case["penalise_flipping"])
+    else:
+        cost = COSTS[case["cost"]]
+    orc = ICemOracle(cfg, model.rollout, cost, record_actions=record_actions)
+    np.random.seed(case["seed"])
+    obs = np.asarray(case["start_obs"], np.float64).copy()
+    orc.beginning_of_rollout()
+    traces = []
+    for _ in range(case["steps"]):
+        tr = orc.get_action(obs)
+        traces.append(tr)
+        obs = model.step(obs[None], tr.action[None])[0]
+    return traces, float(np.random.randn())
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_oracle_matches_reference_golden(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    traces, next_randn = run_oracle_case(cases.CASES[name])
+    assert next_randn == float(g["next_randn"])          # identical RNG consumption
+    assert len(traces) == int(g["num_steps"])
+    for s, tr in enumerate(traces):
+        np.testing.assert_allclose(tr.action, g[f"s{s}_action"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(tr.mean_after_shift, g[f"s{s}_mean_after_shift"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(tr.std_after_reset, g[f"s{s}_std_after_reset"], rtol=0, atol=1e-12)
+        assert len(tr.iterations) == int(g[f"s{s}_num_iters"])
+        for i, it in enumerate(tr.iterations):
+            np.testing.assert_allclose(it.costs, g[f"s{s}_i{i}_costs"], rtol=0, atol=1e-10)
+            np.testing.assert_array_equal(it.elite_idx, g[f"s{s}_i{i}_elite_idx"])   # bit-exact, in order
+            np.testing.assert_allclose(it.mean, g[f"s{s}_i{i}_mean"], rtol=0, atol=1e-12)
+            np.testing.assert_allclose(it.std, g[f"s{s}_i{i}_std"], rtol=0, atol=1e-12)
+
+
+def test_appendix_c_known_answers(golden_dir):
+    """SURVEY Appendix C numbers, typed in independently of the fixture file."""
+    traces, next_randn = run_oracle_case(cases.CASES["appendix_c"])
+    np.testing.assert_allclose(
+        traces[0].action, [0.00573912, 0.03802868, 0.12162141, 0.30960938, -0.1226788, -0.08239668], atol=1e-8)
+    assert [it.population for it in traces[0].iterations] == [40, 35, 28]
+    assert [it.population for it in traces[1].iterations] == [43, 35, 28]
+    assert list(traces[0].iterations[0].elite_idx) == [16, 20, 8, 29, 31, 33, 15, 0, 28, 21]
+    assert list(traces[2].iterations[0].elite_idx) == [40, 41, 42, 17, 2, 0, 34, 35, 11, 33]
+    np.testing.assert_allclose(traces[2].iterations[2].costs.min(), -13.22418276, atol=1e-7)
+    assert abs(next_randn - (-1.409332708115941)) < 1e-15
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference not present")
+def test_oracle_matches_live_reference():
+    from oracle import ref_harness
+    case = cases.CASES["cheetah_n128"]
+    steps, next_ref = ref_harness.run_reference_episode(
+        case["model"](), case["cost"], case["ctrl"], case["low"], case["high"], case["start_obs"],
+        case["seed"], 2, case["penalise_flipping"])
+    short = dict(case, steps=2)
+    traces, next_orc = run_oracle_case(short)
+    assert next_ref == next_orc
+    for st, tr in zip(steps, traces):
+        np.testing.assert_allclose(tr.action, st["action"], atol=1e-12)
+        for a, b in zip(tr.iterations, st["iterations"]):
+            np.testing.assert_array_equal(a.elite_idx, b["elite_idx"])
+            np.testing.assert_allclose(a.costs, b["costs"], atol=1e-10)
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference not present")
+def test_costs_match_reference_cost_fn():
+    ref_loader.install_reference()
+    import environments.mujoco as m
+
+    class Dummy:
+        penalise_flipping = True
+    rs = np.random.RandomState(0)
+    for od in (17, 18):
+        o = 2.5 * rs.randn(7, 30, od)
+        a = rs.randn(7, 30, 6)
+        np.testing.assert_array_equal(m.HalfCheetahMaybeWithPosition.cost_fn(Dummy(), o, a),
+                                      costs_np.halfcheetah_cost(o, a, True))
+    o = rs.randn(7, 30, 378)
+    a = rs.randn(7, 30, 17)
+    np.testing.assert_array_equal(m.HumanoidStandup.cost_fn(Dummy(), o, a, None),
+                                  costs_np.humanoid_standup_cost(o, a))
+
+
+def test_population_schedule_configs():
+    """SURVEY section 8 population sizes for the BASELINE configs."""
+    def sched(n, iters):
+        return population_schedule(ICemConfig(horizon=30, num_simulated_trajectories=n, action_low=[-1], action_high=[1],
+                                              factor_decrease_num=1.25, opt_iterations=iters))
+    assert sched(128, 3) == [128, 102, 81]
+    assert sched(4096, 5) == [4096, 3276, 2620, 2096, 1676]
+    assert sched(16384, 3) == [16384, 13107, 10485]
+    assert sched(262144, 3) == [262144, 209715, 167772]
+    assert sched(40, 3) == [40, 32, 25]
+    cfg = ICemConfig(horizon=30, num_simulated_trajectories=40, action_low=[-1], action_high=[1],
+                     factor_decrease_num=1.25, opt_iterations=3)
+    assert trajectories_per_plan_step(cfg, True) == 97
+    assert trajectories_per_plan_step(cfg, False) == 100
+
+
+def test_colorednoise_draw_equivalence_and_constants():
+    """normal(scale=s) == standard_normal*s bit-for-bit; Appendix A constants; matrix form == irfft."""
+    s, sigma = cn.spectrum_scale(0.25, 30)
+    np.testing.assert_allclose(s[:4], [1.5298, 1.5298, 1.4029, 1.3335], atol=5e-5)
+    assert abs(sigma - 0.309708) < 1e-6
+    assert abs(cn.spectrum_scale(2.0, 30)[1] - 2.511658) < 1e-6
+    assert abs(cn.spectrum_scale(0.25, 12)[1] - 0.462438) < 1e-6
+    np.random.seed(5)
+    a = np.random.normal(scale=s, size=(3, 4, 16))
+    np.random.seed(5)
+    b = np.random.standard_normal((3, 4, 16)) * s
+    np.testing.assert_array_equal(a, b)
+    np.random.seed(9)
+    rec_prev, cn.RECORDER = cn.RECORDER, []
+    y = cn.powerlaw_psd_gaussian(0.25, (5, 6, 30))
+    (zr, zi), = cn.RECORDER
+    cn.RECORDER = rec_prev
+    np.testing.assert_array_equal(y, cn.synthesize(zr, zi, 0.25, 30))
+    assert 0.9 < y.var() < 1.2
+
+
+def test_min_trajectories_error():
+    with pytest.raises(ValueError, match="At least two trajectories"):
+        ICemConfig(horizon=3, num_simulated_trajectories=1, action_low=[-1], action_high=[1])
