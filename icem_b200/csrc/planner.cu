@@ -1,0 +1,1033 @@
+// libicem_b200: device-resident iCEM planner + C ABI (include/icem_b200.h).
+//
+// One planner object == one `MpcICem` instance (reference: icem/controllers/icem.py:16-247).  The whole plan
+// step (all CEM iterations: fused sample->rollout->cost kernel, select+refit kernel, optional NCCL
+// all-gather) is enqueued on one stream without host synchronisation and replayed as a CUDA graph;
+// only the start state goes in and action[d] (+ best cost) comes out per step.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../../include/icem_b200.h"
+#include "comm.cuh"
+#include "common.cuh"
+#include "dyn_articulated.cuh"
+#include "dyn_dense.cuh"
+#include "rollout.cuh"
+#include "select_refit.cuh"
+
+namespace icem {
+
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+struct InvalidArg : std::runtime_error { using std::runtime_error::runtime_error; };
+struct StateError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct Unsupported : std::runtime_error { using std::runtime_error::runtime_error; };
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) {
+      ICEM_CUDA(cudaMalloc(&p, count * sizeof(T)));
+      ICEM_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+    }
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+struct IterPlan {
+  int n_global;       // N_i
+  int chunk;          // ceil(N_i / world)
+  int n_fresh_local;  // rows this rank samples
+  int global_offset;  // global index of local row 0
+  int n_shift_local;  // shifted-elite rows this rank simulates at iteration 0 when elites exist
+  int rows_cap;       // n_fresh_local + n_shift_local
+  size_t cost_off;    // offset into costs buffer
+  size_t act_off;     // offset (rows) into actions buffer
+};
+
+}  // namespace icem
+
+using namespace icem;
+
+struct icem_planner {
+  icem_config_t cfg{};
+  std::vector<float> low, high;
+  int h = 0, d = 0, hd = 0, K = 0, k = 0, n_keep = 0, stride = 0, iters = 0;
+  int state_dim = 0, obs_dim = 0;
+  int sm_count = 148;
+  bool white = false;
+  std::vector<IterPlan> plan;
+  cudaStream_t stream = nullptr;
+
+  // device state
+  DevBuf<float> actions, costs, G, d_low, d_high, mean, stdv, init_mean, init_std;
+  DevBuf<float> elite_actions[2], elite_costs[2];
+  DevBuf<int32_t> elite_idx[2];
+  DevBuf<float> trace_mean, trace_std, trace_costs;
+  DevBuf<int32_t> trace_idx;
+  DevBuf<float> out;              // [d] action, [1] best cost
+  DevBuf<unsigned char> step_in;  // StepState + start state (fp32)
+  DevBuf<unsigned long long> cand;
+  DevBuf<unsigned int> ticket;
+  DevBuf<float> w_obs, w_act, bias;      // dense model
+  DevBuf<unsigned char> flush;           // L2 flush buffer (bench)
+  std::vector<DevBuf<float>> inj_zr, inj_zi;
+  std::vector<int> inj_rows;
+  // multi-rank
+  Comm comm;
+  DevBuf<unsigned char> send_rec, recv_rec;
+  size_t rec_bytes = 0;
+
+  // pinned host staging
+  unsigned char* h_in = nullptr;
+  float* h_out = nullptr;
+  size_t in_bytes = 0;
+
+  // model params
+  DenseTanh::Params dense{};
+  bool model_ready = false;
+  Articulated::Params art{};
+
+  // run state
+  bool was_reset = false;
+  uint32_t step = 0;
+  bool has_prev = false;
+  bool inject_pending = false;
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  std::vector<cudaEvent_t> ev_roll;   // pairs around rollout kernels (bench / timing mode)
+  float last_total_ms = 0.f, last_rollout_ms = 0.f;
+
+  ~icem_planner() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    for (auto e : ev_roll) cudaEventDestroy(e);
+    if (ev_a) cudaEventDestroy(ev_a);
+    if (ev_b) cudaEventDestroy(ev_b);
+    if (h_in) cudaFreeHost(h_in);
+    if (h_out) cudaFreeHost(h_out);
+    comm.destroy();
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace icem {
+
+// --------------------------------------------------------------------------------------------------
+// Synthesis matrix of the power-law colored-noise sampler (colorednoise.powerlaw_psd_gaussian, call
+// site icem/controllers/icem.py:73-75; algorithm restated in oracle/shims/colorednoise.py):
+//   y[t] = sum_j G[t][j] z[j],  z = [zr(K), zi(K)] unit normals,
+//   y = irfft(s*(zr + i zi), n=h) / sigma,  s_k = f_k^(-beta/2) (DC takes bin 1's scale),
+//   sigma = 2 sqrt(sum_{k>=1} w_k^2) / h  (w = s, Nyquist halved for even h).
+static std::vector<float> build_synthesis_matrix(int h, double beta, bool v2) {
+  const int K = h / 2 + 1;
+  std::vector<double> s(K);
+  for (int k = 0; k < K; ++k) s[k] = (double)k / h;
+  const double fmin = 1.0 / h;
+  int ix = 0;
+  for (int k = 0; k < K; ++k) ix += s[k] < fmin;
+  if (ix && ix < K)
+    for (int k = 0; k < ix; ++k) s[k] = s[ix];
+  for (int k = 0; k < K; ++k) s[k] = std::pow(s[k], -beta / 2.0);
+  double acc = 0;
+  for (int k = 1; k < K; ++k) {
+    double w = s[k];
+    if (k == K - 1) w *= (1 + (h % 2)) / 2.0;
+    acc += w * w;
+  }
+  const double sigma = 2.0 * std::sqrt(acc) / h;
+  const bool even = (h % 2) == 0;
+  std::vector<float> G((size_t)h * 2 * K, 0.f);
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int t = 0; t < h; ++t) {
+    for (int k = 0; k < K; ++k) {
+      double gr, gi;
+      const bool dc = k == 0, nyq = even && k == K - 1;
+      if (dc) { gr = s[0] / h; gi = 0; }
+      else if (nyq) { gr = ((t & 1) ? -1.0 : 1.0) * s[k] / h; gi = 0; }
+      else {
+        const double ang = two_pi * (double)((long long)k * t % h) / h;
+        gr = 2.0 * std::cos(ang) * s[k] / h;
+        gi = -2.0 * std::sin(ang) * s[k] / h;
+      }
+      if (v2 && (dc || nyq)) gr *= std::sqrt(2.0);
+      G[(size_t)t * 2 * K + k] = (float)(gr / sigma);
+      G[(size_t)t * 2 * K + K + k] = (float)(gi / sigma);
+    }
+  }
+  return G;
+}
+
+static void upload(DevBuf<float>& b, const std::vector<float>& v) {
+  b.alloc(v.size());
+  ICEM_CUDA(cudaMemcpy(b.p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+// --------------------------------------------------------------------------------------------------
+static SamplerConst sampler_const(icem_planner* p) {
+  SamplerConst sc{};
+  sc.h = p->h; sc.d = p->d; sc.K = p->K; sc.white = p->white;
+  sc.G = p->G.p; sc.low = p->d_low.p; sc.high = p->d_high.p;
+  return sc;
+}
+
+static CostConst cost_const(icem_planner* p) {
+  CostConst cc{};
+  cc.kind = p->cfg.cost;
+  cc.reduce = p->cfg.cost_along_trajectory;
+  cc.penalise_flipping = p->cfg.cost_penalise_flipping;
+  if (p->cfg.cost == ICEM_COST_HALFCHEETAH) {
+    // environments/mujoco.py:77-84: (root angle, x velocity) = obs[2], obs[9] (18-dim) or obs[1], obs[8] (17-dim)
+    cc.idx_a = p->obs_dim == 18 ? 2 : 1;
+    cc.idx_b = p->obs_dim == 18 ? 9 : 8;
+  } else {
+    cc.idx_a = 2;   // environments/mujoco.py:267 root z
+    cc.idx_b = 0;
+  }
+  return cc;
+}
+
+static StepState* step_state_dev(icem_planner* p) { return reinterpret_cast<StepState*>(p->step_in.p); }
+static float* start_state_dev(icem_planner* p) { return reinterpret_cast<float*>(p->step_in.p + sizeof(StepState)); }
+
+template <class Dyn, bool kSample, bool kRollout>
+static void launch_rollout(icem_planner* p, const RolloutArgs& a, const typename Dyn::Params& dp, int rows_max) {
+  const SamplerConst sc = sampler_const(p);
+  const CostConst cc = cost_const(p);
+  const int warps = Dyn::kWarpsPerCta;
+  const size_t smem = rollout_smem_bytes<Dyn, kSample>(sc, dp, a.stride, warps);
+  auto kern = rollout_kernel<Dyn, kSample, kRollout>;
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    ICEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int occ = 0;
+  ICEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
+  if (occ < 1) throw InvalidArg("rollout kernel does not fit on an SM (shared memory)");
+  const int ctas_needed = (rows_max + warps - 1) / warps;
+  const int grid = std::max(1, std::min(ctas_needed, p->sm_count * occ));   // persistent: <= one resident wave
+  kern<<<grid, warps * 32, smem, p->stream>>>(a, sc, cc, dp);
+  ICEM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+template <bool kSample, bool kRollout>
+static void launch_rollout_dyn(icem_planner* p, const RolloutArgs& a, int rows_max) {
+  switch (p->cfg.dynamics) {
+    case ICEM_DYN_DENSE_TANH:
+      launch_rollout<DenseTanh, kSample, kRollout>(p, a, p->dense, rows_max);
+      break;
+    case ICEM_DYN_HALFCHEETAH:
+    case ICEM_DYN_HUMANOID_STANDUP:
+      launch_rollout<Articulated, kSample, kRollout>(p, a, p->art, rows_max);
+      break;
+    default:
+      throw Unsupported("dynamics id not supported by this build");
+  }
+}
+
+static RolloutArgs rollout_args(icem_planner* p, int i) {
+  const IterPlan& ip = p->plan[i];
+  RolloutArgs a{};
+  a.n_fresh_local = ip.n_fresh_local;
+  a.n_shift_local = ip.n_shift_local;
+  a.global_offset = ip.global_offset;
+  a.n_fresh_global = ip.n_global;
+  a.iteration = i;
+  a.inject_mean_row0 = p->cfg.use_mean_actions && i == p->iters - 1;
+  a.stride = p->stride;
+  a.actions = p->actions.p + ip.act_off * p->stride;
+  a.costs = p->costs.p + ip.cost_off;
+  a.mean = p->mean.p;
+  a.std = p->stdv.p;
+  a.prev_elites = p->elite_actions[(p->iters - 1) & 1].p;
+  a.start_state = start_state_dev(p);
+  a.inj_zr = (size_t)i < p->inj_zr.size() ? p->inj_zr[i].p : nullptr;
+  a.inj_zi = (size_t)i < p->inj_zi.size() ? p->inj_zi[i].p : nullptr;
+  a.ss = step_state_dev(p);
+  a.seed_lo = (uint32_t)p->cfg.seed;
+  a.seed_hi = (uint32_t)(p->cfg.seed >> 32);
+  return a;
+}
+
+static RefitArgs refit_args(icem_planner* p, int i) {
+  const IterPlan& ip = p->plan[i];
+  RefitArgs r{};
+  r.h = p->h; r.d = p->d; r.k = p->k; r.stride = p->stride; r.iteration = i;
+  r.last_iteration = i == p->iters - 1;
+  r.world = p->cfg.world_size;
+  r.n_keep = (i > 0 && p->cfg.keep_previous_elites) ? p->n_keep : 0;
+  r.n_fresh_global = ip.n_global;
+  r.alpha = (float)p->cfg.alpha;
+  r.one_minus_alpha = (float)(1.0 - p->cfg.alpha);
+  if (p->cfg.world_size > 1) {
+    r.rec_keys = reinterpret_cast<const unsigned long long*>(p->recv_rec.p);
+    r.rec_rank_stride_bytes = p->rec_bytes;
+    r.local_actions = nullptr;
+  } else {
+    r.rec_keys = nullptr;   // set inside select_kernel
+    r.rec_rank_stride_bytes = 0;
+    r.local_actions = p->actions.p + ip.act_off * p->stride;
+  }
+  r.local_n_fresh = ip.n_fresh_local;
+  r.local_offset = ip.global_offset;
+  const int nb = i & 1, pb = (i > 0 ? i - 1 : p->iters - 1) & 1;
+  r.prev_elite_actions = p->elite_actions[pb].p;
+  r.prev_elite_costs = p->elite_costs[pb].p;
+  r.new_elite_actions = p->elite_actions[nb].p;
+  r.new_elite_costs = p->elite_costs[nb].p;
+  r.new_elite_idx = p->elite_idx[nb].p;
+  r.mean = p->mean.p; r.std = p->stdv.p; r.init_std = p->init_std.p;
+  r.trace_mean = p->trace_mean.p + (size_t)i * p->hd;
+  r.trace_std = p->trace_std.p + (size_t)i * p->hd;
+  r.trace_costs = p->trace_costs.p + (size_t)i * p->k;
+  r.trace_idx = p->trace_idx.p + (size_t)i * p->k;
+  r.out_action = p->out.p;
+  r.out_best_cost = p->out.p + p->d;
+  return r;
+}
+
+static int select_grid(icem_planner* p, int rows) {
+  return std::max(1, std::min(p->sm_count, (rows + 2047) / 2048));
+}
+
+// enqueue all CEM iterations of one plan step on the planner's stream
+static void enqueue_iterations(icem_planner* p, bool time_rollouts) {
+  for (int i = 0; i < p->iters; ++i) {
+    const IterPlan& ip = p->plan[i];
+    RolloutArgs a = rollout_args(p, i);
+    if (time_rollouts) ICEM_CUDA(cudaEventRecord(p->ev_roll[2 * i], p->stream));
+    launch_rollout_dyn<true, true>(p, a, ip.rows_cap);
+    if (time_rollouts) ICEM_CUDA(cudaEventRecord(p->ev_roll[2 * i + 1], p->stream));
+
+    SelectArgs s{};
+    s.n_fresh_local = ip.n_fresh_local; s.n_shift_local = ip.n_shift_local;
+    s.global_offset = ip.global_offset; s.n_fresh_global = ip.n_global; s.iteration = i;
+    s.k = p->k; s.stride = p->stride;
+    s.costs = a.costs; s.actions = a.actions; s.ss = a.ss;
+    s.cand = p->cand.p; s.ticket = p->ticket.p;
+    RefitArgs r = refit_args(p, i);
+    const size_t smem = (size_t)p->k * sizeof(unsigned long long);
+    if (p->cfg.world_size == 1) {
+      select_kernel<<<select_grid(p, ip.rows_cap), kSelectThreads, smem, p->stream>>>(s, r, 1);
+      ICEM_CUDA(cudaGetLastError());
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else {
+      s.send_keys = reinterpret_cast<unsigned long long*>(p->send_rec.p);
+      s.send_actions = reinterpret_cast<float*>(p->send_rec.p + (size_t)p->k * sizeof(unsigned long long));
+      select_kernel<<<select_grid(p, ip.rows_cap), kSelectThreads, smem, p->stream>>>(s, r, 0);
+      ICEM_CUDA(cudaGetLastError());
+      p->comm.all_gather(p->send_rec.p, p->recv_rec.p, p->rec_bytes, p->stream);
+      merge_refit_kernel<<<1, kSelectThreads, smem, p->stream>>>(r);
+      ICEM_CUDA(cudaGetLastError());
+      g_launches.fetch_add(2, std::memory_order_relaxed);
+    }
+  }
+}
+
+// state_dev <- f(state_dev, executed action): closed loop on the device
+template <class Dyn>
+__global__ void advance_kernel(typename Dyn::Params dp, float* state, const float* action, float* next_state,
+                               float* obs_out, int obs_dim) {
+  extern __shared__ __align__(128) float smem[];
+  float* s_dyn = smem;
+  float* w_dyn = s_dyn + ((Dyn::cta_floats(dp) + 3) & ~3);
+  float* s_act = w_dyn + ((Dyn::warp_floats(dp) + 3) & ~3);
+  Dyn::cta_init(dp, s_dyn);
+  for (int i = threadIdx.x; i < dp.act_dim; i += blockDim.x) s_act[i] = action[i];
+  __syncthreads();
+  Dyn dyn;
+  dyn.bind(dp, s_dyn, w_dyn);
+  dyn.reset(state);
+  if (action) dyn.step(s_act);
+  __syncwarp();
+  if (next_state) dyn.export_state(next_state);
+  if (obs_out)
+    for (int i = threadIdx.x; i < obs_dim; i += 32) obs_out[i] = dyn.obs(i);
+}
+
+template <class Dyn>
+static void launch_advance(icem_planner* p, const typename Dyn::Params& dp, float* state, const float* action,
+                           float* next_state, float* obs_out, int obs_dim) {
+  const size_t smem = (((Dyn::cta_floats(dp) + 3) & ~3) + ((Dyn::warp_floats(dp) + 3) & ~3) + dp.act_dim + 4) *
+                      sizeof(float);
+  auto kern = advance_kernel<Dyn>;
+  if (smem > 48 * 1024)
+    ICEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<1, 32, smem, p->stream>>>(dp, state, action, next_state, obs_out, obs_dim);
+  ICEM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+static void advance_dyn(icem_planner* p, float* state, const float* action, float* next_state, float* obs_out,
+                        int obs_dim) {
+  switch (p->cfg.dynamics) {
+    case ICEM_DYN_DENSE_TANH:
+      launch_advance<DenseTanh>(p, p->dense, state, action, next_state, obs_out, obs_dim);
+      break;
+    case ICEM_DYN_HALFCHEETAH:
+    case ICEM_DYN_HUMANOID_STANDUP:
+      launch_advance<Articulated>(p, p->art, state, action, next_state, obs_out, obs_dim);
+      break;
+    default:
+      throw Unsupported("dynamics id not supported by this build");
+  }
+}
+
+static void require_model(icem_planner* p) {
+  if (!p->model_ready) throw StateError("forward model parameters not set (icem_set_dense_model / ...)");
+}
+
+static void build_plan(icem_planner* p) {
+  const icem_config_t& c = p->cfg;
+  p->plan.clear();
+  int n = c.num_simulated_trajectories;
+  size_t cost_off = 0, act_off = 0;
+  int rows_max = 0;
+  for (int i = 0; i < c.opt_iterations; ++i) {
+    if (i > 0) n = std::max(c.elites_size * 2, (int)((double)n / c.factor_decrease_num));   // icem.py:126-127
+    IterPlan ip{};
+    ip.n_global = n;
+    ip.chunk = (n + c.world_size - 1) / c.world_size;
+    ip.global_offset = std::min(n, c.rank * ip.chunk);
+    ip.n_fresh_local = std::min(n, ip.global_offset + ip.chunk) - ip.global_offset;
+    // shifted elites (iteration 0, t>0) are simulated on the LAST rank at global indices N_0..
+    ip.n_shift_local = (i == 0 && c.shift_elites_over_time && c.rank == c.world_size - 1) ? p->n_keep : 0;
+    ip.rows_cap = ip.n_fresh_local + ip.n_shift_local;
+    ip.cost_off = cost_off;
+    cost_off += (size_t)ip.rows_cap;
+    ip.act_off = c.keep_iteration_actions ? act_off : 0;
+    act_off += (size_t)ip.rows_cap;
+    rows_max = std::max(rows_max, ip.rows_cap);
+    p->plan.push_back(ip);
+  }
+  p->costs.alloc(std::max<size_t>(cost_off, 1));
+  p->actions.alloc((size_t)std::max<size_t>(c.keep_iteration_actions ? act_off : (size_t)rows_max, 1) * p->stride);
+}
+
+static void reset_distribution(icem_planner* p) {
+  ICEM_CUDA(cudaMemcpyAsync(p->mean.p, p->init_mean.p, p->hd * sizeof(float), cudaMemcpyDeviceToDevice, p->stream));
+  ICEM_CUDA(cudaMemcpyAsync(p->stdv.p, p->init_std.p, p->hd * sizeof(float), cudaMemcpyDeviceToDevice, p->stream));
+}
+
+static void write_step_in(icem_planner* p, const double* state) {
+  StepState ss{};
+  ss.step = p->step;
+  ss.has_prev_elites = p->has_prev ? 1 : 0;
+  ss.inject = p->inject_pending ? 1 : 0;
+  memcpy(p->h_in, &ss, sizeof ss);
+  if (state) {
+    float* f = reinterpret_cast<float*>(p->h_in + sizeof(StepState));
+    for (int i = 0; i < p->state_dim; ++i) f[i] = (float)state[i];
+  }
+}
+
+static void ensure_graph(icem_planner* p) {
+  if (p->graph_exec) return;
+  cudaGraph_t g = nullptr;
+  ICEM_CUDA(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+  try {
+    ICEM_CUDA(cudaMemcpyAsync(p->step_in.p, p->h_in, p->in_bytes, cudaMemcpyHostToDevice, p->stream));
+    enqueue_iterations(p, false);
+    ICEM_CUDA(cudaMemcpyAsync(p->h_out, p->out.p, (p->d + 1) * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+  } catch (...) {
+    cudaStreamEndCapture(p->stream, &g);
+    if (g) cudaGraphDestroy(g);
+    throw;
+  }
+  ICEM_CUDA(cudaStreamEndCapture(p->stream, &g));
+  cudaError_t e = cudaGraphInstantiate(&p->graph_exec, g, 0);
+  cudaGraphDestroy(g);
+  ICEM_CUDA(e);
+}
+
+static void finish_step(icem_planner* p) {
+  p->step += 1;
+  p->has_prev = true;
+  if (p->inject_pending) {
+    p->inject_pending = false;
+    p->inj_zr.clear();
+    p->inj_zi.clear();
+    p->inj_rows.clear();
+  }
+}
+
+static int rows_of(icem_planner* p, int i, bool first_step) {
+  const IterPlan& ip = p->plan[i];
+  return ip.n_fresh_local + ((i == 0 && !first_step) ? ip.n_shift_local : 0);
+}
+
+}  // namespace icem
+
+// ====================================================================================================
+// C ABI
+// ====================================================================================================
+#define ICEM_API_BEGIN try {
+#define ICEM_API_END                                                         \
+  }                                                                          \
+  catch (const icem::InvalidArg& e) { icem::g_last_error = e.what(); return ICEM_ERR_INVALID; }       \
+  catch (const icem::StateError& e) { icem::g_last_error = e.what(); return ICEM_ERR_STATE; }         \
+  catch (const icem::Unsupported& e) { icem::g_last_error = e.what(); return ICEM_ERR_UNSUPPORTED; }  \
+  catch (const icem::CommError& e) { icem::g_last_error = e.what(); return ICEM_ERR_COMM; }           \
+  catch (const icem::CudaError& e) { icem::g_last_error = e.what(); return ICEM_ERR_CUDA; }           \
+  catch (const std::exception& e) { icem::g_last_error = e.what(); return ICEM_ERR_INVALID; }         \
+  return ICEM_OK;
+
+extern "C" {
+
+const char* icem_last_error(void) { return icem::g_last_error.c_str(); }
+int icem_abi_version(void) { return ICEM_ABI_VERSION; }
+uint64_t icem_kernel_launch_count(void) { return icem::g_launches.load(); }
+
+int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
+  ICEM_API_BEGIN
+  if (!cfg || !out) throw InvalidArg("null argument");
+  if (cfg->abi_version != ICEM_ABI_VERSION) throw InvalidArg("icem_config_t.abi_version mismatch");
+  if (cfg->num_simulated_trajectories < 2) throw InvalidArg("At least two trajectories needed!");   // mpc.py:30-31
+  if (cfg->horizon < 1 || cfg->act_dim < 1 || cfg->opt_iterations < 1 || cfg->elites_size < 1)
+    throw InvalidArg("horizon, act_dim, opt_iterations, elites_size must be positive");
+  if (!cfg->action_low || !cfg->action_high) throw InvalidArg("action bounds missing");
+  if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) throw InvalidArg("bad rank/world_size");
+  if (cfg->factor_decrease_num <= 0) throw InvalidArg("factor_decrease_num must be positive");
+  if (cfg->cost_along_trajectory < 0 || cfg->cost_along_trajectory > 2)
+    throw Unsupported("Implement method to compute cost along trajectory");   // abstract_controller.py:88-91
+  if (cfg->cost != ICEM_COST_HALFCHEETAH && cfg->cost != ICEM_COST_HUMANOID_STANDUP) throw Unsupported("unknown cost id");
+  int ndev = 0;
+  ICEM_CUDA(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) throw InvalidArg("CUDA device ordinal out of range");
+  ICEM_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop{};
+  ICEM_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major < 10) throw Unsupported("libicem_b200 is built for sm_100a (B200) only");
+
+  std::unique_ptr<icem_planner> p(new icem_planner);
+  p->cfg = *cfg;
+  p->sm_count = prop.multiProcessorCount;
+  p->h = cfg->horizon; p->d = cfg->act_dim; p->hd = p->h * p->d; p->K = p->h / 2 + 1;
+  p->iters = cfg->opt_iterations;
+  p->white = !(cfg->noise_beta > 0);
+  p->low.assign(cfg->action_low, cfg->action_low + p->d);
+  p->high.assign(cfg->action_high, cfg->action_high + p->d);
+  p->cfg.action_low = p->low.data();
+  p->cfg.action_high = p->high.data();
+  // icem.py:237-240 (floor of two elites)
+  p->k = std::max(2, std::min(cfg->elites_size, cfg->num_simulated_trajectories / 2));
+  if (p->k > 64) throw Unsupported("num_elites > 64 not supported");
+  // icem.py:99,145: int(len(elites) * fraction_elites_reused) -- same double arithmetic as Python
+  p->n_keep = (int)((double)p->k * cfg->fraction_elites_reused);
+  if (p->n_keep < 0 || p->n_keep > p->k) throw InvalidArg("fraction_elites_reused out of range");
+  p->stride = (p->hd + 3) & ~3;   // 16-B multiple for the 1-D TMA bulk copies
+  p->obs_dim = cfg->obs_dim;
+
+  ICEM_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  ICEM_CUDA(cudaEventCreate(&p->ev_a));
+  ICEM_CUDA(cudaEventCreate(&p->ev_b));
+  p->ev_roll.resize(2 * p->iters);
+  for (auto& e : p->ev_roll) ICEM_CUDA(cudaEventCreate(&e));
+
+  upload(p->G, p->white ? std::vector<float>(1, 0.f)
+                        : build_synthesis_matrix(p->h, cfg->noise_beta, cfg->colorednoise_v2 != 0));
+  upload(p->d_low, p->low);
+  upload(p->d_high, p->high);
+  // icem.py:48-59: the bounds are float32 (gym Box) and the reference does this arithmetic on them
+  std::vector<float> m0(p->hd), s0(p->hd);
+  for (int t = 0; t < p->h; ++t)
+    for (int j = 0; j < p->d; ++j) {
+      const float mid = (p->high[j] + p->low[j]) / 2.0f;
+      const float half = (p->high[j] - p->low[j]) / 2.0f;
+      m0[t * p->d + j] = (float)(0.0 + (double)mid);
+      s0[t * p->d + j] = (float)((double)half * cfg->init_std);
+    }
+  upload(p->init_mean, m0);
+  upload(p->init_std, s0);
+  p->mean.alloc(p->hd);
+  p->stdv.alloc(p->hd);
+  for (int b = 0; b < 2; ++b) {
+    p->elite_actions[b].alloc((size_t)p->k * p->stride);
+    p->elite_costs[b].alloc(p->k);
+    p->elite_idx[b].alloc(p->k);
+  }
+  p->trace_mean.alloc((size_t)p->iters * p->hd);
+  p->trace_std.alloc((size_t)p->iters * p->hd);
+  p->trace_costs.alloc((size_t)p->iters * p->k);
+  p->trace_idx.alloc((size_t)p->iters * p->k);
+  p->out.alloc(p->d + 1);
+  p->cand.alloc((size_t)p->sm_count * p->k);
+  p->ticket.alloc(1);
+  build_plan(p.get());
+
+  if (cfg->dynamics == ICEM_DYN_HALFCHEETAH || cfg->dynamics == ICEM_DYN_HUMANOID_STANDUP) {
+    articulated_setup(cfg->dynamics, p->d, &p->art);     // built-in model tables
+    p->state_dim = Articulated::state_dim(p->art);
+    p->model_ready = true;
+  } else if (cfg->dynamics == ICEM_DYN_DENSE_TANH) {
+    p->state_dim = 0;   // known once the model is set
+  } else {
+    throw Unsupported("dynamics id not supported by this build");
+  }
+  if (cfg->world_size > 1) {
+    p->rec_bytes = (size_t)p->k * sizeof(unsigned long long) + (size_t)p->k * p->stride * sizeof(float);
+    p->send_rec.alloc(p->rec_bytes);
+    p->recv_rec.alloc(p->rec_bytes * cfg->world_size);
+  }
+  // staging sized for the largest state we support
+  p->in_bytes = sizeof(StepState) + 256 * sizeof(float);
+  p->step_in.alloc(p->in_bytes);
+  ICEM_CUDA(cudaMallocHost(&p->h_in, p->in_bytes));
+  memset(p->h_in, 0, p->in_bytes);
+  ICEM_CUDA(cudaMallocHost(&p->h_out, (p->d + 1) * sizeof(float)));
+  ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  *out = p.release();
+  ICEM_API_END
+}
+
+int icem_destroy(icem_planner_t* p) {
+  ICEM_API_BEGIN
+  if (p) {
+    cudaSetDevice(p->cfg.device);
+    cudaStreamSynchronize(p->stream);
+    delete p;
+  }
+  ICEM_API_END
+}
+
+int icem_set_dense_model(icem_planner_t* p, int32_t obs_dim, const float* w_obs, const float* w_act,
+                         const float* bias) {
+  ICEM_API_BEGIN
+  if (!p || !w_obs || !w_act) throw InvalidArg("null argument");
+  if (p->cfg.dynamics != ICEM_DYN_DENSE_TANH) throw InvalidArg("planner was not created with ICEM_DYN_DENSE_TANH");
+  if (obs_dim < 1 || obs_dim > 256) throw InvalidArg("obs_dim out of range [1,256]");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  upload(p->w_obs, std::vector<float>(w_obs, w_obs + (size_t)obs_dim * obs_dim));
+  upload(p->w_act, std::vector<float>(w_act, w_act + (size_t)obs_dim * p->d));
+  upload(p->bias, bias ? std::vector<float>(bias, bias + obs_dim) : std::vector<float>(obs_dim, 0.f));
+  p->dense.obs_dim = obs_dim;
+  p->dense.act_dim = p->d;
+  p->dense.w_obs = p->w_obs.p;
+  p->dense.w_act = p->w_act.p;
+  p->dense.bias = p->bias.p;
+  p->state_dim = obs_dim;
+  if (p->obs_dim <= 0) p->obs_dim = obs_dim;
+  p->model_ready = true;
+  if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+  ICEM_API_END
+}
+
+int icem_set_mlp_model(icem_planner_t*, int32_t, const int32_t*, const float* const*, const float* const*) {
+  icem::g_last_error = "ICEM_DYN_MLP is not available in this build";
+  return ICEM_ERR_UNSUPPORTED;
+}
+
+int icem_begin_rollout(icem_planner_t* p) {
+  ICEM_API_BEGIN
+  if (!p) throw InvalidArg("null planner");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  reset_distribution(p);
+  ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  p->was_reset = true;
+  p->step = 0;
+  p->has_prev = false;
+  ICEM_API_END
+}
+
+int icem_plan(icem_planner_t* p, const double* state, int32_t state_dim, double* action_out) {
+  ICEM_API_BEGIN
+  if (!p || !state || !action_out) throw InvalidArg("null argument");
+  if (!p->was_reset) throw StateError("beginning_of_rollout() needs to be called before");   // icem.py:109-110
+  require_model(p);
+  if (state_dim != p->state_dim) throw InvalidArg("state_dim does not match the forward model");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  write_step_in(p, state);
+  ICEM_CUDA(cudaEventRecord(p->ev_a, p->stream));
+  if (p->inject_pending) {
+    // parity mode: direct launches (injected buffers are per-call)
+    ICEM_CUDA(cudaMemcpyAsync(p->step_in.p, p->h_in, p->in_bytes, cudaMemcpyHostToDevice, p->stream));
+    enqueue_iterations(p, false);
+    ICEM_CUDA(cudaMemcpyAsync(p->h_out, p->out.p, (p->d + 1) * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+  } else {
+    ensure_graph(p);
+    ICEM_CUDA(cudaGraphLaunch(p->graph_exec, p->stream));
+  }
+  ICEM_CUDA(cudaEventRecord(p->ev_b, p->stream));
+  ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  ICEM_CUDA(cudaEventElapsedTime(&p->last_total_ms, p->ev_a, p->ev_b));
+  p->last_rollout_ms = 0.f;
+  for (int i = 0; i < p->d; ++i) action_out[i] = (double)p->h_out[i];
+  finish_step(p);
+  ICEM_API_END
+}
+
+int icem_plan_device(icem_planner_t* p) {
+  ICEM_API_BEGIN
+  if (!p) throw InvalidArg("null planner");
+  if (!p->was_reset) throw StateError("beginning_of_rollout() needs to be called before");
+  require_model(p);
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  // only the StepState words change; the start state stays resident
+  write_step_in(p, nullptr);
+  ICEM_CUDA(cudaMemcpyAsync(p->step_in.p, p->h_in, sizeof(StepState), cudaMemcpyHostToDevice, p->stream));
+  enqueue_iterations(p, true);
+  finish_step(p);
+  ICEM_API_END
+}
+
+int icem_advance_state_device(icem_planner_t* p) {
+  ICEM_API_BEGIN
+  if (!p) throw InvalidArg("null planner");
+  require_model(p);
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  advance_dyn(p, start_state_dev(p), p->out.p, start_state_dev(p), nullptr, 0);
+  ICEM_API_END
+}
+
+int icem_sync(icem_planner_t* p) {
+  ICEM_API_BEGIN
+  if (!p) throw InvalidArg("null planner");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  ICEM_API_END
+}
+
+int icem_last_plan_ms(icem_planner_t* p, float* total_ms, float* rollout_ms) {
+  ICEM_API_BEGIN
+  if (!p) throw InvalidArg("null planner");
+  if (total_ms) *total_ms = p->last_total_ms;
+  if (rollout_ms) *rollout_ms = p->last_rollout_ms;
+  ICEM_API_END
+}
+
+int icem_inject_noise(icem_planner_t* p, int32_t iteration, int32_t rows, const float* zr, const float* zi) {
+  ICEM_API_BEGIN
+  if (!p || !zr) throw InvalidArg("null argument");
+  if (iteration < 0 || iteration >= p->iters) throw InvalidArg("iteration out of range");
+  if (!p->white && !zi) throw InvalidArg("zi required for colored noise");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  const int need = rows_of(p, iteration, !p->has_prev);
+  if (rows != need) throw InvalidArg("injected row count does not match this rank's population");
+  if (p->inj_zr.size() != (size_t)p->iters) {
+    p->inj_zr = std::vector<DevBuf<float>>(p->iters);
+    p->inj_zi = std::vector<DevBuf<float>>(p->iters);
+    p->inj_rows.assign(p->iters, 0);
+  }
+  const size_t per_row = p->white ? (size_t)p->hd : (size_t)p->d * p->K;
+  p->inj_zr[iteration].alloc(per_row * rows);
+  ICEM_CUDA(cudaMemcpy(p->inj_zr[iteration].p, zr, per_row * rows * sizeof(float), cudaMemcpyHostToDevice));
+  if (!p->white) {
+    p->inj_zi[iteration].alloc(per_row * rows);
+    ICEM_CUDA(cudaMemcpy(p->inj_zi[iteration].p, zi, per_row * rows * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  p->inj_rows[iteration] = rows;
+  bool all = true;
+  for (int i = 0; i < p->iters; ++i) all = all && p->inj_rows[i] > 0;
+  p->inject_pending = all;
+  ICEM_API_END
+}
+
+int icem_get_mean(icem_planner_t* p, float* out) {
+  ICEM_API_BEGIN
+  if (!p || !out) throw InvalidArg("null argument");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  ICEM_CUDA(cudaMemcpy(out, p->mean.p, p->hd * sizeof(float), cudaMemcpyDeviceToHost));
+  ICEM_API_END
+}
+
+int icem_get_std(icem_planner_t* p, float* out) {
+  ICEM_API_BEGIN
+  if (!p || !out) throw InvalidArg("null argument");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  ICEM_CUDA(cudaMemcpy(out, p->stdv.p, p->hd * sizeof(float), cudaMemcpyDeviceToHost));
+  ICEM_API_END
+}
+
+int icem_num_elites(icem_planner_t* p) { return p ? p->k : -1; }
+int icem_state_dim(icem_planner_t* p) { return p ? p->state_dim : -1; }
+
+int icem_get_elites(icem_planner_t* p, float* actions_out, float* costs_out, int32_t* idx_out) {
+  ICEM_API_BEGIN
+  if (!p) throw InvalidArg("null planner");
+  if (!p->has_prev) throw StateError("no elites yet (no plan step since beginning_of_rollout)");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  const int b = (p->iters - 1) & 1;
+  if (actions_out)
+    ICEM_CUDA(cudaMemcpy2D(actions_out, p->hd * sizeof(float), p->elite_actions[b].p, p->stride * sizeof(float),
+                           p->hd * sizeof(float), p->k, cudaMemcpyDeviceToHost));
+  if (costs_out) ICEM_CUDA(cudaMemcpy(costs_out, p->elite_costs[b].p, p->k * sizeof(float), cudaMemcpyDeviceToHost));
+  if (idx_out) ICEM_CUDA(cudaMemcpy(idx_out, p->elite_idx[b].p, p->k * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  ICEM_API_END
+}
+
+int icem_population_size(icem_planner_t* p, int32_t iteration, int32_t first_step, int32_t* global_out,
+                         int32_t* local_out) {
+  ICEM_API_BEGIN
+  if (!p) throw InvalidArg("null planner");
+  if (iteration < 0 || iteration >= p->iters) throw InvalidArg("iteration out of range");
+  const IterPlan& ip = p->plan[iteration];
+  const bool shift = iteration == 0 && !first_step && p->cfg.shift_elites_over_time;
+  if (global_out) *global_out = ip.n_global + (shift ? p->n_keep : 0);
+  if (local_out) *local_out = ip.n_fresh_local + (shift ? ip.n_shift_local : 0);
+  ICEM_API_END
+}
+
+int icem_get_iteration(icem_planner_t* p, int32_t i, float* mean_out, float* std_out, float* elite_costs_out,
+                       int32_t* elite_idx_out) {
+  ICEM_API_BEGIN
+  if (!p) throw InvalidArg("null planner");
+  if (i < 0 || i >= p->iters) throw InvalidArg("iteration out of range");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  if (mean_out) ICEM_CUDA(cudaMemcpy(mean_out, p->trace_mean.p + (size_t)i * p->hd, p->hd * 4, cudaMemcpyDeviceToHost));
+  if (std_out) ICEM_CUDA(cudaMemcpy(std_out, p->trace_std.p + (size_t)i * p->hd, p->hd * 4, cudaMemcpyDeviceToHost));
+  if (elite_costs_out)
+    ICEM_CUDA(cudaMemcpy(elite_costs_out, p->trace_costs.p + (size_t)i * p->k, p->k * 4, cudaMemcpyDeviceToHost));
+  if (elite_idx_out)
+    ICEM_CUDA(cudaMemcpy(elite_idx_out, p->trace_idx.p + (size_t)i * p->k, p->k * 4, cudaMemcpyDeviceToHost));
+  ICEM_API_END
+}
+
+int icem_get_costs(icem_planner_t* p, int32_t i, float* out, int32_t n) {
+  ICEM_API_BEGIN
+  if (!p || !out) throw InvalidArg("null argument");
+  if (i < 0 || i >= p->iters) throw InvalidArg("iteration out of range");
+  if (n < 0 || n > p->plan[i].rows_cap) throw InvalidArg("row count out of range");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  ICEM_CUDA(cudaMemcpy(out, p->costs.p + p->plan[i].cost_off, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  ICEM_API_END
+}
+
+int icem_get_actions(icem_planner_t* p, int32_t i, float* out, int32_t n) {
+  ICEM_API_BEGIN
+  if (!p || !out) throw InvalidArg("null argument");
+  if (i < 0 || i >= p->iters) throw InvalidArg("iteration out of range");
+  if (!p->cfg.keep_iteration_actions && i != p->iters - 1)
+    throw StateError("create the planner with keep_iteration_actions=1 to read earlier populations");
+  if (n < 0 || n > p->plan[i].rows_cap) throw InvalidArg("row count out of range");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  if (n)
+    ICEM_CUDA(cudaMemcpy2D(out, p->hd * sizeof(float), p->actions.p + p->plan[i].act_off * p->stride,
+                           p->stride * sizeof(float), p->hd * sizeof(float), n, cudaMemcpyDeviceToHost));
+  ICEM_API_END
+}
+
+int icem_sim_step(icem_planner_t* p, const double* state, int32_t state_dim, const double* action,
+                  double* next_state, double* obs_out, int32_t obs_dim, double* reward_out) {
+  ICEM_API_BEGIN
+  if (!p || !state) throw InvalidArg("null argument");
+  require_model(p);
+  if (state_dim != p->state_dim) throw InvalidArg("state_dim does not match the forward model");
+  if (obs_dim < 0 || obs_dim > 512) throw InvalidArg("obs_dim out of range");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  DevBuf<float> buf;
+  const int sd = p->state_dim;
+  buf.alloc((size_t)2 * sd + p->d + std::max(obs_dim, 1));
+  std::vector<float> h((size_t)sd + p->d);
+  for (int i = 0; i < sd; ++i) h[i] = (float)state[i];
+  if (action)
+    for (int i = 0; i < p->d; ++i) h[sd + i] = (float)action[i];
+  ICEM_CUDA(cudaMemcpyAsync(buf.p, h.data(), h.size() * 4, cudaMemcpyHostToDevice, p->stream));
+  float* d_state = buf.p;
+  float* d_act = buf.p + sd;
+  float* d_next = d_act + p->d;
+  float* d_obs = d_next + sd;
+  advance_dyn(p, d_state, action ? d_act : nullptr, d_next, obs_out ? d_obs : nullptr, obs_dim);
+  std::vector<float> r((size_t)sd + obs_dim);
+  ICEM_CUDA(cudaMemcpyAsync(r.data(), d_next, r.size() * 4, cudaMemcpyDeviceToHost, p->stream));
+  ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  if (next_state)
+    for (int i = 0; i < sd; ++i) next_state[i] = r[i];
+  if (obs_out)
+    for (int i = 0; i < obs_dim; ++i) obs_out[i] = r[sd + i];
+  if (reward_out) *reward_out = 0.0;
+  ICEM_API_END
+}
+
+int icem_observe(icem_planner_t* p, const double* state, int32_t state_dim, double* obs_out, int32_t obs_dim) {
+  return icem_sim_step(p, state, state_dim, nullptr, nullptr, obs_out, obs_dim, nullptr);
+}
+
+// ---- single operators ------------------------------------------------------------------------------
+int icem_op_sample(icem_planner_t* p, int32_t n, const float* zr, const float* zi, const float* mean,
+                   const float* std, float* actions_out) {
+  ICEM_API_BEGIN
+  if (!p || !zr || !mean || !std || !actions_out) throw InvalidArg("null argument");
+  if (!p->white && !zi) throw InvalidArg("zi required for colored noise");
+  if (n < 1) throw InvalidArg("n must be positive");
+  require_model(p);
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  const size_t per_row = p->white ? (size_t)p->hd : (size_t)p->d * p->K;
+  DevBuf<float> d_zr, d_zi, d_mean, d_std, d_act, d_cost;
+  DevBuf<unsigned char> d_ss;
+  d_zr.alloc(per_row * n);
+  ICEM_CUDA(cudaMemcpy(d_zr.p, zr, per_row * n * 4, cudaMemcpyHostToDevice));
+  if (!p->white) {
+    d_zi.alloc(per_row * n);
+    ICEM_CUDA(cudaMemcpy(d_zi.p, zi, per_row * n * 4, cudaMemcpyHostToDevice));
+  }
+  d_mean.alloc(p->hd); d_std.alloc(p->hd);
+  ICEM_CUDA(cudaMemcpy(d_mean.p, mean, p->hd * 4, cudaMemcpyHostToDevice));
+  ICEM_CUDA(cudaMemcpy(d_std.p, std, p->hd * 4, cudaMemcpyHostToDevice));
+  d_act.alloc((size_t)n * p->stride);
+  d_cost.alloc(n);
+  d_ss.alloc(sizeof(StepState) + 256 * sizeof(float));
+  StepState ss{0, 0, 1, 0};
+  ICEM_CUDA(cudaMemcpy(d_ss.p, &ss, sizeof ss, cudaMemcpyHostToDevice));
+  RolloutArgs a{};
+  a.n_fresh_local = n; a.n_fresh_global = n; a.stride = p->stride;
+  a.actions = d_act.p; a.costs = d_cost.p; a.mean = d_mean.p; a.std = d_std.p;
+  a.prev_elites = d_act.p;
+  a.start_state = reinterpret_cast<float*>(d_ss.p + sizeof(StepState));
+  a.inj_zr = d_zr.p; a.inj_zi = d_zi.p;
+  a.ss = reinterpret_cast<StepState*>(d_ss.p);
+  launch_rollout_dyn<true, false>(p, a, n);
+  ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  ICEM_CUDA(cudaMemcpy2D(actions_out, p->hd * sizeof(float), d_act.p, p->stride * sizeof(float),
+                         p->hd * sizeof(float), n, cudaMemcpyDeviceToHost));
+  ICEM_API_END
+}
+
+int icem_op_rollout_cost(icem_planner_t* p, int32_t n, const double* state, int32_t state_dim,
+                         const float* actions, float* costs_out) {
+  ICEM_API_BEGIN
+  if (!p || !state || !actions || !costs_out) throw InvalidArg("null argument");
+  if (n < 1) throw InvalidArg("n must be positive");
+  require_model(p);
+  if (state_dim != p->state_dim) throw InvalidArg("state_dim does not match the forward model");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  DevBuf<float> d_act, d_cost, d_ms;
+  DevBuf<unsigned char> d_ss;
+  d_act.alloc((size_t)n * p->stride);
+  ICEM_CUDA(cudaMemcpy2D(d_act.p, p->stride * sizeof(float), actions, p->hd * sizeof(float), p->hd * sizeof(float), n,
+                         cudaMemcpyHostToDevice));
+  d_cost.alloc(n);
+  d_ms.alloc(2 * (size_t)p->hd);
+  d_ss.alloc(sizeof(StepState) + 256 * sizeof(float));
+  std::vector<unsigned char> hs(sizeof(StepState) + 256 * sizeof(float), 0);
+  float* f = reinterpret_cast<float*>(hs.data() + sizeof(StepState));
+  for (int i = 0; i < state_dim; ++i) f[i] = (float)state[i];
+  ICEM_CUDA(cudaMemcpy(d_ss.p, hs.data(), hs.size(), cudaMemcpyHostToDevice));
+  RolloutArgs a{};
+  a.n_fresh_local = n; a.n_fresh_global = n; a.stride = p->stride;
+  a.actions = d_act.p; a.costs = d_cost.p; a.mean = d_ms.p; a.std = d_ms.p + p->hd;
+  a.prev_elites = d_act.p;
+  a.start_state = reinterpret_cast<float*>(d_ss.p + sizeof(StepState));
+  a.ss = reinterpret_cast<StepState*>(d_ss.p);
+  launch_rollout_dyn<false, true>(p, a, n);
+  ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  ICEM_CUDA(cudaMemcpy(costs_out, d_cost.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  ICEM_API_END
+}
+
+int icem_op_topk(icem_planner_t* p, int32_t n, const float* costs, int32_t k, int32_t* idx_out, float* costs_out) {
+  ICEM_API_BEGIN
+  if (!p || !costs || !idx_out || !costs_out) throw InvalidArg("null argument");
+  if (n < 1 || k < 1 || k > 64 || k > n) throw InvalidArg("need 1 <= k <= min(n, 64)");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  DevBuf<float> d_cost, d_co;
+  DevBuf<int32_t> d_idx;
+  DevBuf<unsigned long long> d_cand, d_send;
+  DevBuf<unsigned int> d_ticket;
+  DevBuf<unsigned char> d_ss;
+  DevBuf<float> d_dummy;
+  d_cost.alloc(n);
+  ICEM_CUDA(cudaMemcpy(d_cost.p, costs, (size_t)n * 4, cudaMemcpyHostToDevice));
+  d_co.alloc(k); d_idx.alloc(k);
+  d_cand.alloc((size_t)p->sm_count * k);
+  d_send.alloc(k);
+  d_ticket.alloc(1);
+  d_ss.alloc(sizeof(StepState));
+  d_dummy.alloc(4);
+  SelectArgs s{};
+  s.n_fresh_local = n; s.n_fresh_global = n; s.k = k; s.stride = 0;
+  s.costs = d_cost.p; s.actions = d_dummy.p; s.ss = reinterpret_cast<StepState*>(d_ss.p);
+  s.cand = d_cand.p; s.ticket = d_ticket.p; s.send_keys = d_send.p; s.send_actions = d_dummy.p;
+  RefitArgs r{};
+  select_kernel<<<select_grid(p, n), kSelectThreads, (size_t)k * sizeof(unsigned long long), p->stream>>>(s, r, 0);
+  ICEM_CUDA(cudaGetLastError());
+  topk_finish_kernel<<<1, kSelectThreads, 0, p->stream>>>(d_send.p, k, d_cost.p, d_idx.p, d_co.p);
+  ICEM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  ICEM_CUDA(cudaMemcpy(idx_out, d_idx.p, k * 4, cudaMemcpyDeviceToHost));
+  ICEM_CUDA(cudaMemcpy(costs_out, d_co.p, k * 4, cudaMemcpyDeviceToHost));
+  ICEM_API_END
+}
+
+// ---- multi-GPU -------------------------------------------------------------------------------------
+int icem_comm_get_unique_id(char id_out[ICEM_UNIQUE_ID_BYTES]) {
+  ICEM_API_BEGIN
+  if (!id_out) throw InvalidArg("null argument");
+  Comm::unique_id(id_out);
+  ICEM_API_END
+}
+
+int icem_comm_init(icem_planner_t* p, const char id[ICEM_UNIQUE_ID_BYTES]) {
+  ICEM_API_BEGIN
+  if (!p || !id) throw InvalidArg("null argument");
+  if (p->cfg.world_size < 2) throw InvalidArg("planner was created with world_size 1");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  p->comm.init(id, p->cfg.world_size, p->cfg.rank);
+  ICEM_API_END
+}
+
+// ---- bench -----------------------------------------------------------------------------------------
+int icem_bench_device(icem_planner_t* p, int32_t steps, int32_t warmup, int32_t flush_l2, float* total_ms,
+                      float* rollout_ms, int32_t* rollout_launches) {
+  ICEM_API_BEGIN
+  if (!p) throw InvalidArg("null planner");
+  if (!p->was_reset) throw StateError("beginning_of_rollout() needs to be called before");
+  require_model(p);
+  if (p->cfg.world_size > 1 && !p->comm.ready()) throw StateError("icem_comm_init not called");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  const size_t flush_bytes = 256u << 20;   // > 126 MB L2
+  if (flush_l2 && p->flush.n != flush_bytes) p->flush.alloc(flush_bytes);
+  double tot = 0, roll = 0;
+  int launches = 0;
+  for (int s = 0; s < warmup + steps; ++s) {
+    if (flush_l2) ICEM_CUDA(cudaMemsetAsync(p->flush.p, s & 0xff, flush_bytes, p->stream));
+    ICEM_CUDA(cudaEventRecord(p->ev_a, p->stream));
+    write_step_in(p, nullptr);
+    ICEM_CUDA(cudaMemcpyAsync(p->step_in.p, p->h_in, sizeof(StepState), cudaMemcpyHostToDevice, p->stream));
+    enqueue_iterations(p, true);
+    advance_dyn(p, start_state_dev(p), p->out.p, start_state_dev(p), nullptr, 0);
+    ICEM_CUDA(cudaEventRecord(p->ev_b, p->stream));
+    ICEM_CUDA(cudaStreamSynchronize(p->stream));   // h_in is rewritten next step
+    finish_step(p);
+    if (s >= warmup) {
+      float ms = 0;
+      ICEM_CUDA(cudaEventElapsedTime(&ms, p->ev_a, p->ev_b));
+      tot += ms;
+      for (int i = 0; i < p->iters; ++i) {
+        ICEM_CUDA(cudaEventElapsedTime(&ms, p->ev_roll[2 * i], p->ev_roll[2 * i + 1]));
+        roll += ms;
+        ++launches;
+      }
+    }
+  }
+  if (total_ms) *total_ms = (float)tot;
+  if (rollout_ms) *rollout_ms = (float)roll;
+  if (rollout_launches) *rollout_launches = launches;
+  ICEM_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,279 @@
+// Fused sample -> rollout -> cost kernel (one warp per candidate trajectory, persistent CTAs).
+//
+// Replaces, for one CEM iteration (paths relative to /root/reference/icem/):
+//   controllers/icem.py:61-104   colored-noise sampling, clip, mean injection, shifted elites
+//   controllers/mpc.py:56-67     simulate_trajectories -> forward_model.predict_n_steps
+//   controllers/abstract_controller.py:74-91  trajectory_cost_fn (sum / best / final)
+//
+// Data movement: each warp builds its trajectory's action tile [h][d] in shared memory, rolls the
+// forward model out of it in place, and ships the tile to HBM with ONE 1-D TMA bulk store
+// (cp.async.bulk.global.shared::cta) that overlaps the rollout.  The `kSample == false` variant
+// pulls given action tiles from HBM with TMA bulk loads (mbarrier complete_tx), double-buffered.
+#pragma once
+#include "common.cuh"
+
+namespace icem {
+
+// dynamic, per-plan-step values; lives in device memory so one CUDA graph serves every step
+struct StepState {
+  uint32_t step;            // plan-step counter since beginning_of_rollout (Philox counter word)
+  int32_t has_prev_elites;  // elite_samples non-empty -> shifted elites join iteration 0
+  int32_t inject;           // parity mode: read unit normals from HBM instead of Philox
+  int32_t pad;
+};
+
+struct SamplerConst {
+  int h, d, K;          // horizon, action dim, rFFT bins (h/2+1)
+  int white;            // noise_beta == 0: iid normal, z laid out [row][h][d]
+  const float* G;       // [h][2K] synthesis matrix (colored): y[t] = sum_j G[t][j] * z[j], z = [zr(K), zi(K)]
+  const float* low;     // [d]
+  const float* high;    // [d]
+};
+
+struct CostConst {
+  int kind;             // ICEM_COST_*
+  int reduce;           // ICEM_REDUCE_*
+  int idx_a, idx_b;     // cheetah: (root angle, x velocity) observation indices; humanoid: (root z, -)
+  int penalise_flipping;
+};
+
+struct RolloutArgs {
+  int n_fresh_local;        // fresh rows this rank samples
+  int n_shift_local;        // shifted-elite rows this rank simulates when StepState.has_prev_elites (iteration 0)
+  int global_offset;        // global trajectory index of local row 0
+  int n_fresh_global;       // N_i: global index of the first shifted-elite row
+  int iteration;
+  int inject_mean_row0;     // last iteration && use_mean_actions: global row 0 <- mean (icem.py:87-88)
+  int stride;               // floats per trajectory row in `actions` (16-B multiple)
+  float* actions;           // [rows][stride]
+  float* costs;             // [rows]
+  const float* mean;        // [h*d]
+  const float* std;         // [h*d]
+  const float* prev_elites; // [k][stride] elites of the previous plan step, best first
+  const float* start_state; // [state_dim] fp32
+  const float* inj_zr;      // parity mode draws for this iteration (device), rows as in icem_inject_noise
+  const float* inj_zi;
+  const StepState* ss;
+  uint32_t seed_lo, seed_hi;
+};
+
+// ---------------------------------------------------------------------------------------------
+// cost of one step on the PRE-action observation
+template <class Dyn>
+__device__ __forceinline__ float step_cost(const CostConst& cc, const Dyn& dyn, const float* act, int d) {
+  float a2 = 0.f;
+  for (int m = 0; m < d; ++m) a2 = fmaf(act[m], act[m], a2);   // smem broadcast reads, all lanes redundantly
+  if (cc.kind == 0) {   // environments/mujoco.py:67-99
+    const float ang = dyn.obs(cc.idx_a), vel = dyn.obs(cc.idx_b);
+    float c = 0.f;
+    if (cc.penalise_flipping) {
+      c += (ang > 1.5707963267948966f) ? 10.f : 0.f;
+      c += (ang < -1.5707963267948966f) ? 10.f : 0.f;
+    }
+    return c + 0.1f * a2 - vel;
+  }
+  // environments/mujoco.py:259-277
+  return -dyn.obs(cc.idx_a) + 0.1f * a2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// unit normals for one trajectory row -> z[dim][j] (colored, row stride zs) or straight into the
+// tile (white).  Philox counter = (global row, block, step, iteration); key = seed.
+__device__ __forceinline__ void fill_normals(float* dst, int count, uint32_t grow, const RolloutArgs& a,
+                                             uint32_t step, int K2, int zs, bool white) {
+  const int lane = lane_id();
+  for (int b = lane; b * 4 < count; b += 32) {
+    Philox4 r = philox4x32_10(grow, (uint32_t)b, step, (uint32_t)a.iteration, a.seed_lo, a.seed_hi);
+    float n[4];
+    box_muller(r.x, r.y, n[0], n[1]);
+    box_muller(r.z, r.w, n[2], n[3]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = b * 4 + q;
+      if (c < count) {
+        if (white) {
+          dst[c] = n[q];
+        } else {           // c = part*(d*K) + dim*K + k  ->  z[dim][part*K + k]
+          const int K = K2 >> 1;
+          const int dk = count >> 1;            // d*K
+          const int part = c >= dk;
+          const int r2 = c - part * dk;
+          const int dim = r2 / K;
+          const int k = r2 - dim * K;
+          dst[dim * zs + part * K + k] = n[q];
+        }
+      }
+    }
+  }
+}
+
+template <class Dyn, bool kSample, bool kRollout>
+__global__ void __launch_bounds__(256)
+rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Params dp) {
+  extern __shared__ __align__(128) float smem[];
+  const int warps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int h = sc.h, d = sc.d, hd = h * d;
+  const int K2 = 2 * sc.K;
+  const int gs = K2 + 1;               // padded row strides (bank-conflict-free)
+  const int zs = K2 + 1;
+
+  // ---- CTA-shared constants ----
+  float* s_G = smem;                                   // [h][gs]
+  float* s_mean = s_G + ((h * gs + 3) & ~3);           // [hd]
+  float* s_std = s_mean + ((hd + 3) & ~3);             // [hd]
+  float* s_low = s_std + ((hd + 3) & ~3);              // [d]
+  float* s_high = s_low + ((d + 3) & ~3);              // [d]
+  float* s_dyn = s_high + ((d + 3) & ~3);              // Dyn CTA constants
+  float* s_warp0 = s_dyn + ((Dyn::cta_floats(dp) + 3) & ~3);
+  // ---- per-warp ----
+  const int tile_floats = a.stride;                    // 16-B multiple
+  const int z_floats = kSample ? ((sc.white ? 0 : d * zs) + 3) & ~3 : 0;
+  const int ntile = kSample ? 1 : 2;                   // loads are double-buffered
+  const int warp_floats = ntile * tile_floats + z_floats + ((Dyn::warp_floats(dp) + 3) & ~3) + 4;
+  float* w_base = s_warp0 + (size_t)warp * warp_floats;
+  float* w_tile = w_base;
+  float* w_z = w_tile + ntile * tile_floats;
+  float* w_dyn = w_z + z_floats;
+  uint64_t* w_bar = reinterpret_cast<uint64_t*>(w_dyn + ((Dyn::warp_floats(dp) + 3) & ~3));   // 2 x 8 B
+
+  if (kSample && !sc.white)
+    for (int i = threadIdx.x; i < h * K2; i += blockDim.x) s_G[(i / K2) * gs + (i % K2)] = sc.G[i];
+  for (int i = threadIdx.x; i < hd; i += blockDim.x) {
+    s_mean[i] = a.mean[i];
+    s_std[i] = a.std[i];
+  }
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    s_low[i] = sc.low[i];
+    s_high[i] = sc.high[i];
+  }
+  Dyn::cta_init(dp, s_dyn);
+  if (!kSample && lane == 0) {
+    mbar_init(&w_bar[0], 1);
+    mbar_init(&w_bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const StepState ss = *a.ss;
+  const int n_rows = a.n_fresh_local + ((a.iteration == 0 && ss.has_prev_elites) ? a.n_shift_local : 0);
+  const int warp_global = blockIdx.x * warps + warp;
+  const int warp_stride = gridDim.x * warps;
+  const uint32_t tile_bytes = (uint32_t)tile_floats * 4u;
+  Dyn dyn;
+  dyn.bind(dp, s_dyn, w_dyn);
+
+  if (!kSample) {   // prologue of the TMA load pipeline
+    if (warp_global < n_rows && lane == 0) {
+      mbar_expect_tx(&w_bar[0], tile_bytes);
+      tma_load_1d(w_tile, a.actions + (size_t)warp_global * a.stride, tile_bytes, &w_bar[0]);
+    }
+  }
+
+  int it = 0;
+  for (int row = warp_global; row < n_rows; row += warp_stride, ++it) {
+    float* tile = w_tile;
+    if (kSample) {
+      const bool shifted = row >= a.n_fresh_local;
+      // global trajectory index: fresh rows are contiguous per rank, shifted rows follow N_i
+      const uint32_t grow = shifted ? (uint32_t)(a.n_fresh_global + (row - a.n_fresh_local))
+                                    : (uint32_t)(a.global_offset + row);
+      // the previous trajectory's bulk store must have finished READING the tile
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+      // ---- 1. unit normals ----
+      float* zdst = sc.white ? tile : w_z;
+      const int count = sc.white ? hd : d * K2;
+      if (ss.inject) {
+        if (sc.white) {
+          const float* src = a.inj_zr + (size_t)row * hd;
+          for (int i = lane; i < hd; i += 32) tile[i] = src[i];
+        } else {
+          const int dK = d * sc.K;
+          const float* sr = a.inj_zr + (size_t)row * dK;
+          const float* si = a.inj_zi + (size_t)row * dK;
+          for (int i = lane; i < dK; i += 32) {
+            const int dim = i / sc.K, k = i - dim * sc.K;
+            w_z[dim * zs + k] = sr[i];
+            w_z[dim * zs + sc.K + k] = si[i];
+          }
+        }
+      } else {
+        fill_normals(zdst, count, grow, a, ss.step, K2, zs, sc.white);
+      }
+      __syncwarp();
+      // ---- 2. synthesis + affine + clip (icem.py:73-79), elite shift (icem.py:91-104), mean row ----
+      const bool mean_row = a.inject_mean_row0 && grow == 0u && !shifted;
+      const float* elite = shifted ? a.prev_elites + (size_t)(row - a.n_fresh_local) * a.stride : nullptr;
+      for (int o = lane; o < hd; o += 32) {
+        const int t = o / d, dim = o - t * d;
+        float y;
+        if (sc.white) {
+          y = tile[o];
+        } else {
+          const float* g = s_G + t * gs;
+          const float* z = w_z + dim * zs;
+          float acc = 0.f;
+#pragma unroll 8
+          for (int j = 0; j < K2; ++j) acc = fmaf(g[j], z[j], acc);
+          y = acc;
+        }
+        float v = fminf(fmaxf(fmaf(y, s_std[o], s_mean[o]), s_low[dim]), s_high[dim]);
+        if (mean_row) v = s_mean[o];
+        if (shifted && t < h - 1) v = elite[o + d];
+        tile[o] = v;
+      }
+      for (int o = hd + lane; o < tile_floats; o += 32) tile[o] = 0.f;   // row padding
+      __syncwarp();
+      // ---- 3. ship the tile: one TMA bulk store, overlapped with the rollout ----
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_1d(a.actions + (size_t)row * a.stride, tile, tile_bytes);
+        tma_store_commit();
+      }
+    } else {
+      // consume buffer (it&1); prefetch the next row into the other buffer
+      const int buf = it & 1;
+      tile = w_tile + buf * tile_floats;
+      const int nxt = row + warp_stride;
+      if (nxt < n_rows && lane == 0) {
+        mbar_expect_tx(&w_bar[buf ^ 1], tile_bytes);
+        tma_load_1d(w_tile + (buf ^ 1) * tile_floats, a.actions + (size_t)nxt * a.stride, tile_bytes,
+                    &w_bar[buf ^ 1]);
+      }
+      mbar_wait(&w_bar[buf], (uint32_t)((it >> 1) & 1));
+    }
+
+    if (kRollout) {
+      // ---- 4. open-loop rollout from the shared start state, cost on the pre-action observation ----
+      dyn.reset(a.start_state);
+      float total = (cc.reduce == 1) ? INFINITY : 0.f;
+      for (int t = 0; t < h; ++t) {
+        const float* act = tile + t * d;
+        const float c = step_cost(cc, dyn, act, d);
+        if (cc.reduce == 0) total += c;
+        else if (cc.reduce == 1) total = fminf(total, c);
+        else total = c;
+        if (t + 1 < h) dyn.step(act);      // the final predicted state is never scored (F9)
+      }
+      if (lane == 0) a.costs[row] = total;
+    }
+    __syncwarp();
+  }
+  if (kSample && lane == 0) tma_store_wait_all();
+}
+
+// shared-memory footprint of rollout_kernel for `warps` warps per CTA
+template <class Dyn, bool kSample>
+inline size_t rollout_smem_bytes(const SamplerConst& sc, const typename Dyn::Params& dp, int stride, int warps) {
+  const int h = sc.h, d = sc.d, hd = h * d, K2 = 2 * sc.K, gs = K2 + 1;
+  size_t f = ((h * gs + 3) & ~3) + 2 * ((hd + 3) & ~3) + 2 * ((d + 3) & ~3) + ((Dyn::cta_floats(dp) + 3) & ~3);
+  const int z_floats = kSample ? ((sc.white ? 0 : d * gs) + 3) & ~3 : 0;
+  const int ntile = kSample ? 1 : 2;
+  const size_t warp_floats = (size_t)ntile * stride + z_floats + ((Dyn::warp_floats(dp) + 3) & ~3) + 4;
+  return (f + warps * warp_floats) * sizeof(float);
+}
+
+}  // namespace icem

@@ -1,0 +1,232 @@
+"""Object wrapper over one `icem_planner_t` handle (include/icem_b200.h).  Host buffers are NumPy."""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import IcemError, check, dptr, f32, f64, fptr, iptr  # noqa: F401
+
+
+@dataclass
+class PlannerSettings:
+    """Flattened keyword surface of MpcICem (reference: controllers/icem.py:22,213-233;
+    controllers/mpc.py:22; controllers/abstract_controller.py:64-65)."""
+    horizon: int
+    num_simulated_trajectories: int
+    action_low: np.ndarray
+    action_high: np.ndarray
+    dynamics: str = "dense_tanh"
+    cost: str = "halfcheetah"
+    obs_dim: int = 0
+    penalise_flipping: bool = True
+    factor_decrease_num: float = 1.0
+    cost_along_trajectory: str = "sum"
+    alpha: float = 0.1
+    elites_size: int = 10
+    opt_iterations: int = 3
+    init_std: float = 0.5
+    use_mean_actions: bool = True
+    keep_previous_elites: bool = True
+    shift_elites_over_time: bool = True
+    fraction_elites_reused: float = 0.3
+    noise_beta: float = 1.0
+    seed: int = 0
+    device: int = 0
+    world_size: int = 1
+    rank: int = 0
+    colorednoise_v2: bool = False
+    keep_iteration_actions: bool = False
+
+
+class Planner:
+    def __init__(self, s: PlannerSettings):
+        lib = _lib.load()
+        self._lib = lib
+        self.settings = s
+        self._low = f32(s.action_low)
+        self._high = f32(s.action_high)
+        if self._low.ndim != 1 or self._low.shape != self._high.shape:
+            raise ValueError("action bounds must be 1-D arrays of equal length")
+        if s.cost_along_trajectory not in _lib.REDUCE:   # abstract_controller.py:88-91
+            raise NotImplementedError(
+                "Implement method {} to compute cost along trajectory".format(s.cost_along_trajectory))
+        self.h, self.d = int(s.horizon), int(self._low.shape[0])
+        cfg = _lib.IcemConfig(
+            abi_version=_lib.ICEM_ABI_VERSION, device=s.device, horizon=self.h, act_dim=self.d,
+            num_simulated_trajectories=int(s.num_simulated_trajectories), opt_iterations=int(s.opt_iterations),
+            elites_size=int(s.elites_size), use_mean_actions=int(bool(s.use_mean_actions)),
+            keep_previous_elites=int(bool(s.keep_previous_elites)),
+            shift_elites_over_time=int(bool(s.shift_elites_over_time)),
+            cost_along_trajectory=_lib.REDUCE[s.cost_along_trajectory], dynamics=_lib.DYN[s.dynamics],
+            cost=_lib.COST[s.cost], cost_penalise_flipping=int(bool(s.penalise_flipping)), obs_dim=int(s.obs_dim),
+            colorednoise_v2=int(bool(s.colorednoise_v2)), keep_iteration_actions=int(bool(s.keep_iteration_actions)),
+            world_size=int(s.world_size), rank=int(s.rank),
+            factor_decrease_num=float(s.factor_decrease_num), alpha=float(s.alpha), init_std=float(s.init_std),
+            fraction_elites_reused=float(s.fraction_elites_reused), noise_beta=float(s.noise_beta),
+            seed=int(s.seed) & (2 ** 64 - 1), action_low=fptr(self._low), action_high=fptr(self._high))
+        self._h = C.c_void_p()
+        check(lib.icem_create(C.byref(cfg), C.byref(self._h)))
+        self.k = lib.icem_num_elites(self._h)
+        self.iters = int(s.opt_iterations)
+        self.K = self.h // 2 + 1
+
+    # ---- lifetime -----------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.icem_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- model --------------------------------------------------------------------------------
+    def set_dense_model(self, w_obs, w_act, bias=None):
+        w_obs, w_act = f32(w_obs), f32(w_act)
+        n = w_obs.shape[0]
+        if w_obs.shape != (n, n) or w_act.shape != (n, self.d):
+            raise ValueError("dense model shapes must be [n,n] and [n,d]")
+        b = f32(bias) if bias is not None else None
+        check(self._lib.icem_set_dense_model(self._h, n, fptr(w_obs), fptr(w_act), fptr(b) if b is not None else None))
+
+    @property
+    def state_dim(self):
+        return self._lib.icem_state_dim(self._h)
+
+    # ---- plan step ----------------------------------------------------------------------------
+    def begin_rollout(self):
+        check(self._lib.icem_begin_rollout(self._h))
+
+    def plan(self, state) -> np.ndarray:
+        st = f64(state).ravel()
+        out = np.empty(self.d, dtype=np.float64)
+        check(self._lib.icem_plan(self._h, dptr(st), st.shape[0], dptr(out)))
+        return out
+
+    def plan_device(self):
+        check(self._lib.icem_plan_device(self._h))
+
+    def advance_state_device(self):
+        check(self._lib.icem_advance_state_device(self._h))
+
+    def sync(self):
+        check(self._lib.icem_sync(self._h))
+
+    def last_plan_ms(self):
+        a, b = C.c_float(), C.c_float()
+        check(self._lib.icem_last_plan_ms(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def inject_noise(self, iteration, zr, zi=None):
+        zr = f32(zr)
+        zi_ = f32(zi) if zi is not None else None
+        check(self._lib.icem_inject_noise(self._h, iteration, zr.shape[0], fptr(zr),
+                                          fptr(zi_) if zi_ is not None else None))
+
+    # ---- observable state ---------------------------------------------------------------------
+    def mean(self):
+        out = np.empty((self.h, self.d), dtype=np.float32)
+        check(self._lib.icem_get_mean(self._h, fptr(out)))
+        return out
+
+    def std(self):
+        out = np.empty((self.h, self.d), dtype=np.float32)
+        check(self._lib.icem_get_std(self._h, fptr(out)))
+        return out
+
+    def elites(self):
+        a = np.empty((self.k, self.h, self.d), dtype=np.float32)
+        c = np.empty(self.k, dtype=np.float32)
+        i = np.empty(self.k, dtype=np.int32)
+        check(self._lib.icem_get_elites(self._h, fptr(a), fptr(c), iptr(i)))
+        return a, c, i
+
+    def population_size(self, iteration, first_step):
+        g, l = C.c_int32(), C.c_int32()
+        check(self._lib.icem_population_size(self._h, iteration, int(bool(first_step)), C.byref(g), C.byref(l)))
+        return g.value, l.value
+
+    def iteration_record(self, iteration):
+        m = np.empty((self.h, self.d), dtype=np.float32)
+        s = np.empty((self.h, self.d), dtype=np.float32)
+        c = np.empty(self.k, dtype=np.float32)
+        i = np.empty(self.k, dtype=np.int32)
+        check(self._lib.icem_get_iteration(self._h, iteration, fptr(m), fptr(s), fptr(c), iptr(i)))
+        return dict(mean=m, std=s, elite_costs=c, elite_idx=i)
+
+    def costs(self, iteration, n):
+        out = np.empty(n, dtype=np.float32)
+        check(self._lib.icem_get_costs(self._h, iteration, fptr(out), n))
+        return out
+
+    def actions(self, iteration, n):
+        out = np.empty((n, self.h, self.d), dtype=np.float32)
+        check(self._lib.icem_get_actions(self._h, iteration, fptr(out), n))
+        return out
+
+    # ---- device model -------------------------------------------------------------------------
+    def sim_step(self, state, action, obs_dim=0):
+        st, ac = f64(state).ravel(), f64(action).ravel()
+        nxt = np.empty(st.shape[0], dtype=np.float64)
+        obs = np.empty(max(obs_dim, 1), dtype=np.float64)
+        rew = C.c_double()
+        check(self._lib.icem_sim_step(self._h, dptr(st), st.shape[0], dptr(ac), dptr(nxt),
+                                      dptr(obs) if obs_dim else None, obs_dim, C.byref(rew)))
+        return nxt, (obs[:obs_dim] if obs_dim else None), rew.value
+
+    def observe(self, state, obs_dim):
+        st = f64(state).ravel()
+        obs = np.empty(obs_dim, dtype=np.float64)
+        check(self._lib.icem_observe(self._h, dptr(st), st.shape[0], dptr(obs), obs_dim))
+        return obs
+
+    # ---- single operators ---------------------------------------------------------------------
+    def op_sample(self, zr, zi, mean, std):
+        zr = f32(zr)
+        zi_ = f32(zi) if zi is not None else None
+        n = zr.shape[0]
+        out = np.empty((n, self.h, self.d), dtype=np.float32)
+        check(self._lib.icem_op_sample(self._h, n, fptr(zr), fptr(zi_) if zi_ is not None else None,
+                                       fptr(f32(mean)), fptr(f32(std)), fptr(out)))
+        return out
+
+    def op_rollout_cost(self, state, actions):
+        st, a = f64(state).ravel(), f32(actions)
+        n = a.shape[0]
+        out = np.empty(n, dtype=np.float32)
+        check(self._lib.icem_op_rollout_cost(self._h, n, dptr(st), st.shape[0], fptr(a), fptr(out)))
+        return out
+
+    def op_topk(self, costs, k):
+        c = f32(costs).ravel()
+        idx = np.empty(k, dtype=np.int32)
+        val = np.empty(k, dtype=np.float32)
+        check(self._lib.icem_op_topk(self._h, c.shape[0], fptr(c), k, iptr(idx), fptr(val)))
+        return idx, val
+
+    # ---- multi-GPU ----------------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(_lib.UNIQUE_ID_BYTES)
+        check(_lib.load().icem_comm_get_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes):
+        if len(unique_id) != _lib.UNIQUE_ID_BYTES:
+            raise ValueError("unique id must be 128 bytes")
+        check(self._lib.icem_comm_init(self._h, C.create_string_buffer(unique_id, _lib.UNIQUE_ID_BYTES)))
+
+    # ---- bench --------------------------------------------------------------------------------
+    def bench_device(self, steps, warmup, flush_l2=True):
+        tot, roll, n = C.c_float(), C.c_float(), C.c_int32()
+        check(self._lib.icem_bench_device(self._h, steps, warmup, int(bool(flush_l2)), C.byref(tot), C.byref(roll),
+                                          C.byref(n)))
+        return tot.value, roll.value, n.value
+
+
+def kernel_launch_count() -> int:
+    return int(_lib.load().icem_kernel_launch_count())

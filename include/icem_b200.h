@@ -1,0 +1,173 @@
+/*
+ * icem_b200 -- C ABI of the B200-native iCEM planner (libicem_b200.so).
+ *
+ * The reference (martius-lab/iCEM) has no FFI: its drop-in boundary is the Python `Controller`
+ * plugin API (`beginning_of_rollout` / `get_action`, icem/misc/base_types.py:42-59,
+ * icem/controllers/abstract_controller.py:43-58).  `icem_b200/controller.py::MpcICemB200` is the
+ * thin Python class that mirrors that API and forwards to the entry points below through ctypes;
+ * INTEGRATION.md shows the binding.  Every entry point cites the reference interface it replaces
+ * (paths relative to /root/reference/icem/).
+ *
+ * Conventions: plain pointers and sizes, no torch types; all functions return 0 on success and a
+ * non-zero code on failure, with a thread-local message available from icem_last_error();
+ * all `float*`/`double*`/`int32_t*` arguments are HOST pointers unless the name ends in `_dev`.
+ */
+#ifndef ICEM_B200_H
+#define ICEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICEM_ABI_VERSION 1
+
+/* status codes */
+enum { ICEM_OK = 0, ICEM_ERR_INVALID = 1, ICEM_ERR_CUDA = 2, ICEM_ERR_STATE = 3, ICEM_ERR_UNSUPPORTED = 4,
+       ICEM_ERR_COMM = 5 };
+
+/* forward models (what `forward_model.predict_n_steps` runs, controllers/mpc.py:56-67) */
+enum {
+  ICEM_DYN_DENSE_TANH = 0,       /* obs' = tanh(W_o obs + W_a act + b): single dense layer batched model
+                                    (models/abstract_models.py:17-53 with a dense `predict`) */
+  ICEM_DYN_HALFCHEETAH = 1,      /* ground-truth planar articulated body (stands in for gym HalfCheetah-v3) */
+  ICEM_DYN_HUMANOID_STANDUP = 2, /* ground-truth 3-D articulated body (stands in for gym HumanoidStandup-v2) */
+  ICEM_DYN_MLP = 3               /* dense MLP forward model (tensor-core rollout) */
+};
+
+/* per-step cost functions (env.cost_fn, controllers/abstract_controller.py:70,78-80) */
+enum {
+  ICEM_COST_HALFCHEETAH = 0,     /* environments/mujoco.py:67-99  */
+  ICEM_COST_HUMANOID_STANDUP = 1 /* environments/mujoco.py:259-277 */
+};
+
+/* cost_along_trajectory (controllers/abstract_controller.py:82-91) */
+enum { ICEM_REDUCE_SUM = 0, ICEM_REDUCE_BEST = 1, ICEM_REDUCE_FINAL = 2 };
+
+/* Keyword surface of MpcICem (controllers/icem.py:22,213-233; controllers/mpc.py:22;
+ * controllers/abstract_controller.py:64-65) plus what the env contributes. */
+typedef struct icem_config {
+  int32_t abi_version;            /* = ICEM_ABI_VERSION */
+  int32_t device;                 /* CUDA device ordinal */
+  int32_t horizon;                /* h */
+  int32_t act_dim;                /* d = env.action_space.shape[0] */
+  int32_t num_simulated_trajectories; /* N (GLOBAL population of iteration 0) */
+  int32_t opt_iterations;
+  int32_t elites_size;
+  int32_t use_mean_actions;
+  int32_t keep_previous_elites;
+  int32_t shift_elites_over_time;
+  int32_t cost_along_trajectory;  /* ICEM_REDUCE_* */
+  int32_t dynamics;               /* ICEM_DYN_* */
+  int32_t cost;                   /* ICEM_COST_* */
+  int32_t cost_penalise_flipping; /* HalfCheetah env_params.penalise_flipping */
+  int32_t obs_dim;                /* observation width the cost reads (17/18 cheetah; >=3 humanoid) */
+  int32_t colorednoise_v2;        /* 0: colorednoise 1.x spectrum (default); 1: 2.x sqrt(2) DC/Nyquist scaling */
+  int32_t keep_iteration_actions; /* debug/parity: keep every iteration's population for icem_get_actions */
+  int32_t world_size;             /* number of ranks sharing one plan (1 = single GPU) */
+  int32_t rank;
+  double factor_decrease_num;     /* gamma */
+  double alpha;
+  double init_std;
+  double fraction_elites_reused;
+  double noise_beta;
+  uint64_t seed;                  /* Philox key (production noise) */
+  const float* action_low;        /* [d] env.action_space.low  (float32 like gym.spaces.Box) */
+  const float* action_high;       /* [d] */
+} icem_config_t;
+
+typedef struct icem_planner icem_planner_t;
+
+const char* icem_last_error(void);
+int icem_abi_version(void);
+/* number of kernels of this library launched by the calling process so far (bench `gpu_launches`) */
+uint64_t icem_kernel_launch_count(void);
+
+/* ---- planner lifetime: MpcICem.__init__ (controllers/icem.py:22-29, :235-247) ------------------------- */
+int icem_create(const icem_config_t* cfg, icem_planner_t** out);
+int icem_destroy(icem_planner_t* p);
+
+/* ---- forward-model parameters (the object `main.py:105-109` builds and hands to the controller) -------- */
+/* ICEM_DYN_DENSE_TANH: w_obs[obs_dim*obs_dim] row-major, w_act[obs_dim*act_dim], bias[obs_dim] (may be NULL) */
+int icem_set_dense_model(icem_planner_t* p, int32_t obs_dim, const float* w_obs, const float* w_act,
+                         const float* bias);
+/* ICEM_DYN_MLP: n_layers dense layers, layer l: weight[out_l*in_l] row-major + bias[out_l]; tanh between
+ * layers, last layer linear, output = next observation delta (obs' = obs + mlp([obs, act])) */
+int icem_set_mlp_model(icem_planner_t* p, int32_t n_layers, const int32_t* layer_dims /* n_layers+1 */,
+                       const float* const* weights, const float* const* biases);
+
+/* ---- MpcICem.beginning_of_rollout (controllers/icem.py:31-43; controllers/mpc.py:69-73) ---------------- */
+int icem_begin_rollout(icem_planner_t* p);
+
+/* ---- MpcICem.get_action (controllers/icem.py:106-189): one plan step ------------------------------------
+ * state: forward-model start state (GT state without the leading time entry for the articulated models,
+ * the observation for ICEM_DYN_DENSE_TANH / ICEM_DYN_MLP), float64 like the reference's arrays.
+ * action_out[d]: the executed action (first action of the best trajectory of the last CEM iteration).
+ * Returns ICEM_ERR_STATE ("beginning_of_rollout() needs to be called before") if not reset. */
+int icem_plan(icem_planner_t* p, const double* state, int32_t state_dim, double* action_out);
+
+/* Same plan step with the start state already resident on the device (no host<->device copy): the state is
+ * the one left by the previous icem_plan / icem_advance_state_device.  Asynchronous; pair with icem_sync. */
+int icem_plan_device(icem_planner_t* p);
+/* state_dev <- f(state_dev, last executed action): closed loop entirely on the device (bench `value`). */
+int icem_advance_state_device(icem_planner_t* p);
+int icem_sync(icem_planner_t* p);
+/* CUDA-event time of the last completed plan step on the planner's stream (ms) and of its rollout kernels */
+int icem_last_plan_ms(icem_planner_t* p, float* total_ms, float* rollout_kernels_ms);
+
+/* ---- parity mode: identical Gaussian draws --------------------------------------------------
+ * Provide the UNIT normal draws the next icem_plan consumes for CEM iteration `iteration`, in the reference's
+ * order (oracle/shims/colorednoise.py): zr[rows][d][K] then zi[rows][d][K] (K = h/2+1), rows = this rank's
+ * fresh trajectories followed by its shifted-elite rows; for noise_beta == 0: z[rows][h][d] in zr, zi NULL.
+ * Cleared after the plan step that consumed them. */
+int icem_inject_noise(icem_planner_t* p, int32_t iteration, int32_t rows, const float* zr, const float* zi);
+
+/* ---- observable planner state (attributes MpcICem exposes: mean, std, elite_samples) ------------------- */
+int icem_get_mean(icem_planner_t* p, float* mean_out /* [h*d] */);
+int icem_get_std(icem_planner_t* p, float* std_out /* [h*d] */);
+int icem_num_elites(icem_planner_t* p);
+int icem_get_elites(icem_planner_t* p, float* actions_out /* [k*h*d] */, float* costs_out /* [k] */,
+                    int32_t* idx_out /* [k] */);
+/* per-iteration record of the last plan step */
+int icem_population_size(icem_planner_t* p, int32_t iteration, int32_t first_step, int32_t* global_out,
+                         int32_t* local_out);
+int icem_get_iteration(icem_planner_t* p, int32_t iteration, float* mean_out, float* std_out,
+                       float* elite_costs_out, int32_t* elite_idx_out);
+int icem_get_costs(icem_planner_t* p, int32_t iteration, float* costs_out, int32_t n /* local rows */);
+int icem_get_actions(icem_planner_t* p, int32_t iteration, float* actions_out, int32_t n /* local rows */);
+
+/* ---- forward_model.predict / env.step on the device model (controllers/icem.py:186-188) ---------------- */
+int icem_sim_step(icem_planner_t* p, const double* state, int32_t state_dim, const double* action,
+                  double* next_state, double* obs_out, int32_t obs_dim, double* reward_out);
+int icem_state_dim(icem_planner_t* p);
+int icem_observe(icem_planner_t* p, const double* state, int32_t state_dim, double* obs_out, int32_t obs_dim);
+
+/* ---- single operators with HOST buffers (kernel-level parity tests; each is one kernel of the plan step) - */
+/* controllers/icem.py:61-82: actions[n][h][d] = clip(colored(z) * std + mean, low, high) */
+int icem_op_sample(icem_planner_t* p, int32_t n, const float* zr, const float* zi, const float* mean,
+                   const float* std, float* actions_out);
+/* controllers/mpc.py:56-67 + controllers/abstract_controller.py:74-91: costs[n] for given action sequences */
+int icem_op_rollout_cost(icem_planner_t* p, int32_t n, const double* state, int32_t state_dim,
+                         const float* actions, float* costs_out);
+/* controllers/icem.py:199: k smallest by ascending (cost, index); NaN sorts last */
+int icem_op_topk(icem_planner_t* p, int32_t n, const float* costs, int32_t k, int32_t* idx_out, float* costs_out);
+
+/* ---- multi-GPU: one NCCL all-gather of per-shard elites per CEM iteration ------------------------------ */
+#define ICEM_UNIQUE_ID_BYTES 128
+int icem_comm_get_unique_id(char id_out[ICEM_UNIQUE_ID_BYTES]);
+int icem_comm_init(icem_planner_t* p, const char id[ICEM_UNIQUE_ID_BYTES]);
+
+/* ---- bench helpers ------------------------------------------------------------------------------------- */
+/* Run `steps` device-resident closed-loop plan steps (plan_device + advance_state_device) after `warmup`,
+ * flushing L2 between steps when flush_l2 != 0; CUDA events on the planner's stream.
+ * total_ms: timed region; rollout_ms: summed duration of the fused sample->rollout->cost kernels in it;
+ * rollout_launches: how many of them. */
+int icem_bench_device(icem_planner_t* p, int32_t steps, int32_t warmup, int32_t flush_l2, float* total_ms,
+                      float* rollout_ms, int32_t* rollout_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICEM_B200_H */
