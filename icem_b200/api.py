@@ -1,0 +1,121 @@
+"""Stand-alone copies of the reference's plugin ABC *signatures* (no logic), used only when the reference package
+is not importable (e.g. on a box without /root/reference).  When the reference IS importable (the launcher put
+`/root/reference/icem` on sys.path), `controller.py` / `models.py` subclass the reference's own ABCs instead, so
+`issubclass(MpcICemB200, ModelBasedController)` in `main.get_controllers` (icem/main.py:43) holds.
+
+Mirrors: icem/misc/base_types.py:42-59 (Controller), :62-118 (ForwardModel);
+icem/controllers/abstract_controller.py:43-58 (StatefulController), :61-72 (ModelBasedController).
+"""
+from abc import ABC, abstractmethod
+
+
+def reference_bases():
+    """(Controller bases, ForwardModel base, RolloutBuffer, Rollout, AbstractGroundTruthModel) from the reference
+    if importable, else None."""
+    try:
+        from controllers.abstract_controller import ModelBasedController as RefMBC  # noqa
+        from controllers.abstract_controller import StatefulController as RefSC  # noqa
+        from misc.rolloutbuffer import Rollout, RolloutBuffer  # noqa
+        from models.abstract_models import ForwardModelWithDefaults  # noqa
+        from models.gt_model import AbstractGroundTruthModel  # noqa
+        return dict(mbc=RefMBC, sc=RefSC, rollout=Rollout, buffer=RolloutBuffer, fm=ForwardModelWithDefaults,
+                    gt=AbstractGroundTruthModel)
+    except ImportError:
+        return None
+
+
+class Controller(ABC):
+    needs_training = False
+    needs_data = False
+    has_state = False
+    required_settings = []
+
+    def __init__(self, *, env):
+        self.env = env
+
+    @abstractmethod
+    def get_action(self, obs, state, mode="train"):
+        pass
+
+
+class StatefulController(Controller, ABC):
+    has_state = True
+
+    @abstractmethod
+    def beginning_of_rollout(self, *, observation, state=None, mode):
+        pass
+
+    @abstractmethod
+    def end_of_rollout(self, total_time, total_return, mode):
+        pass
+
+
+class ModelBasedController(Controller, ABC):
+    def __init__(self, *, forward_model, env, cost_along_trajectory, do_visualize_plan=None,
+                 use_env_reward_as_cost=False, **kwargs):
+        super().__init__(env=env, **kwargs)
+        self.forward_model = forward_model
+        self.do_visualize_plan = do_visualize_plan
+        self.visualize_env = None
+        self.cost_fn = self.env.cost_fn
+        self.cost_along_trajectory = cost_along_trajectory
+        self.use_env_reward_as_cost = use_env_reward_as_cost
+
+
+class ForwardModel(ABC):
+    supports_stochastic = False
+
+    def __init__(self, *, env):
+        self.env = env
+
+    def reset(self, observation):
+        return None
+
+    def got_actual_observation_and_env_state(self, *, observation, env_state=None, model_state=None):
+        return None
+
+    def train(self, buffer):
+        pass
+
+    def save(self, path):
+        pass
+
+    def load(self, path):
+        pass
+
+
+class AbstractGroundTruthModel(ForwardModel, ABC):
+    pass
+
+
+class EliteRollout:
+    """Minimal stand-in for misc/rolloutbuffer.py::Rollout: field access by name."""
+
+    def __init__(self, **fields):
+        self._fields = fields
+
+    def __getitem__(self, key):
+        return self._fields[key]
+
+    def __len__(self):
+        return len(next(iter(self._fields.values())))
+
+
+class EliteBuffer:
+    """Minimal stand-in for misc/rolloutbuffer.py::RolloutBuffer: len / truthiness / iteration / as_array."""
+
+    def __init__(self, rollouts=None):
+        self.rollouts = list(rollouts or [])
+
+    def __len__(self):
+        return len(self.rollouts)
+
+    def __iter__(self):
+        return iter(self.rollouts)
+
+    def __getitem__(self, i):
+        return self.rollouts[i]
+
+    def as_array(self, key):
+        import numpy as np
+        return np.concatenate([r[key][None, ...] for r in self.rollouts], axis=0)

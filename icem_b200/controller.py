@@ -1,0 +1,208 @@
+"""MpcICemB200 -- drop-in for the reference's `MpcICem` (icem/controllers/icem.py:16-247).
+
+Same constructor keywords (settings JSON `controller_params`), same plugin methods
+(`beginning_of_rollout` / `get_action` / `end_of_rollout`), same observable attributes (`mean`, `std`,
+`elite_samples`, `model_evals_per_timestep`) and the same error behaviour; the CEM loop itself runs as CUDA kernels
+behind the C ABI (include/icem_b200.h).  There is NO CPU path: a forward model without `cuda_spec()` or a missing
+library / device raises.
+"""
+from warnings import warn
+
+import numpy as np
+
+from . import api
+from .planner import IcemError, Planner, PlannerSettings
+
+_ref = api.reference_bases()
+_Bases = (_ref["mbc"], _ref["sc"]) if _ref else (api.ModelBasedController, api.StatefulController)
+
+_ENV_COSTS = {"HalfCheetahMaybeWithPosition": "halfcheetah", "HumanoidStandup": "humanoid_standup"}
+
+
+def _get_logger(name):
+    try:
+        import allogger
+        return allogger.get_logger(scope=name, default_outputs=["tensorboard"])
+    except ImportError:
+        return None
+
+
+class MpcICemB200(*_Bases):
+    def __init__(self, *, action_sampler_params, horizon, num_simulated_trajectories, factor_decrease_num=1,
+                 verbose=False, seed=None, device=None, world_size=None, rank=None, **kwargs):
+        super().__init__(**kwargs)     # ModelBasedController: forward_model, env, cost_along_trajectory, ...
+        # controllers/mpc.py:22-36
+        self.horizon = horizon
+        self.num_sim_traj = num_simulated_trajectories
+        self.factor_decrease_num = factor_decrease_num
+        if num_simulated_trajectories < 2:
+            raise ValueError("At least two trajectories needed!")
+        self.verbose = verbose
+        self.forward_model_state = None
+        self._parse_action_sampler_params(**action_sampler_params)
+        self._check_validity_parameters()
+        self.logger = _get_logger(self.__class__.__name__)
+        self.was_reset = False
+        if getattr(self, "use_env_reward_as_cost", False):
+            raise NotImplementedError("use_env_reward_as_cost is not implemented by the CUDA controller")
+
+        fm = self.forward_model
+        if not getattr(fm, "is_cuda_model", False) or not hasattr(fm, "cuda_spec"):
+            raise TypeError(f"MpcICemB200 needs a CUDA-capable forward model (got {type(fm).__name__}); "
+                            "use forward_model 'CudaGroundTruthModel' / 'CudaDenseTanhModel'. There is no CPU fallback.")
+        spec = fm.cuda_spec()
+        cost, penalise = self._cost_spec()
+        if device is None or world_size is None or rank is None:
+            from .distributed import default_placement
+            dev_, ws_, rk_ = default_placement()
+            device = dev_ if device is None else device
+            world_size = ws_ if world_size is None else world_size
+            rank = rk_ if rank is None else rank
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1))   # follows np.random.seed(Seeding.SEED), misc/seeding.py:18
+        self._planner = Planner(PlannerSettings(
+            horizon=horizon, num_simulated_trajectories=num_simulated_trajectories,
+            action_low=self.env.action_space.low, action_high=self.env.action_space.high,
+            dynamics=spec["dynamics"], cost=cost, obs_dim=spec["obs_dim"], penalise_flipping=penalise,
+            factor_decrease_num=factor_decrease_num, cost_along_trajectory=self.cost_along_trajectory,
+            alpha=self.alpha, elites_size=self.elites_size, opt_iterations=self.opt_iter, init_std=self.init_std,
+            use_mean_actions=self.use_mean_actions, keep_previous_elites=self.keep_previous_elites,
+            shift_elites_over_time=self.shift_elites_over_time, fraction_elites_reused=self.fraction_elites_reused,
+            noise_beta=self.noise_beta, seed=seed, device=device, world_size=world_size, rank=rank))
+        if spec.get("dense") is not None:
+            self._planner.set_dense_model(*spec["dense"])
+        if world_size > 1:
+            from .distributed import init_planner_comm
+            init_planner_comm(self._planner)
+        self.expected_cost = None
+
+    # ---- settings (controllers/icem.py:213-247) ------------------------------------------------
+    def _parse_action_sampler_params(self, *, alpha, elites_size, opt_iterations, init_std, use_mean_actions,
+                                     keep_previous_elites, shift_elites_over_time, fraction_elites_reused,
+                                     noise_beta=1):
+        self.alpha = alpha
+        self.elites_size = elites_size
+        self.opt_iter = opt_iterations
+        self.init_std = init_std
+        self.use_mean_actions = use_mean_actions
+        self.keep_previous_elites = keep_previous_elites
+        self.shift_elites_over_time = shift_elites_over_time
+        self.fraction_elites_reused = fraction_elites_reused
+        self.noise_beta = noise_beta
+
+    def _check_validity_parameters(self):
+        self.num_elites = min(self.elites_size, self.num_sim_traj // 2)
+        if self.num_elites < 2:
+            warn('Number of trajectories is too low for given elites_frac. Setting num_elites to 2.')
+            self.num_elites = 2
+        space = self.env.action_space
+        if type(space).__name__ == "Discrete":
+            raise NotImplementedError("CEM ERROR: Implement categorical distribution for discrete envs.")
+        elif type(space).__name__ == "Box":
+            self.dim_samples = (self.horizon, space.shape[0])
+        else:
+            raise NotImplementedError
+
+    def _cost_spec(self):
+        env = self.env
+        if hasattr(env, "cuda_cost_spec"):
+            return env.cuda_cost_spec()
+        for cls in type(env).__mro__:
+            if cls.__name__ in _ENV_COSTS:
+                return _ENV_COSTS[cls.__name__], bool(getattr(env, "penalise_flipping", False))
+        raise NotImplementedError(f"no CUDA cost function for env {type(env).__name__}")
+
+    # ---- plugin API ----------------------------------------------------------------------------
+    def beginning_of_rollout(self, *, observation, state=None, mode):
+        # controllers/mpc.py:69-73
+        if state is not None and isinstance(self.forward_model, (api.AbstractGroundTruthModel,) + (
+                (_ref["gt"],) if _ref else ())):
+            self.forward_model_state = state
+        else:
+            self.forward_model_state = self.forward_model.reset(observation)
+        self._planner.begin_rollout()
+        self.was_reset = True
+        self._elite_cache = None
+        self._steps_since_reset = 0
+        # controllers/icem.py:38-43
+        self.model_evals_per_timestep = sum(
+            [max(self.elites_size * 2, int(self.num_sim_traj / (self.factor_decrease_num ** i)))
+             for i in range(0, self.opt_iter)]) * self.horizon
+        print(f"iCEM using {self.model_evals_per_timestep} evaluations per step "
+              f"and {self.model_evals_per_timestep / self.horizon} trajectories per step")
+
+    def end_of_rollout(self, total_time, total_return, mode):
+        pass
+
+    def get_action(self, obs, state, mode="train"):
+        if not self.was_reset:
+            raise AttributeError("beginning_of_rollout() needs to be called before")
+        if self.verbose:
+            print(f"-------------------- {self.mean[0][0:6]}")
+        self.forward_model_state = self.forward_model.got_actual_observation_and_env_state(
+            observation=obs, env_state=state, model_state=self.forward_model_state)
+        start = self.forward_model.start_state(obs, self.forward_model_state)
+        first = self._steps_since_reset == 0
+        try:
+            executed_action = self._planner.plan(start)
+        except IcemError as e:
+            if "beginning_of_rollout" in str(e):
+                raise AttributeError(str(e))
+            raise
+        self._steps_since_reset += 1
+        self._elite_cache = None
+        if self.verbose:
+            self._print_iterations(first)
+        rec = self._planner.iteration_record(self.opt_iter - 1) if (self.logger is not None or self.verbose) else None
+        if rec is not None:
+            self.expected_cost = float(rec["elite_costs"][0])
+            if self.logger is not None:
+                self.logger.log(self.expected_cost, key="Expected_trajectory_cost")   # icem.py:177
+        # for stateful models, actually simulate step (icem.py:185-188); the result is overwritten by the next
+        # call whenever the env state is supplied, so it is only evaluated when it will be used
+        if self.forward_model_state is not None and state is None:
+            _, self.forward_model_state, _ = self.forward_model.predict(
+                observations=obs, states=self.forward_model_state, actions=executed_action)
+        return executed_action
+
+    def _print_iterations(self, first):
+        p = self._planner
+        for i in range(self.opt_iter):
+            _, n_local = p.population_size(i, first)
+            costs = p.costs(i, n_local).astype(np.float64)
+            rec = p.iteration_record(i)
+
+            def display_cost(cost):
+                return cost / self.horizon if self.cost_along_trajectory == "sum" else cost
+            print('iter {}:{} --- best cost: {:.2f} --- mean: {:.2f} --- worst: {:.2f}  elites: {}...'
+                  .format(i, n_local, display_cost(min(np.amin(costs), rec["elite_costs"][0])),
+                          display_cost(np.mean(costs)), display_cost(np.amax(costs)), rec["elite_idx"][0:6]))
+
+    # ---- observable attributes -----------------------------------------------------------------
+    @property
+    def mean(self):
+        return self._planner.mean().astype(np.float64)
+
+    @property
+    def std(self):
+        return self._planner.std().astype(np.float64)
+
+    @property
+    def elite_samples(self):
+        """RolloutBuffer of the k elites of the last CEM iteration, best first (icem.py:201); the device keeps
+        only what the planner needs, so the rollouts carry `actions` (+ per-trajectory `costs`)."""
+        if getattr(self, "_steps_since_reset", 0) == 0:
+            return (_ref["buffer"]() if _ref else api.EliteBuffer())
+        if self._elite_cache is None:
+            acts, costs, _ = self._planner.elites()
+            if _ref:
+                rollouts = [_ref["rollout"].from_dict(actions=a.astype(np.float64)) for a in acts]
+                self._elite_cache = _ref["buffer"](rollouts=rollouts)
+            else:
+                self._elite_cache = api.EliteBuffer(
+                    [api.EliteRollout(actions=a.astype(np.float64)) for a in acts])
+            self._elite_costs = costs.astype(np.float64)
+        return self._elite_cache
+
+    def close(self):
+        self._planner.close()

@@ -1,0 +1,123 @@
+"""CUDA-capable forward models for the B200 controller.
+
+The reference hands the controller a `ForwardModel` object built from a registry string
+(icem/main.py:105-109, icem/models/__init__.py:5-26).  These classes are what a settings file names in
+`"forward_model"` for the B200 path (`launch.py` registers them in `models_dict`); they do not simulate on the
+host -- they describe the device model (`cuda_spec`) and the controller keeps every rollout on the GPU.
+"""
+import numpy as np
+
+from . import api
+
+_ref = api.reference_bases()
+_FMBase = _ref["fm"] if _ref else api.ForwardModel
+_GTBase = _ref["gt"] if _ref else api.AbstractGroundTruthModel
+
+
+class CudaDenseTanhModel(_FMBase):
+    """obs' = tanh(W_o obs + W_a act + b): the dense single-layer batched model (the path
+    `ForwardModelWithDefaults.predict_n_steps`, icem/models/abstract_models.py:31-53, takes)."""
+    is_cuda_model = True
+
+    def __init__(self, *, env, w_obs, w_act, bias=None, **kwargs):
+        super().__init__(env=env, **kwargs)
+        self.w_obs = np.asarray(w_obs, np.float32)
+        self.w_act = np.asarray(w_act, np.float32)
+        self.bias = None if bias is None else np.asarray(bias, np.float32)
+        self.is_trained = True
+
+    def cuda_spec(self):
+        return dict(dynamics="dense_tanh", dense=(self.w_obs, self.w_act, self.bias), obs_dim=self.w_obs.shape[0])
+
+    def start_state(self, observation, model_state):
+        return np.asarray(observation, np.float64)
+
+    # ForwardModel API -------------------------------------------------------------------------
+    def train(self, buffer):
+        pass
+
+    def reset(self, observation):
+        return None
+
+    def got_actual_observation_and_env_state(self, *, observation, env_state=None, model_state=None):
+        return None
+
+    def predict(self, *, observations, states, actions):
+        # float64 host evaluation of ONE transition for API completeness (post-plan bookkeeping,
+        # icem/controllers/icem.py:186-188, is skipped for state-less models because reset() returns None)
+        o = np.asarray(observations, np.float64)
+        nxt = np.tanh(o @ self.w_obs.T.astype(np.float64) + np.asarray(actions, np.float64) @ self.w_act.T.astype(
+            np.float64) + (0 if self.bias is None else self.bias.astype(np.float64)))
+        return nxt, states, np.zeros(o.shape[:-1] + (1,))
+
+    def predict_n_steps(self, *, start_observations, start_states, policy, horizon):
+        raise NotImplementedError("CudaDenseTanhModel rollouts run inside MpcICemB200 on the device")
+
+    def rollout_generator(self, *a, **k):
+        raise NotImplementedError
+
+    def rollout_field_names(self):
+        return "observations", "next_observations", "actions", "rewards"
+
+    def save(self, path):
+        pass
+
+    def load(self, path):
+        pass
+
+
+class CudaGroundTruthModel(_GTBase):
+    """Ground-truth model of a device-simulated stand-in env (envs.py): the role of
+    `ParallelGroundTruthModel` (icem/models/gt_par_model.py:17-100) with the worker pool replaced by the GPU."""
+    is_cuda_model = True
+
+    def __init__(self, *, env, num_parallel=None, **kwargs):
+        super().__init__(env=env, **kwargs)
+        if not hasattr(env, "cuda_dynamics"):
+            raise NotImplementedError("Environment does not support the CUDA ground truth forward model")
+        self.is_trained = True
+
+    def cuda_spec(self):
+        return dict(dynamics=self.env.cuda_dynamics, dense=None, obs_dim=self.env.observation_space.shape[0])
+
+    def start_state(self, observation, model_state):
+        if model_state is None:
+            raise ValueError("CudaGroundTruthModel needs the env state (rollout_params.use_env_states: true)")
+        return np.asarray(model_state, np.float64)[1:]     # [time, qpos, qvel] -> (qpos, qvel)
+
+    def close(self):
+        pass
+
+    def train(self, buffer):
+        pass
+
+    def set_state(self, state):
+        raise NotImplementedError
+
+    def get_state(self, observation):
+        return self.env.state_from_observation(observation)
+
+    def reset(self, observation):
+        return self.get_state(observation)
+
+    def got_actual_observation_and_env_state(self, *, observation, env_state=None, model_state=None):
+        # icem/models/gt_par_model.py:60-64
+        return self.reset(observation) if env_state is None else env_state
+
+    def predict(self, *, observations, states, actions):
+        return self.env.simulate(states, actions)
+
+    def predict_n_steps(self, *, start_observations, start_states, policy, horizon):
+        raise NotImplementedError("CudaGroundTruthModel rollouts run inside MpcICemB200 on the device")
+
+    def rollout_generator(self, *a, **k):
+        raise NotImplementedError
+
+    def rollout_field_names(self):
+        return "observations", "next_observations", "actions", "rewards"
+
+    def save(self, path):
+        pass
+
+    def load(self, path):
+        pass

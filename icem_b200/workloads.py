@@ -1,0 +1,98 @@
+"""Named workloads = the BASELINE.json configs, as PlannerSettings + synthetic start states.
+
+Only sizes / hyper-parameters / seeds live here (resolved values of the reference's
+settings/<env>/i-cem-blitz.json); no oracle code.
+"""
+import numpy as np
+
+from .planner import PlannerSettings
+
+_BLITZ = dict(alpha=0.1, elites_size=10, fraction_elites_reused=0.3, init_std=0.5, keep_previous_elites=True,
+              shift_elites_over_time=True, use_mean_actions=True, factor_decrease_num=1.25, horizon=30,
+              cost_along_trajectory="sum")
+
+
+def dense_model_weights(obs_dim, act_dim, seed):
+    """Deterministic toy dense model (SURVEY Appendix C recipe)."""
+    rs = np.random.RandomState(seed)
+    a = 0.95 * np.eye(obs_dim) + 0.02 * rs.randn(obs_dim, obs_dim)
+    b = 0.1 * rs.randn(obs_dim, act_dim)
+    return a, b, np.zeros(obs_dim)
+
+
+WORKLOADS = {
+    # BASELINE configs[1]: HalfCheetah GT dynamics, h=30, beta=0.25, N=4096, 5 CEM iterations
+    "halfcheetah_gt_n4096": dict(
+        settings=dict(_BLITZ, num_simulated_trajectories=4096, opt_iterations=5, noise_beta=0.25,
+                      dynamics="halfcheetah", cost="halfcheetah", obs_dim=17, penalise_flipping=True),
+        act_dim=6, bound=1.0, env="HalfCheetah"),
+    # BASELINE configs[2]: Humanoid Standup GT dynamics, h=30, beta=2.0, N=16384, elite reuse 0.3, 3 iterations
+    "humanoid_standup_gt_n16384": dict(
+        settings=dict(_BLITZ, num_simulated_trajectories=16384, opt_iterations=3, noise_beta=2.0,
+                      dynamics="humanoid_standup", cost="humanoid_standup", obs_dim=47),
+        act_dim=17, bound=0.4, env="HumanoidStandup"),
+    # one shard of BASELINE configs[4] (N=262144 over 8 GPUs): 32768 trajectories per GPU
+    "humanoid_standup_gt_shard32768": dict(
+        settings=dict(_BLITZ, num_simulated_trajectories=32768, opt_iterations=3, noise_beta=2.0,
+                      dynamics="humanoid_standup", cost="humanoid_standup", obs_dim=47),
+        act_dim=17, bound=0.4, env="HumanoidStandup"),
+    # memory-side variant: same sampler / top-k / refit path with a trivially cheap dense forward model
+    "dense_tanh_cheetah_n4096": dict(
+        settings=dict(_BLITZ, num_simulated_trajectories=4096, opt_iterations=5, noise_beta=0.25,
+                      dynamics="dense_tanh", cost="halfcheetah", obs_dim=17, penalise_flipping=True),
+        act_dim=6, bound=1.0, env=None, dense=(17, 6, 7)),
+    "dense_tanh_humanoid_n16384": dict(
+        settings=dict(_BLITZ, num_simulated_trajectories=16384, opt_iterations=3, noise_beta=2.0,
+                      dynamics="dense_tanh", cost="humanoid_standup", obs_dim=47),
+        act_dim=17, bound=0.4, env=None, dense=(47, 17, 11)),
+}
+
+
+def get_workload(name):
+    if name not in WORKLOADS:
+        raise KeyError(f"unknown workload {name!r}; choose from {sorted(WORKLOADS)}")
+    return WORKLOADS[name]
+
+
+def planner_settings(name, world_size=1, rank=0, device=0, seed=0, scale_population=1) -> PlannerSettings:
+    w = get_workload(name)
+    s = dict(w["settings"])
+    s["num_simulated_trajectories"] = int(s["num_simulated_trajectories"] * scale_population)
+    low = -w["bound"] * np.ones(w["act_dim"], np.float32)
+    return PlannerSettings(action_low=low, action_high=-low, world_size=world_size, rank=rank, device=device,
+                           seed=seed, **s)
+
+
+def populations(settings: PlannerSettings):
+    """N_i per CEM iteration (icem/controllers/icem.py:123-127)."""
+    out, n = [], settings.num_simulated_trajectories
+    for i in range(settings.opt_iterations):
+        if i > 0:
+            n = max(settings.elites_size * 2, int(n / settings.factor_decrease_num))
+        out.append(n)
+    return out
+
+
+def trajectories_per_step(settings: PlannerSettings, first_step=False):
+    k = max(2, min(settings.elites_size, settings.num_simulated_trajectories // 2))
+    n = sum(populations(settings))
+    if not first_step and settings.shift_elites_over_time:
+        n += int(k * settings.fraction_elites_reused)
+    return n
+
+
+def start_state(name, seed=0):
+    """Synthetic start state mirroring the gym reset noise."""
+    w = get_workload(name)
+    rs = np.random.RandomState(1000 + seed)
+    if w["env"] == "HalfCheetah":
+        qpos = rs.uniform(-0.1, 0.1, 9)
+        qvel = 0.1 * rs.randn(9)
+        return np.concatenate([qpos, qvel])
+    if w["env"] == "HumanoidStandup":
+        from .envs import humanoid_standup_qpos0
+        qpos = humanoid_standup_qpos0() + rs.uniform(-0.01, 0.01, 24)
+        qvel = rs.uniform(-0.01, 0.01, 23)
+        return np.concatenate([qpos, qvel])
+    obs_dim = w["dense"][0]
+    return 0.1 * rs.randn(obs_dim)
