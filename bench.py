@@ -151,10 +151,11 @@ def build_controller(name, world, rank, device):
                                   "keep_previous_elites", "shift_elites_over_time", "fraction_elites_reused",
                                   "noise_beta")}
     if w["env"] is None:
+        wts = workloads.dense_model_weights(*w["dense"])
         env = envs.DenseStandInEnv(name="dense", act_dim=w["act_dim"], bound=w["bound"], cost=st["cost"],
-                                   obs_dim=st["obs_dim"], penalise_flipping=st.get("penalise_flipping", False))
-        model = CudaDenseTanhModel(env=env, **dict(zip(("w_obs", "w_act", "bias"),
-                                                       workloads.dense_model_weights(*w["dense"]))))
+                                   obs_dim=st["obs_dim"], penalise_flipping=st.get("penalise_flipping", False),
+                                   weights=wts)
+        model = CudaDenseTanhModel(env=env, **dict(zip(("w_obs", "w_act", "bias"), wts)))
     else:
         env = envs.make_env(w["env"], device=device)
         model = CudaGroundTruthModel(env=env)

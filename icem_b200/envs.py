@@ -1,0 +1,292 @@
+"""Stand-in environments for the B200 path.
+
+gym / mujoco-py / MuJoCo are not installable here, so the two in-scope environments are provided as
+`GroundTruthSupportEnv`-shaped classes (reference contract: icem/environments/abstract_environments.py:140-178,
+what the callers touch is listed in SURVEY Appendix D item 4) whose `step` runs ONE transition of the same device
+model the planner rolls out (`icem_sim_step`, include/icem_b200.h).  The articulated-body model is this repo's own
+(icem_b200/csrc/dyn_articulated.cuh); it is NOT MuJoCo -- see DESIGN.md "Ground-truth dynamics".
+
+Cost functions: each env carries `cost_fn` with the reference's signature and arithmetic
+(environments/mujoco.py:67-99, :259-277) for host-side use by other controllers; the CUDA controller reads
+`cuda_cost_spec()` and evaluates the same formula inside the rollout kernel.
+"""
+import math
+
+import numpy as np
+
+from . import api
+from .planner import Planner, PlannerSettings
+
+try:   # the reference's env base class when the reference is importable (launcher), else a minimal stand-in
+    from environments.abstract_environments import GroundTruthSupportEnv as _EnvBase  # noqa
+    _HAVE_REF_ENV = True
+except ImportError:   # pragma: no cover - exercised on boxes without the reference
+    _HAVE_REF_ENV = False
+
+    class _EnvBase:
+        def __init__(self, *, name, **kwargs):
+            self.name = name
+            self.init_kwargs = {}
+
+        def store_init_arguments(self, all_parameters):
+            forbidden = {"self", "__class__"}
+            self.init_kwargs = {k: v for k, v in all_parameters.items() if k not in forbidden}
+            self.init_kwargs.update(self.init_kwargs.pop("kwargs", {}))
+
+
+class Box:
+    """gym.spaces.Box surface the controller reads: low / high / shape (float32 like gym)."""
+
+    def __init__(self, low, high):
+        self.low = np.asarray(low, np.float32)
+        self.high = np.asarray(high, np.float32)
+        self.shape = self.low.shape
+        self.dtype = np.dtype(np.float32)
+
+    def sample(self):
+        return np.random.uniform(self.low, self.high).astype(np.float32)
+
+
+# ---- cost functions restated from the reference (host side; the kernels evaluate the same formulas) ------------
+def halfcheetah_cost_fn(observation, action, next_obs=None, penalise_flipping=True):
+    """environments/mujoco.py:67-99."""
+    observation, action = np.asarray(observation), np.asarray(action)
+    if observation.shape[-1] == 18:
+        root_angle, velocity = observation[..., 2], observation[..., 9]
+    elif observation.shape[-1] == 17:
+        root_angle, velocity = observation[..., 1], observation[..., 8]
+    else:
+        raise AttributeError(f"Got state of dimension {observation.shape[-1]}. Possible dimensions are 17 or 18.")
+    scores = np.zeros(action.shape[:-1])
+    if penalise_flipping:
+        scores = scores + (root_angle > math.pi / 2) * 10
+        scores = scores + (root_angle < -math.pi / 2) * 10
+    return scores + 0.1 * np.sum(action ** 2, axis=-1) - velocity
+
+
+def humanoid_standup_cost_fn(observation, action, next_obs=None):
+    """environments/mujoco.py:259-277."""
+    observation, action = np.asarray(observation), np.asarray(action)
+    return -observation[..., 2] + 0.1 * np.square(action).sum(axis=-1)
+
+
+class DenseStandInEnv(_EnvBase):
+    """Environment whose true dynamics IS the dense-tanh model (obs' = tanh(W_o obs + W_a a + b)); used for the
+    memory-side workloads and the plumbing tests.  state == observation."""
+
+    def __init__(self, *, name="dense", act_dim, bound, cost, obs_dim, penalise_flipping=False, weights=None,
+                 **kwargs):
+        super().__init__(name=name, **kwargs)
+        self.store_init_arguments(locals())
+        self.action_space = Box(-bound * np.ones(act_dim), bound * np.ones(act_dim))
+        self.observation_space = Box(-np.ones(obs_dim), np.ones(obs_dim))
+        self.cost = cost
+        self.penalise_flipping = penalise_flipping
+        self.weights = weights
+        self._obs = np.zeros(obs_dim)
+        self._rs = np.random.RandomState(0)
+
+    def cuda_cost_spec(self):
+        return self.cost, self.penalise_flipping
+
+    def cost_fn(self, observation, action, next_obs):
+        if self.cost == "halfcheetah":
+            return halfcheetah_cost_fn(observation, action, next_obs, self.penalise_flipping)
+        return humanoid_standup_cost_fn(observation, action, next_obs)
+
+    def seed(self, seed=None):
+        self._rs = np.random.RandomState(seed)
+        return [seed]
+
+    def reset(self):
+        self._obs = 0.1 * self._rs.randn(self.observation_space.shape[0])
+        return self._obs.copy()
+
+    def reset_with_mode(self, mode):
+        return self.reset()
+
+    def step(self, action):
+        if self.weights is None:
+            raise RuntimeError("DenseStandInEnv needs weights=(w_obs, w_act, bias) to step")
+        w_o, w_a, b = self.weights
+        cost = float(self.cost_fn(self._obs, np.asarray(action, np.float64), None))
+        self._obs = np.tanh(w_o @ self._obs + w_a @ np.asarray(action, np.float64) + (0 if b is None else b))
+        return self._obs.copy(), -cost, False, {}
+
+    def get_GT_state(self):
+        return self._obs.copy()
+
+    def set_GT_state(self, state):
+        self._obs = np.asarray(state, np.float64).copy()
+
+    def set_state_from_observation(self, observation):
+        self.set_GT_state(observation)
+
+    def close(self):
+        pass
+
+
+# ---- articulated ground-truth stand-ins --------------------------------------------------------------------------
+_ARTICULATED = {
+    # name -> (dynamics id string, nq, nv, act_dim, ctrl bound, obs_dim (reference layout), reset noise)
+    "HalfCheetah": dict(dynamics="halfcheetah", nq=9, nv=9, act_dim=6, bound=1.0),
+    "HumanoidStandup": dict(dynamics="humanoid_standup", nq=24, nv=23, act_dim=17, bound=0.4),
+}
+
+
+def halfcheetah_qpos0():
+    return np.zeros(9)
+
+
+def humanoid_standup_qpos0():
+    """Initial pose of the lying humanoid: root at z=0.105, rotated -90 deg about y (face up), joints at zero."""
+    q = np.zeros(24)
+    q[2] = 0.105
+    q[3:7] = [0.7071067811865476, 0.0, -0.7071067811865476, 0.0]
+    return q
+
+
+class _DeviceSimEnv(_EnvBase):
+    """Common part: one device planner handle used only for `icem_sim_step` (single transitions)."""
+    kind = None
+
+    def __init__(self, *, name, device=0, **kwargs):
+        super().__init__(name=name, **kwargs)
+        spec = _ARTICULATED[self.kind]
+        self.spec = spec
+        self.device = device
+        self.cuda_dynamics = spec["dynamics"]
+        b = spec["bound"]
+        self.action_space = Box(-b * np.ones(spec["act_dim"]), b * np.ones(spec["act_dim"]))
+        self._sim = None
+        self._rs = np.random.RandomState(0)
+        self._t = 0.0
+        self._state = np.concatenate([self._qpos0(), np.zeros(spec["nv"])])
+
+    # -- device model --------------------------------------------------------------------------------
+    def _simulator(self):
+        if self._sim is None:      # created lazily: after fork()s of the host process
+            self._sim = Planner(PlannerSettings(
+                horizon=2, num_simulated_trajectories=2, action_low=self.action_space.low,
+                action_high=self.action_space.high, dynamics=self.cuda_dynamics, cost=self.cuda_cost_spec()[0],
+                obs_dim=self.observation_space.shape[0], device=self.device))
+        return self._sim
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_sim"] = None
+        return d
+
+    def seed(self, seed=None):
+        self._rs = np.random.RandomState(seed)
+        return [seed]
+
+    def reset_with_mode(self, mode):
+        return self.reset()
+
+    def get_GT_state(self):
+        # MjSimState.flatten() layout [time, qpos, qvel] (environments/mujoco.py:37-38)
+        return np.concatenate([[self._t], self._state])
+
+    def set_GT_state(self, state):
+        state = np.asarray(state, np.float64)
+        self._t = float(state[0])
+        self._state = state[1:].copy()
+
+    def set_state_from_observation(self, observation):
+        raise NotImplementedError("the observation does not determine the state; use env states")
+
+    def step(self, action):
+        a = np.clip(np.asarray(action, np.float64), self.action_space.low, self.action_space.high)
+        obs = self._obs()
+        cost = float(self.cost_fn(obs, a, None))
+        nxt, _, _ = self._simulator().sim_step(self._state, a)
+        self._state = nxt
+        self._t += self.dt
+        return self._obs(), -cost, False, {}
+
+    def simulate(self, state, action):
+        self.set_GT_state(state)
+        obs, r, _, _ = self.step(action)
+        return obs, self.get_GT_state(), r
+
+    def close(self):
+        if self._sim is not None:
+            self._sim.close()
+            self._sim = None
+
+
+class HalfCheetahMaybeWithPosition(_DeviceSimEnv):
+    """Stand-in for environments/mujoco.py:48-131.  obs = qpos[1:] ++ qvel (17) or qpos ++ qvel (18)."""
+    kind = "HalfCheetah"
+    dt = 0.05
+
+    def __init__(self, *, name="HalfCheetah", penalise_flipping=True, exclude_current_positions_from_observation=True,
+                 device=0, **kwargs):
+        self.penalise_flipping = penalise_flipping
+        self.exclude_pos = exclude_current_positions_from_observation
+        n = 17 if self.exclude_pos else 18
+        self.observation_space = Box(-np.inf * np.ones(n), np.inf * np.ones(n))
+        super().__init__(name=name, device=device, **kwargs)
+        self.store_init_arguments(locals())
+
+    def _qpos0(self):
+        return halfcheetah_qpos0()
+
+    def cuda_cost_spec(self):
+        return "halfcheetah", self.penalise_flipping
+
+    def cost_fn(self, observation, action, next_obs):
+        return halfcheetah_cost_fn(observation, action, next_obs, self.penalise_flipping)
+
+    def _obs(self):
+        return self._state[1:].copy() if self.exclude_pos else self._state.copy()
+
+    def reset(self):
+        # gym half_cheetah_v3 reset noise
+        qpos = self._qpos0() + self._rs.uniform(-0.1, 0.1, 9)
+        qvel = 0.1 * self._rs.randn(9)
+        self._state = np.concatenate([qpos, qvel])
+        self._t = 0.0
+        return self._obs()
+
+
+class HumanoidStandup(_DeviceSimEnv):
+    """Stand-in for environments/mujoco.py:228-277.  The reference observation is 378 wide but its cost reads only
+    obs[2] (= qpos[2], root height); this env exposes obs = qpos ++ qvel (47)."""
+    kind = "HumanoidStandup"
+    dt = 0.015
+
+    def __init__(self, *, name="HumanoidStandup", device=0, **kwargs):
+        self.observation_space = Box(-np.inf * np.ones(47), np.inf * np.ones(47))
+        super().__init__(name=name, device=device, **kwargs)
+        self.store_init_arguments(locals())
+
+    def _qpos0(self):
+        return humanoid_standup_qpos0()
+
+    def cuda_cost_spec(self):
+        return "humanoid_standup", False
+
+    def cost_fn(self, observation, action, next_obs):
+        return humanoid_standup_cost_fn(observation, action, next_obs)
+
+    def _obs(self):
+        return self._state.copy()
+
+    def reset(self):
+        c = 0.01
+        qpos = self._qpos0() + self._rs.uniform(-c, c, 24)
+        qpos[3:7] /= np.linalg.norm(qpos[3:7])
+        qvel = self._rs.uniform(-c, c, 23)
+        self._state = np.concatenate([qpos, qvel])
+        self._t = 0.0
+        return self._obs()
+
+
+def make_env(kind, device=0, **kwargs):
+    if kind == "HalfCheetah":
+        return HalfCheetahMaybeWithPosition(name=kind, device=device, **kwargs)
+    if kind == "HumanoidStandup":
+        return HumanoidStandup(name=kind, device=device, **kwargs)
+    raise KeyError(kind)
