@@ -29,6 +29,21 @@ class IcemConfig(C.Structure):
     ]
 
 
+class IcemArticulatedModel(C.Structure):
+    _fields_ = (
+        [(n, C.c_int32) for n in ("nb", "nq", "nv", "nu", "nc", "nsub", "obs_offset")]
+        + [(n, C.c_float) for n in ("dt", "gravity", "ctrl_limit", "contact_stiffness", "contact_damping",
+                                    "contact_damping_max", "friction_viscous", "friction")]
+        + [(n, C.POINTER(C.c_int32)) for n in ("body_parent", "body_dof_start", "body_dof_count")]
+        + [(n, C.POINTER(C.c_float)) for n in ("body_pos", "body_mass", "body_com", "body_inertia")]
+        + [(n, C.POINTER(C.c_int32)) for n in ("dof_body", "dof_type", "dof_qadr", "dof_parent", "dof_limited",
+                                               "dof_act")]
+        + [(n, C.POINTER(C.c_float)) for n in ("dof_axis", "dof_anchor", "dof_stiffness", "dof_damping",
+                                               "dof_armature", "dof_lo", "dof_hi", "dof_klim", "dof_blim", "dof_gear")]
+        + [("con_body", C.POINTER(C.c_int32)), ("con_pos", C.POINTER(C.c_float)), ("con_radius", C.POINTER(C.c_float))]
+    )
+
+
 class IcemError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(msg)
@@ -49,6 +64,7 @@ SIGNATURES = {
     "icem_destroy": (C.c_int, [_H]),
     "icem_set_dense_model": (C.c_int, [_H, C.c_int32, _F, _F, _F]),
     "icem_set_mlp_model": (C.c_int, [_H, C.c_int32, _I, C.POINTER(_F), C.POINTER(_F)]),
+    "icem_set_articulated_model": (C.c_int, [_H, C.POINTER(IcemArticulatedModel)]),
     "icem_begin_rollout": (C.c_int, [_H]),
     "icem_plan": (C.c_int, [_H, _D, C.c_int32, _D]),
     "icem_plan_device": (C.c_int, [_H]),

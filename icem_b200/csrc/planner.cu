@@ -103,7 +103,8 @@ struct icem_planner {
   // model params
   DenseTanh::Params dense{};
   bool model_ready = false;
-  Articulated::Params art{};
+  Articulated<32>::Params art{};      // Params is layout-identical for every NVMAX instantiation
+  DevBuf<ArtModel> art_model;
 
   // run state
   bool was_reset = false;
@@ -206,6 +207,13 @@ static CostConst cost_const(icem_planner* p) {
 static StepState* step_state_dev(icem_planner* p) { return reinterpret_cast<StepState*>(p->step_in.p); }
 static float* start_state_dev(icem_planner* p) { return reinterpret_cast<float*>(p->step_in.p + sizeof(StepState)); }
 
+template <int NVMAX>
+static typename Articulated<NVMAX>::Params art_params(icem_planner* p) {
+  typename Articulated<NVMAX>::Params q{};
+  q.model = p->art.model; q.act_dim = p->art.act_dim; q.nq = p->art.nq; q.nv = p->art.nv;
+  return q;
+}
+
 template <class Dyn, bool kSample, bool kRollout>
 static void launch_rollout(icem_planner* p, const RolloutArgs& a, const typename Dyn::Params& dp, int rows_max) {
   const SamplerConst sc = sampler_const(p);
@@ -236,7 +244,12 @@ static void launch_rollout_dyn(icem_planner* p, const RolloutArgs& a, int rows_m
       break;
     case ICEM_DYN_HALFCHEETAH:
     case ICEM_DYN_HUMANOID_STANDUP:
-      launch_rollout<Articulated, kSample, kRollout>(p, a, p->art, rows_max);
+      if (p->art.nv <= 12)
+        launch_rollout<Articulated<12>, kSample, kRollout>(p, a, art_params<12>(p), rows_max);
+      else if (p->art.nv <= 24)
+        launch_rollout<Articulated<24>, kSample, kRollout>(p, a, art_params<24>(p), rows_max);
+      else
+        launch_rollout<Articulated<32>, kSample, kRollout>(p, a, art_params<32>(p), rows_max);
       break;
     default:
       throw Unsupported("dynamics id not supported by this build");
@@ -384,7 +397,12 @@ static void advance_dyn(icem_planner* p, float* state, const float* action, floa
       break;
     case ICEM_DYN_HALFCHEETAH:
     case ICEM_DYN_HUMANOID_STANDUP:
-      launch_advance<Articulated>(p, p->art, state, action, next_state, obs_out, obs_dim);
+      if (p->art.nv <= 12)
+        launch_advance<Articulated<12>>(p, art_params<12>(p), state, action, next_state, obs_out, obs_dim);
+      else if (p->art.nv <= 24)
+        launch_advance<Articulated<24>>(p, art_params<24>(p), state, action, next_state, obs_out, obs_dim);
+      else
+        launch_advance<Articulated<32>>(p, art_params<32>(p), state, action, next_state, obs_out, obs_dim);
       break;
     default:
       throw Unsupported("dynamics id not supported by this build");
@@ -574,9 +592,7 @@ int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
   build_plan(p.get());
 
   if (cfg->dynamics == ICEM_DYN_HALFCHEETAH || cfg->dynamics == ICEM_DYN_HUMANOID_STANDUP) {
-    articulated_setup(cfg->dynamics, p->d, &p->art);     // built-in model tables
-    p->state_dim = Articulated::state_dim(p->art);
-    p->model_ready = true;
+    p->state_dim = 0;   // known once icem_set_articulated_model provides the tables
   } else if (cfg->dynamics == ICEM_DYN_DENSE_TANH) {
     p->state_dim = 0;   // known once the model is set
   } else {
@@ -625,6 +641,90 @@ int icem_set_dense_model(icem_planner_t* p, int32_t obs_dim, const float* w_obs,
   p->dense.bias = p->bias.p;
   p->state_dim = obs_dim;
   if (p->obs_dim <= 0) p->obs_dim = obs_dim;
+  p->model_ready = true;
+  if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+  ICEM_API_END
+}
+
+int icem_set_articulated_model(icem_planner_t* p, const icem_articulated_model_t* a) {
+  ICEM_API_BEGIN
+  if (!p || !a) throw InvalidArg("null argument");
+  if (p->cfg.dynamics != ICEM_DYN_HALFCHEETAH && p->cfg.dynamics != ICEM_DYN_HUMANOID_STANDUP)
+    throw InvalidArg("planner was not created with an articulated dynamics id");
+  if (a->nb < 1 || a->nb > kArtMaxBodies || a->nv < 1 || a->nv > kArtMaxDofs || a->nc < 0 ||
+      a->nc > kArtMaxContacts || a->nq < a->nv || a->nq + a->nv > 64 || a->nsub < 1)
+    throw InvalidArg("articulated model dimensions out of range (bodies<=16, dofs<=32, contacts<=32, nq+nv<=64)");
+  if (a->nu != p->d) throw InvalidArg("articulated model control dimension does not match act_dim");
+  if (a->obs_offset < 0 || a->obs_offset >= a->nq) throw InvalidArg("obs_offset out of range");
+  if (!(a->dt > 0)) throw InvalidArg("dt must be positive");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  std::unique_ptr<ArtModel> mp(new ArtModel);
+  ArtModel& m = *mp;
+  memset(&m, 0, sizeof m);
+  m.nb = a->nb; m.nq = a->nq; m.nv = a->nv; m.nu = a->nu; m.nc = a->nc; m.nsub = a->nsub;
+  m.obs_offset = a->obs_offset;
+  m.dt = a->dt; m.gravity = a->gravity; m.ctrl_limit = a->ctrl_limit;
+  m.kc = a->contact_stiffness; m.cc = a->contact_damping; m.kv = a->friction_viscous; m.mu = a->friction;
+  m.cdmax = a->contact_damping_max;
+  for (int b = 0; b < m.nb; ++b) {
+    const int par = a->body_parent[b];
+    if (par >= b || par < -1) throw InvalidArg("bodies must be listed parent-before-child");
+    m.b_parent[b] = par;
+    m.b_depth[b] = par < 0 ? 0 : m.b_depth[par] + 1;
+    m.max_depth = std::max(m.max_depth, m.b_depth[b]);
+    m.b_dof_start[b] = a->body_dof_start[b];
+    m.b_dof_count[b] = a->body_dof_count[b];
+    if (m.b_dof_start[b] < 0 || m.b_dof_count[b] < 0 || m.b_dof_start[b] + m.b_dof_count[b] > m.nv)
+      throw InvalidArg("body dof range out of bounds");
+    if (par >= 0) {
+      if (m.b_nchild[par] >= kArtMaxChildren) throw InvalidArg("a body has more than 4 children");
+      m.b_child[par][m.b_nchild[par]++] = b;
+    }
+    for (int i = 0; i < 3; ++i) { m.b_pos[b][i] = a->body_pos[3 * b + i]; m.b_com[b][i] = a->body_com[3 * b + i]; }
+    for (int i = 0; i < 6; ++i) m.b_inertia[b][i] = a->body_inertia[6 * b + i];
+    m.b_mass[b] = a->body_mass[b];
+  }
+  for (int j = 0; j < m.nv; ++j) {
+    m.d_body[j] = a->dof_body[j]; m.d_type[j] = a->dof_type[j]; m.d_qadr[j] = a->dof_qadr[j];
+    m.d_limited[j] = a->dof_limited[j]; m.d_act[j] = a->dof_act[j];
+    if (m.d_body[j] < 0 || m.d_body[j] >= m.nb || m.d_type[j] < 0 || m.d_type[j] > 3 || m.d_qadr[j] < 0 ||
+        m.d_qadr[j] >= m.nq || m.d_act[j] >= m.nu)
+      throw InvalidArg("dof table entry out of range");
+    const int par = a->dof_parent[j];
+    if (par >= j || par < -1) throw InvalidArg("dof_parent must point to an earlier dof");
+    m.d_chain[j] = (1u << j) | (par >= 0 ? m.d_chain[par] : 0u);
+    for (int i = 0; i < 3; ++i) { m.d_axis[j][i] = a->dof_axis[3 * j + i]; m.d_anchor[j][i] = a->dof_anchor[3 * j + i]; }
+    m.d_stiff[j] = a->dof_stiffness[j]; m.d_damp[j] = a->dof_damping[j]; m.d_arm[j] = a->dof_armature[j];
+    m.d_lo[j] = a->dof_lo[j]; m.d_hi[j] = a->dof_hi[j]; m.d_klim[j] = a->dof_klim[j]; m.d_blim[j] = a->dof_blim[j];
+    m.d_gear[j] = a->dof_gear[j];
+  }
+  // a free joint must be 3 translations followed by 3 rotations on the same body
+  for (int j = 0; j < m.nv; ++j) {
+    if (m.d_type[j] == kFreeRot) throw InvalidArg("free-joint rotation dofs must follow three translation dofs");
+    if (m.d_type[j] != kFreeTrans) continue;
+    if (j + 5 >= m.nv) throw InvalidArg("incomplete free joint");
+    for (int k = 0; k < 6; ++k)
+      if (m.d_type[j + k] != (k < 3 ? kFreeTrans : kFreeRot) || m.d_body[j + k] != m.d_body[j])
+        throw InvalidArg("free joint must be 3 translation dofs followed by 3 rotation dofs");
+    j += 5;
+  }
+  int prev_body = -1;
+  for (int c = 0; c < m.nc; ++c) {
+    const int b = a->con_body[c];
+    if (b < 0 || b >= m.nb || b < prev_body) throw InvalidArg("contact spheres must be sorted by body");
+    if (b != prev_body) m.b_con_start[b] = c;
+    m.b_con_count[b] += 1;
+    prev_body = b;
+    m.c_body[c] = b;
+    for (int i = 0; i < 3; ++i) m.c_pos[c][i] = a->con_pos[3 * c + i];
+    m.c_radius[c] = a->con_radius[c];
+  }
+  p->art_model.alloc(1);
+  ICEM_CUDA(cudaMemcpy(p->art_model.p, &m, sizeof m, cudaMemcpyHostToDevice));
+  p->art.model = p->art_model.p;
+  p->art.act_dim = p->d; p->art.nq = m.nq; p->art.nv = m.nv;
+  p->state_dim = m.nq + m.nv;
+  if (p->obs_dim <= 0) p->obs_dim = p->state_dim - m.obs_offset;
   p->model_ready = true;
   if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
   ICEM_API_END

@@ -135,15 +135,14 @@ _ARTICULATED = {
 
 
 def halfcheetah_qpos0():
-    return np.zeros(9)
+    from .robots import get_model
+    return get_model("halfcheetah").qpos0.copy()
 
 
 def humanoid_standup_qpos0():
     """Initial pose of the lying humanoid: root at z=0.105, rotated -90 deg about y (face up), joints at zero."""
-    q = np.zeros(24)
-    q[2] = 0.105
-    q[3:7] = [0.7071067811865476, 0.0, -0.7071067811865476, 0.0]
-    return q
+    from .robots import get_model
+    return get_model("humanoid_standup").qpos0.copy()
 
 
 class _DeviceSimEnv(_EnvBase):

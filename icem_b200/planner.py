@@ -38,6 +38,8 @@ class PlannerSettings:
     rank: int = 0
     colorednoise_v2: bool = False
     keep_iteration_actions: bool = False
+    articulated_model: object = None     # robots.CompiledModel; None = the built-in tables for `dynamics`
+    obs_offset: Optional[int] = None
 
 
 class Planner:
@@ -71,6 +73,13 @@ class Planner:
         self.k = lib.icem_num_elites(self._h)
         self.iters = int(s.opt_iterations)
         self.K = self.h // 2 + 1
+        if s.dynamics in ("halfcheetah", "humanoid_standup") and s.articulated_model is not False:
+            from . import robots
+            model = s.articulated_model if s.articulated_model is not None else robots.get_model(s.dynamics)
+            obs_offset = s.obs_offset
+            if obs_offset is None:     # HalfCheetah's 17-wide observation drops qpos[0] (environments/mujoco.py:80-82)
+                obs_offset = 1 if (s.dynamics == "halfcheetah" and s.obs_dim != 18) else 0
+            self.set_articulated_model(model, obs_offset)
 
     # ---- lifetime -----------------------------------------------------------------------------
     def close(self):
@@ -92,6 +101,27 @@ class Planner:
             raise ValueError("dense model shapes must be [n,n] and [n,d]")
         b = f32(bias) if bias is not None else None
         check(self._lib.icem_set_dense_model(self._h, n, fptr(w_obs), fptr(w_act), fptr(b) if b is not None else None))
+
+    def set_articulated_model(self, m, obs_offset=0):
+        """Upload robots.CompiledModel tables (icem_set_articulated_model)."""
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        keep = dict(
+            body_parent=i32(m.body_parent), body_dof_start=i32(m.body_dof_start), body_dof_count=i32(m.body_dof_count),
+            body_pos=f32(m.body_pos), body_mass=f32(m.body_mass), body_com=f32(m.body_com),
+            body_inertia=f32(m.body_inertia), dof_body=i32(m.dof_body), dof_type=i32(m.dof_type),
+            dof_qadr=i32(m.dof_qadr), dof_parent=i32(m.dof_parent), dof_limited=i32(m.dof_limited),
+            dof_act=i32(m.dof_act), dof_axis=f32(m.dof_axis), dof_anchor=f32(m.dof_anchor),
+            dof_stiffness=f32(m.dof_stiffness), dof_damping=f32(m.dof_damping), dof_armature=f32(m.dof_armature),
+            dof_lo=f32(m.dof_lo), dof_hi=f32(m.dof_hi), dof_klim=f32(m.dof_klim), dof_blim=f32(m.dof_blim),
+            dof_gear=f32(m.dof_gear), con_body=i32(m.con_body), con_pos=f32(m.con_pos), con_radius=f32(m.con_radius))
+        st = _lib.IcemArticulatedModel(
+            nb=m.nb, nq=m.nq, nv=m.nv, nu=m.nu, nc=m.nc, nsub=m.nsub, obs_offset=int(obs_offset), dt=m.dt,
+            gravity=m.gravity, ctrl_limit=m.ctrl_limit, contact_stiffness=m.contact_stiffness,
+            contact_damping=m.contact_damping, contact_damping_max=m.contact_damping_max,
+            friction_viscous=m.friction_viscous, friction=m.friction,
+            **{k: (iptr(v) if v.dtype == np.int32 else fptr(v)) for k, v in keep.items()})
+        check(self._lib.icem_set_articulated_model(self._h, C.byref(st)))
+        self.articulated = m
 
     @property
     def state_dim(self):

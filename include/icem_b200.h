@@ -98,6 +98,42 @@ int icem_set_dense_model(icem_planner_t* p, int32_t obs_dim, const float* w_obs,
 int icem_set_mlp_model(icem_planner_t* p, int32_t n_layers, const int32_t* layer_dims /* n_layers+1 */,
                        const float* const* weights, const float* const* biases);
 
+/* ICEM_DYN_HALFCHEETAH / ICEM_DYN_HUMANOID_STANDUP: tables of the articulated-body model the kernels simulate
+ * (the role of the MuJoCo model the reference's GroundTruthModel owns, models/gt_model.py:24-57).  All arrays are
+ * HOST pointers, copied by the call.  Bodies are listed parent-before-child, dofs in body order, contact spheres
+ * sorted by body.  dof_type: 0 slide, 1 hinge, 2 free-joint translation, 3 free-joint rotation (body-frame angular
+ * velocity; the three share dof_qadr = start of the unit quaternion w,x,y,z).  State layout = [qpos(nq), qvel(nv)];
+ * the observation the cost reads is state[obs_offset:]. */
+typedef struct icem_articulated_model {
+  int32_t nb, nq, nv, nu, nc;
+  int32_t nsub;                   /* substeps per control step (env frame_skip) */
+  int32_t obs_offset;
+  float dt;                       /* substep length */
+  float gravity, ctrl_limit;
+  float contact_stiffness, contact_damping, contact_damping_max, friction_viscous, friction;
+  const int32_t* body_parent;     /* [nb], -1 = world */
+  const int32_t* body_dof_start;  /* [nb] */
+  const int32_t* body_dof_count;  /* [nb] */
+  const float* body_pos;          /* [nb*3] frame offset in the parent frame */
+  const float* body_mass;         /* [nb] */
+  const float* body_com;          /* [nb*3] */
+  const float* body_inertia;      /* [nb*6] xx yy zz xy xz yz about the com, body axes */
+  const int32_t* dof_body;        /* [nv] */
+  const int32_t* dof_type;        /* [nv] */
+  const int32_t* dof_qadr;        /* [nv] */
+  const int32_t* dof_parent;      /* [nv] previous dof on the path to the root, -1 = none */
+  const int32_t* dof_limited;     /* [nv] */
+  const int32_t* dof_act;         /* [nv] control index driving this dof, -1 = none */
+  const float* dof_axis;          /* [nv*3] unit, body frame */
+  const float* dof_anchor;        /* [nv*3] body frame */
+  const float* dof_stiffness; const float* dof_damping; const float* dof_armature;   /* [nv] each */
+  const float* dof_lo; const float* dof_hi; const float* dof_klim; const float* dof_blim; const float* dof_gear;
+  const int32_t* con_body;        /* [nc] */
+  const float* con_pos;           /* [nc*3] body frame */
+  const float* con_radius;        /* [nc] */
+} icem_articulated_model_t;
+int icem_set_articulated_model(icem_planner_t* p, const icem_articulated_model_t* model);
+
 /* ---- MpcICem.beginning_of_rollout (controllers/icem.py:31-43; controllers/mpc.py:69-73) ---------------- */
 int icem_begin_rollout(icem_planner_t* p);
 

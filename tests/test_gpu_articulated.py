@@ -1,0 +1,169 @@
+"""GPU parity of the articulated ground-truth path (csrc/dyn_articulated.cuh through the C ABI) against the
+independent float64 oracle (oracle/articulated_np.py) on the same tables.
+
+Tolerances (fp32 spatial-vector RNEA/CRBA + in-register Cholesky vs float64 Jacobian formulation + LAPACK):
+  one env step from the same state     |d state| <= 2e-4        (measured: median 1e-5, max 5e-5)
+  h=30 trajectory cost                 median |d| <= 1e-4, 95 % of the population within 5e-3, elite set exact;
+                                       contact make/break events amplify fp32 rounding over 150 substeps, so a
+                                       few trajectories differ more -- they are asserted not to be near the elite
+                                       boundary
+  elite indices per CEM iteration      bit-exact, in order, whenever the oracle's elite cost gaps exceed the
+                                       measured cost error on those trajectories
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import costs_np
+from oracle.articulated_np import make_model
+from oracle.icem_np import ICemConfig, ICemOracle, reduce_costs
+from tests.util import elite_gap, stack_noise
+
+pytestmark = pytest.mark.gpu
+
+SPECS = {
+    "halfcheetah": dict(cost="halfcheetah", obs_dim=17, beta=0.25),
+    "humanoid_standup": dict(cost="humanoid_standup", obs_dim=47, beta=2.0),
+}
+
+
+def _cost_fn(name):
+    if name == "halfcheetah":
+        return lambda o, a: costs_np.halfcheetah_cost(o, a, True)
+    return costs_np.humanoid_standup_cost
+
+
+def _planner(name, n=64, iters=3, **over):
+    from icem_b200.planner import Planner, PlannerSettings
+    from icem_b200.robots import get_model
+    m = get_model(name)
+    sp = SPECS[name]
+    lim = m.ctrl_limit
+    kw = dict(horizon=30, num_simulated_trajectories=n, action_low=-lim * np.ones(m.nu, np.float32),
+              action_high=lim * np.ones(m.nu, np.float32), dynamics=name, cost=sp["cost"], obs_dim=sp["obs_dim"],
+              penalise_flipping=True, factor_decrease_num=1.25, opt_iterations=iters, noise_beta=sp["beta"],
+              keep_iteration_actions=True)
+    kw.update(over)
+    return Planner(PlannerSettings(**kw)), m
+
+
+@pytest.mark.parametrize("name", sorted(SPECS))
+def test_env_step_matches_oracle(name):
+    p, m = _planner(name)
+    mod = make_model(name)
+    rs = np.random.RandomState(0)
+    st = np.concatenate([m.qpos0, 0.1 * rs.randn(m.nv)])
+    for t in range(40):
+        u = rs.uniform(-m.ctrl_limit, m.ctrl_limit, m.nu) * (1.5 if t % 7 == 0 else 1.0)   # also beyond the clip
+        ref = mod.step_state(st[None], u[None])[0]
+        got, obs, _ = p.sim_step(st, u, obs_dim=SPECS[name]["obs_dim"])
+        assert np.abs(got - ref).max() <= 2e-4, (t, np.abs(got - ref).max())
+        np.testing.assert_allclose(obs, mod.observe(got), atol=1e-6)
+        st = ref
+    # golden fixture of the oracle (tests/golden/articulated_<name>.npz): first transitions from its start state
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"articulated_{name}.npz"))
+    st = g["start"]
+    for t in range(3):
+        got, _, _ = p.sim_step(st, g["actions"][0, t])
+        st = got
+        np.testing.assert_allclose(mod.observe(got), g["observations"][0, t + 1], atol=5e-4)
+    p.close()
+
+
+@pytest.mark.parametrize("name", sorted(SPECS))
+def test_rollout_costs_match_oracle(name):
+    p, m = _planner(name)
+    mod = make_model(name)
+    rs = np.random.RandomState(3)
+    n = 96
+    lim = m.ctrl_limit
+    acts = rs.uniform(-lim, lim, (n, 30, m.nu)).astype(np.float32)
+    start = np.concatenate([m.qpos0, 0.1 * rs.randn(m.nv)]).astype(np.float32).astype(np.float64)
+    obs = mod.rollout(start, acts.astype(np.float64))
+    ref = reduce_costs(_cost_fn(name)(obs, acts.astype(np.float64)), "sum")
+    got = p.op_rollout_cost(start, acts)
+    d = np.abs(got - ref)
+    assert np.median(d) <= 1e-4, np.median(d)
+    assert np.mean(d <= 5e-3) >= 0.95, np.sort(d)[-8:]
+    k = 10
+    order = np.argsort(ref, kind="stable")
+    if elite_gap(ref, k) > 4 * d[order[: k + 1]].max():
+        np.testing.assert_array_equal(np.argsort(got, kind="stable")[:k], order[:k])
+    else:
+        assert set(np.argsort(got, kind="stable")[:k]) == set(order[:k])
+    p.close()
+
+
+@pytest.mark.parametrize("name,n,steps", [("halfcheetah", 64, 3), ("humanoid_standup", 48, 2)])
+def test_plan_steps_match_oracle(name, n, steps):
+    """Consecutive plan steps on the oracle's exact Gaussian draws with the articulated ground-truth model:
+    sampled actions, costs, elite index lists, refit mean/std and the executed action."""
+    p, m = _planner(name, n=n)
+    mod = make_model(name)
+    lim = m.ctrl_limit
+    cfg = ICemConfig(horizon=30, num_simulated_trajectories=n, action_low=-lim * np.ones(m.nu, np.float32),
+                     action_high=lim * np.ones(m.nu, np.float32), factor_decrease_num=1.25, opt_iterations=3,
+                     noise_beta=SPECS[name]["beta"])
+    orc = ICemOracle(cfg, mod.rollout, _cost_fn(name), record_actions=True)
+    np.random.seed(11)
+    rs = np.random.RandomState(4)
+    state = np.concatenate([m.qpos0, 0.1 * rs.randn(m.nv)]).astype(np.float32).astype(np.float64)
+    orc.beginning_of_rollout()
+    p.begin_rollout()
+    k = cfg.num_elites
+    checked = 0
+    for s in range(steps):
+        tr = orc.get_action(state)
+        for i, it in enumerate(tr.iterations):
+            zr, zi = stack_noise(it.noise)
+            p.inject_noise(i, zr, zi)
+        act = p.plan(state)
+        diverged = False
+        for i, it in enumerate(tr.iterations):
+            rec = p.iteration_record(i)
+            n_sim = it.population - (orc._n_keep() if i > 0 else 0)
+            c_dev = p.costs(i, n_sim)
+            d = np.abs(c_dev - it.costs[:n_sim])
+            order = np.argsort(it.costs, kind="stable")
+            near = [j for j in order[: k + 3] if j < n_sim]
+            err = float(d[near].max()) if near else 0.0
+            if i == 0 or not diverged:
+                a_dev = p.actions(i, n_sim)
+                assert np.abs(a_dev - it.actions[:n_sim]).max() <= 5e-6 * 2 * lim + 1e-6
+                assert np.median(d) <= 2e-4
+            if elite_gap(it.costs, k) > 4 * err + 1e-5 and not diverged:
+                np.testing.assert_array_equal(rec["elite_idx"], it.elite_idx)
+                assert np.abs(rec["mean"] - it.mean).max() <= 1e-5
+                assert np.abs(rec["std"] - it.std).max() <= 1e-5
+                checked += 1
+            else:
+                # a near-tie inside the elite list may legitimately reorder under fp32; later iterations of this
+                # plan step then sample from a (slightly) different distribution and are not comparable
+                diverged = True
+        if not diverged:
+            assert np.abs(act - tr.action).max() <= 1e-5
+        # continue from the ORACLE's state and distribution is not possible on the device; stop at divergence
+        if diverged:
+            break
+        state = mod.step_state(state[None], tr.action[None])[0].astype(np.float32).astype(np.float64)
+    assert checked >= 3, f"only {checked} iterations had decisive elite gaps"
+    p.close()
+
+
+def test_closed_loop_cheetah_runs_forward():
+    """Behavioural sanity of the whole stack on the ground-truth model: 40 closed-loop plan steps with production
+    (Philox) noise move the HalfCheetah forward (cost = -velocity)."""
+    from icem_b200 import workloads
+    from icem_b200.planner import Planner
+    s = workloads.planner_settings("halfcheetah_gt_n4096", scale_population=1 / 8)
+    p = Planner(s)
+    p.begin_rollout()
+    state = workloads.start_state("halfcheetah_gt_n4096")
+    x0 = state[0]
+    for _ in range(40):
+        a = p.plan(state)
+        state, _, _ = p.sim_step(state, a)
+    assert np.isfinite(state).all()
+    assert state[0] - x0 > 1.0, state[0] - x0          # > 0.5 m/s on average over 2 s
+    p.close()
