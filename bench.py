@@ -31,7 +31,7 @@ if ROOT not in sys.path:
 METRIC = "candidate trajs rolled-out/sec at h=30"
 UNIT = "trajectories/s"
 DEFAULT_WORKLOAD = "humanoid_standup_gt_n16384"
-DEFAULT_SHARD_WORKLOAD = "humanoid_standup_gt_shard32768"
+DEFAULT_SHARD_WORKLOAD = DEFAULT_WORKLOAD     # weak scaling: the same 16384 trajectories per GPU at every N
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -273,7 +273,7 @@ def run_ours(args):
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         from oracle import cpu_bench
-        cpu = cpu_bench.run(name, cores=1, budget_s=12.0)
+        cpu = cpu_bench.run(name, cores=os.cpu_count() or 1, budget_s=15.0)
 
     if rank == 0:
         line = {
@@ -306,7 +306,7 @@ def run_reference(args):
     from oracle import cpu_bench
     name = args.workload or (DEFAULT_WORKLOAD if world == 1 else DEFAULT_SHARD_WORKLOAD)
     cores = os.cpu_count() or 1
-    res = cpu_bench.run(name, cores=cores, budget_s=20.0, steps=args.steps, warmup=min(args.warmup, 1))
+    res = cpu_bench.run(name, cores=cores, budget_s=25.0, steps=max(1, min(args.steps, 3)), warmup=0)
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -224,8 +224,8 @@ class HalfCheetahMaybeWithPosition(_DeviceSimEnv):
                  device=0, **kwargs):
         self.penalise_flipping = penalise_flipping
         self.exclude_pos = exclude_current_positions_from_observation
-        n = 17 if self.exclude_pos else 18
-        self.observation_space = Box(-np.inf * np.ones(n), np.inf * np.ones(n))
+        self.observation_space = Box(-np.inf * np.ones(17 if self.exclude_pos else 18),
+                                     np.inf * np.ones(17 if self.exclude_pos else 18))
         super().__init__(name=name, device=device, **kwargs)
         self.store_init_arguments(locals())
 

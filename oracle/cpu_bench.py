@@ -78,40 +78,38 @@ def build_oracle(name, population=None):
     return cfg, model, cost, start
 
 
-def run(name, cores=1, budget_s=15.0, steps=None, warmup=1):
+def run(name, cores=1, budget_s=15.0, steps=None, warmup=0):
     """Time the oracle port on a bounded sample of workload `name`.  Returns the `cpu_baseline` object."""
     cores = max(1, int(cores))
     cfg_full, model, cost, start = build_oracle(name)
     n_full = cfg_full.num_simulated_trajectories
     roll = _ParallelRollout(model, cores)
     try:
-        # calibrate on a small population (also warms the worker pool)
-        n_cal = min(n_full, max(64, 16 * cores))
-        cfg, _, _, _ = build_oracle(name, population=n_cal)
-        orc = ICemOracle(cfg, roll, cost)
-        np.random.seed(0)
-        orc.beginning_of_rollout()
-        orc.get_action(start)
+        # calibrate the per-trajectory rollout cost on a small batch (also warms the worker pool)
+        rs = np.random.RandomState(0)
+        n_cal = max(32, 8 * cores)
+        acts = rs.uniform(cfg_full.action_low, cfg_full.action_high, (n_cal, cfg_full.horizon, cfg_full.act_dim))
+        roll(start, acts[: 2 * cores])
         t0 = time.perf_counter()
-        orc.get_action(start)
-        per_traj = (time.perf_counter() - t0) / trajectories_per_plan_step(cfg, first_step=False)
-        want_steps = steps if steps else 2
-        per_step_budget = budget_s / (want_steps + warmup)
-        n_fit = int(per_step_budget / max(per_traj, 1e-9) / max(cfg_full.opt_iterations * 0.7, 1))
-        n_sample = int(min(n_full, max(n_cal, n_fit)))
+        roll(start, acts)
+        per_traj = (time.perf_counter() - t0) / n_cal
+        want_steps = int(steps) if steps else 2
+        ratio = trajectories_per_plan_step(cfg_full, first_step=False) / float(n_full)    # trajectories per unit N
+        n_fit = int(budget_s / (want_steps + warmup) / max(per_traj * ratio, 1e-12))
+        n_sample = int(min(n_full, max(2 * cfg_full.elites_size + 4, n_fit)))
         cfg, _, _, _ = build_oracle(name, population=n_sample)
         orc = ICemOracle(cfg, roll, cost)
         np.random.seed(0)
         orc.beginning_of_rollout()
+        orc.get_action(start) if warmup else None
         state = start
         t_sum, n_traj = 0.0, 0
-        for i in range(warmup + want_steps):
+        for i in range(want_steps):
+            first = (i == 0 and not warmup)
             t0 = time.perf_counter()
             orc.get_action(state)
-            dt = time.perf_counter() - t0
-            if i >= warmup:
-                t_sum += dt
-                n_traj += trajectories_per_plan_step(cfg, first_step=False)
+            t_sum += time.perf_counter() - t0
+            n_traj += trajectories_per_plan_step(cfg, first_step=first)
         value = n_traj / t_sum
     finally:
         roll.close()

@@ -1,0 +1,4 @@
+set -x
+nvidia-smi -L
+python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29711 bench.py --gpus 2 --steps 10 --warmup 3 2>&1 | tail -3

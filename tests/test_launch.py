@@ -1,0 +1,78 @@
+"""CPU plumbing tests (T7 / BASELINE configs[0]): the reference's UNCHANGED icem/main.py runs in this container
+
+  (a) with its own MpcICem + GroundTruthModel over the oracle-backed stand-in HalfCheetah (proves shims, settings
+      hierarchy, registries, checkpoints), and
+  (b) through icem_b200.launch with controller "mpc-icem-b200" + forward model "CudaGroundTruthModel": every layer up
+      to the C ABI is exercised and, because this container has no GPU, icem_create must fail LOUDLY (no CPU fallback).
+
+Both need /root/reference (absent on the GPU box -> skipped there)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from oracle import ref_loader
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.skipif(not ref_loader.reference_available(), reason="reference sources not present")
+
+
+def _settings(tmp_path, **over):
+    s = {
+        "inherits_from": [],
+        "env": "HalfCheetah",
+        "env_params": {"exclude_current_positions_from_observation": True, "penalise_flipping": True},
+        "seed": 3,
+        "controller": "mpc-icem",
+        "controller_params": {
+            "horizon": 30, "num_simulated_trajectories": 16, "factor_decrease_num": 1.25,
+            "cost_along_trajectory": "sum", "do_visualize_plan": False, "verbose": False,
+            "action_sampler_params": {"alpha": 0.1, "elites_size": 4, "fraction_elites_reused": 0.3, "init_std": 0.5,
+                                      "keep_previous_elites": True, "shift_elites_over_time": True,
+                                      "use_mean_actions": True, "opt_iterations": 3, "noise_beta": 0.25}},
+        "forward_model": "GroundTruthModel", "forward_model_params": {},
+        "initial_controller": "none", "initial_controller_params": {}, "initial_number_of_rollouts": 0,
+        "number_of_rollouts": 1, "append_data": False, "append_data_eval": False, "training_iterations": 1,
+        "evaluation_rollouts": 0,
+        "rollout_params": {"render": False, "render_initial": False, "render_eval": False, "record": False,
+                           "only_final_reward": False, "use_env_states": True, "task_horizon": 2},
+        "checkpoints": {"load": False, "save": True, "save_every_n_iter": 1, "restart_every_n_iter": None},
+        "model_dir": str(tmp_path / "results"),
+    }
+    s.update(over)
+    path = tmp_path / "settings.json"
+    path.write_text(json.dumps(s))
+    return str(path)
+
+
+def test_reference_main_runs_unchanged_on_cpu(tmp_path):
+    """(a) reference controller + reference GroundTruthModel + oracle-backed env, 2 env steps."""
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from oracle import ref_loader, envs_np\n"
+        "ref_loader.install_reference(); envs_np.install()\n"
+        "import main; sys.argv=['main.py', %r]; main.main()\n" % (ROOT, _settings(tmp_path)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "iCEM using" in res.stdout                                  # controllers/icem.py:42-43
+    out = tmp_path / "results"
+    assert (out / "settings.json").exists()
+    assert (out / "checkpoints_latest").exists()
+
+
+def test_launcher_reaches_c_abi_and_fails_loudly_without_gpu(tmp_path):
+    """(b) the B200 plugin classes are resolved by the reference's registries and constructed by main.get_controllers;
+    without a CUDA device the C ABI refuses (never a silent CPU path)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this leg asserts the no-GPU failure mode")
+    path = _settings(tmp_path, controller="mpc-icem-b200", forward_model="CudaGroundTruthModel",
+                     forward_model_params={"num_parallel": 8})
+    res = subprocess.run([sys.executable, "-m", "icem_b200.launch", path, "--shims",
+                          os.path.join(ROOT, "oracle", "shims")], cwd=str(tmp_path), capture_output=True, text=True,
+                         timeout=600, env=dict(os.environ, PYTHONPATH=ROOT))
+    assert res.returncode != 0
+    assert "IcemError" in res.stderr and "cuda" in res.stderr.lower(), res.stderr[-2000:]
+    assert "MpcICemB200" in res.stderr or "controller.py" in res.stderr
