@@ -5,17 +5,22 @@
 // this is the repo's own soft-contact engine on the tables of icem_b200/robots.py, checked against the
 // independent float64 restatement oracle/articulated_np.py.  PARITY WITH MUJOCO IS UNPINNED.
 //
-// Per substep (frame_skip substeps per control step, control held), all in one warp:
-//   1. kinematics by tree level (lane = body): world rotation / position relative to the root origin O,
-//      motion axes S_j (Plucker [w; v_O]), body velocity v_b and velocity-product acceleration a_b
-//   2. floor contacts (lane = contact sphere): Hunt-Crossley normal force + capped viscous friction -> wrench
-//   3. recursive Newton-Euler bias: f_b = I_b a_b + v_b x* I_b v_b - f_ext, accumulated leaf -> root together
-//      with the composite inertias (lane = body, parents pull from children level by level)
-//   4. lane = dof: bias_j = S_j . f, row j of the composite-rigid-body mass matrix (kept in REGISTERS),
-//      applied torques (actuator gear, joint spring, limit spring-damper; springs/dampers implicit)
-//   5. (M + dt B + dt^2 K) qacc = rhs by an in-register Cholesky factorisation: column broadcasts with warp shuffles,
-//      forward substitution by shuffles, back substitution by warp reductions
-//   6. semi-implicit Euler; unit-quaternion update for a free root joint
+// Per substep (frame_skip substeps per control step, control held), all in one warp, data exchanged through a
+// per-warp shared-memory scratch and warp shuffles:
+//   1a. lane = body : transform of every body relative to its parent through its own joints (all bodies at once)
+//   1b. lane = body : compose parent x local down the tree, one tree level at a time (positions relative to the
+//                     root origin O so that fp32 keeps its precision far from the world origin)
+//   1c. lane = dof  : motion axes S_j (Plucker [w; v_O]) in world coordinates
+//   1d. lane = dof  : velocities and velocity-product accelerations as two pointer-doubling prefix sums along the
+//                     dof chains (log2(chain length) rounds instead of one round per tree level)
+//   2.  lane = contact sphere : floor contact force (Hunt-Crossley normal, capped viscous Coulomb friction) -> wrench
+//   3.  lane = body : spatial inertia about O and Newton-Euler force f_b = I a + v x* I v - f_ext;
+//       lane = (parent, component): leaf -> root accumulation of forces and composite inertias
+//   4.  lane = dof  : bias_j = S_j . f, applied torques (gear, spring, limit spring-damper), row j of the
+//                     composite-rigid-body mass matrix, kept in REGISTERS
+//   5.  (M + dt B + dt^2 K) qacc = rhs: in-register Cholesky (column broadcasts by shuffle), forward substitution by
+//       shuffles, back substitution on the transposed factor (transposed through shared memory)
+//   6.  semi-implicit Euler; unit-quaternion update for a free root joint
 #pragma once
 #include "common.cuh"
 
@@ -25,17 +30,25 @@ constexpr int kArtMaxBodies = 16;
 constexpr int kArtMaxDofs = 32;
 constexpr int kArtMaxContacts = 32;
 constexpr int kArtMaxChildren = 4;
+constexpr int kArtMaxDepth = 8;
+constexpr int kArtMaxLevelParents = 8;
+constexpr int kArtScanRounds = 5;
 enum { kSlide = 0, kHinge = 1, kFreeTrans = 2, kFreeRot = 3 };
 
 // POD model tables; built on the host (planner.cu: icem_set_articulated_model), copied to shared memory per CTA.
 struct ArtModel {
   int nb, nq, nv, nu, nc, nsub, max_depth, obs_offset;
   float dt, gravity, ctrl_limit, kc, cc, kv, mu, cdmax;
+  int scan_rounds, pad1, pad2, pad3;
   int b_parent[kArtMaxBodies], b_depth[kArtMaxBodies], b_dof_start[kArtMaxBodies], b_dof_count[kArtMaxBodies];
   int b_nchild[kArtMaxBodies], b_child[kArtMaxBodies][kArtMaxChildren];
   int b_con_start[kArtMaxBodies], b_con_count[kArtMaxBodies];
+  int b_last_dof[kArtMaxBodies];      // last dof on the path root -> body (-1: none)
+  int lvl_np[kArtMaxDepth], lvl_parent[kArtMaxDepth][kArtMaxLevelParents];   // bodies with children, per depth
   float b_pos[kArtMaxBodies][3], b_mass[kArtMaxBodies], b_com[kArtMaxBodies][3], b_inertia[kArtMaxBodies][6];
   int d_body[kArtMaxDofs], d_type[kArtMaxDofs], d_qadr[kArtMaxDofs], d_limited[kArtMaxDofs], d_act[kArtMaxDofs];
+  int d_vref[kArtMaxDofs];            // dof whose inclusive velocity sum is the velocity of the frame S_j is fixed in
+  int d_jump[kArtScanRounds][kArtMaxDofs];   // 2^r-th ancestor dof (-1: none): pointer-doubling prefix sums
   unsigned d_chain[kArtMaxDofs];      // bit c set: dof c is dof j or one of its ancestors
   float d_axis[kArtMaxDofs][3], d_anchor[kArtMaxDofs][3];
   float d_stiff[kArtMaxDofs], d_damp[kArtMaxDofs], d_arm[kArtMaxDofs], d_lo[kArtMaxDofs], d_hi[kArtMaxDofs];
@@ -55,22 +68,40 @@ __device__ __forceinline__ void matvec3(const float* R, const float* v, float* o
   const float z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
   o[0] = x; o[1] = y; o[2] = z;
 }
+__device__ __forceinline__ void matmul3(const float* A, const float* B, float* C) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) C[r * 3 + c] = A[r * 3] * B[c] + A[r * 3 + 1] * B[3 + c] + A[r * 3 + 2] * B[6 + c];
+}
 
 // padded strides of the per-warp arrays (odd strides: conflict-free when lane = row)
-constexpr int kSR = 9, kSP = 3, kS6 = 7, kSI = 11;
+constexpr int kSR = 9, kSP = 3, kS6 = 7, kSRec = 17;
 
 template <int NVMAX>
 struct Articulated {
   static constexpr int kWarpsPerCta = 8;
+  static constexpr int kLd = NVMAX + 1;           // row stride of the transposition buffer (odd for NVMAX even)
   struct Params {
     const ArtModel* model;   // device global memory
     int act_dim, nq, nv;
   };
+  // per-warp scratch layout (floats)
+  static constexpr int oState = 0;                                  // [64]  qpos, qvel
+  static constexpr int oO = 64;                                     // [4]   root origin (absolute)
+  static constexpr int oRb = oO + 4;                                // [16][9]
+  static constexpr int oPb = oRb + kArtMaxBodies * kSR;             // [16][3]
+  static constexpr int oRec = oPb + kArtMaxBodies * kSP;            // [16][17]  f(6) + composite inertia(10)
+  static constexpr int oSd = oRec + kArtMaxBodies * kSRec;          // [32][7]   S_j
+  static constexpr int oX = oSd + kArtMaxDofs * kS6;                // [32][7]   prefix sums of S qd
+  static constexpr int oY = oX + kArtMaxDofs * kS6;                 // [32][7]   prefix sums of (v x S) qd
+  static constexpr int oCw = oY + kArtMaxDofs * kS6;                // [32][7]   contact wrenches
+  static constexpr int oEnd = oCw + kArtMaxContacts * kS6;
+  // the transposition buffer of the Cholesky factor aliases Rb.. (dead by then)
+  static_assert(NVMAX * kLd <= oEnd - oRb, "transposition buffer does not fit");
+
   __host__ __device__ static int cta_floats(const Params&) { return (int)((sizeof(ArtModel) + 3) / 4); }
-  __host__ __device__ static int warp_floats(const Params&) {
-    return 64 /*state*/ + 4 /*O*/ + kArtMaxBodies * (kSR + kSP + 2 * kS6 /*v,a*/ + kS6 /*f*/ + kSI) +
-           kArtMaxDofs * kS6 /*S*/ + kArtMaxContacts * kS6 /*contact wrenches*/ + kArtMaxDofs /*qacc*/;
-  }
+  __host__ __device__ static int warp_floats(const Params&) { return oEnd; }
   __host__ __device__ static int state_dim(const Params& p) { return p.nq + p.nv; }
 
   __device__ static void cta_init(const Params& p, float* s) {
@@ -80,169 +111,213 @@ struct Articulated {
   }
 
   const ArtModel* M;
-  float *st, *O, *Rb, *pb, *vb, *ab, *fb, *Ib, *Sd, *cw, *acc;
+  float* w;     // per-warp scratch
 
   __device__ void bind(const Params&, const float* cta, float* warp) {
     M = reinterpret_cast<const ArtModel*>(cta);
-    st = warp;
-    O = st + 64;
-    Rb = O + 4;
-    pb = Rb + kArtMaxBodies * kSR;
-    vb = pb + kArtMaxBodies * kSP;
-    ab = vb + kArtMaxBodies * kS6;
-    fb = ab + kArtMaxBodies * kS6;
-    Ib = fb + kArtMaxBodies * kS6;
-    Sd = Ib + kArtMaxBodies * kSI;
-    cw = Sd + kArtMaxDofs * kS6;
-    acc = cw + kArtMaxContacts * kS6;
+    w = warp;
   }
   __device__ void reset(const float* start_state) {
     const int n = M->nq + M->nv;
-    for (int i = lane_id(); i < n; i += 32) st[i] = start_state[i];
+    for (int i = lane_id(); i < n; i += 32) w[oState + i] = start_state[i];
     __syncwarp();
   }
-  __device__ float obs(int i) const { return st[i + M->obs_offset]; }
+  __device__ float obs(int i) const { return w[oState + i + M->obs_offset]; }
   __device__ void export_state(float* out) const {
     const int n = M->nq + M->nv;
-    for (int i = lane_id(); i < n; i += 32) out[i] = st[i];
+    for (int i = lane_id(); i < n; i += 32) out[i] = w[oState + i];
   }
   __device__ void step(const float* ctrl) {
     for (int s = 0; s < M->nsub; ++s) substep(ctrl);
+  }
+
+  // inclusive prefix sum of 6-vectors along the dof chains: X[j] <- sum_{i in chain(j)} X[i]   (lane = dof)
+  __device__ __forceinline__ void chain_scan(float* X, float* x, int j, bool is_dof) {
+    const ArtModel& m = *M;
+    for (int r = 0; r < m.scan_rounds; ++r) {
+      float t[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const int src = is_dof ? m.d_jump[r][j] : -1;
+      if (src >= 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) t[i] = X[src * kS6 + i];
+      }
+      __syncwarp();
+      if (src >= 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { x[i] += t[i]; X[j * kS6 + i] = x[i]; }
+      }
+      __syncwarp();
+    }
   }
 
   // ------------------------------------------------------------------------------------------------------------
   __device__ void substep(const float* ctrl) {
     const ArtModel& m = *M;
     const int lane = lane_id();
-    const float* q = st;
-    const float* qd = st + m.nq;
+    const float* q = w + oState;
+    const float* qd = w + oState + m.nq;
+    float* O = w + oO;
+    float* Rb = w + oRb;
+    float* pb = w + oPb;
+    float* rec = w + oRec;
+    float* Sd = w + oSd;
+    float* X = w + oX;
+    float* Y = w + oY;
+    float* cw = w + oCw;
     const float dt = m.dt;
-
-    // ---- 1. kinematics, velocities, velocity-product accelerations: lane = body, level by level -------------
     const bool is_body = lane < m.nb;
+    const bool is_dof = lane < m.nv;
     const int depth = is_body ? m.b_depth[lane] : 1 << 20;
-    float R[9], p[3], v[6], a[6];
+
+    // ---- 1a. lane = body: transform relative to the parent through the body's own joints -----------------------
+    float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f}, p[3] = {0.f, 0.f, 0.f};
+    if (is_body) {
+      const int b = lane;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = 0.f;
+      for (int i = 0; i < 3; ++i) p[i] = m.b_pos[b][i];
+      const int j0 = m.b_dof_start[b], j1 = j0 + m.b_dof_count[b];
+      for (int j = j0; j < j1; ++j) {
+        const int t = m.d_type[j];
+        if (t == kFreeTrans) {                 // free joint (root): 3 translations + ball, S directly in world
+          const int qa = m.d_qadr[j];
+          p[0] = q[qa]; p[1] = q[qa + 1]; p[2] = q[qa + 2];
+          const float qw = q[qa + 3], x = q[qa + 4], y = q[qa + 5], z = q[qa + 6];
+          R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - qw * z); R[2] = 2.f * (x * z + qw * y);
+          R[3] = 2.f * (x * y + qw * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - qw * x);
+          R[6] = 2.f * (x * z - qw * y); R[7] = 2.f * (y * z + qw * x); R[8] = 1.f - 2.f * (x * x + y * y);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) p[i] = 0.f;
+          for (int k = 0; k < 3; ++k) {
+            float* St = Sd + (j + k) * kS6;
+            float* Sr = Sd + (j + 3 + k) * kS6;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { v[i] = 0.f; a[i] = 0.f; }
-    for (int L = 0; L <= m.max_depth; ++L) {
-      if (depth == L) {
-        const int b = lane, par = m.b_parent[b];
-        bool rel = true;          // positions already relative to O?
-        if (par >= 0) {
-          float Rp[9];
-#pragma unroll
-          for (int i = 0; i < 9; ++i) Rp[i] = Rb[par * kSR + i];
-          float off[3];
-          matvec3(Rp, m.b_pos[b], off);
-#pragma unroll
-          for (int i = 0; i < 3; ++i) p[i] = pb[par * kSP + i] + off[i];
-#pragma unroll
-          for (int i = 0; i < 9; ++i) R[i] = Rp[i];
-#pragma unroll
-          for (int i = 0; i < 6; ++i) { v[i] = vb[par * kS6 + i]; a[i] = ab[par * kS6 + i]; }
+            for (int i = 0; i < 6; ++i) { St[i] = 0.f; Sr[i] = 0.f; }
+            St[3 + k] = 1.f;
+            Sr[0] = R[k]; Sr[1] = R[3 + k]; Sr[2] = R[6 + k];   // column k of R, anchored at O (= p)
+          }
+          j += 5;
+          continue;
+        }
+        float ax[3];
+        matvec3(R, m.d_axis[j], ax);
+        const float qj = q[m.d_qadr[j]];
+        float* loc = Sd + j * kS6;             // local record (axis, anchor) in the parent frame, finished in 1c
+        loc[0] = ax[0]; loc[1] = ax[1]; loc[2] = ax[2];
+        if (t == kSlide) {
+          loc[3] = loc[4] = loc[5] = 0.f;
+          p[0] += ax[0] * qj; p[1] += ax[1] * qj; p[2] += ax[2] * qj;
         } else {
-          R[0] = R[4] = R[8] = 1.f;
+          float an[3];
+          matvec3(R, m.d_anchor[j], an);
+          an[0] += p[0]; an[1] += p[1]; an[2] += p[2];
+          loc[3] = an[0]; loc[4] = an[1]; loc[5] = an[2];
+          float sn, cs;
+          sincosf(qj, &sn, &cs);
+          const float C = 1.f - cs;
+          const float Rj[9] = {cs + ax[0] * ax[0] * C, ax[0] * ax[1] * C - ax[2] * sn, ax[0] * ax[2] * C + ax[1] * sn,
+                               ax[1] * ax[0] * C + ax[2] * sn, cs + ax[1] * ax[1] * C, ax[1] * ax[2] * C - ax[0] * sn,
+                               ax[2] * ax[0] * C - ax[1] * sn, ax[2] * ax[1] * C + ax[0] * sn, cs + ax[2] * ax[2] * C};
+          float Rn[9];
+          matmul3(Rj, R, Rn);
 #pragma unroll
-          for (int i = 0; i < 3; ++i) p[i] = m.b_pos[b][i];     // absolute until the first rotation
-          a[5] = m.gravity;                                      // gravity as a fictitious base acceleration
-          rel = false;
+          for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+          float dp[3] = {p[0] - an[0], p[1] - an[1], p[2] - an[2]}, rp[3];
+          matvec3(Rj, dp, rp);
+          p[0] = an[0] + rp[0]; p[1] = an[1] + rp[1]; p[2] = an[2] + rp[2];
         }
-        const int j0 = m.b_dof_start[b], j1 = j0 + m.b_dof_count[b];
-        for (int j = j0; j < j1; ++j) {
-          const int t = m.d_type[j];
-          if (t == kFreeTrans) {                 // free joint: 3 translations + ball, one block
-            const int qa = m.d_qadr[j];
-            if (!rel) { O[0] = q[qa]; O[1] = q[qa + 1]; O[2] = q[qa + 2]; p[0] = p[1] = p[2] = 0.f; rel = true; }
-            const float w = q[qa + 3], x = q[qa + 4], y = q[qa + 5], z = q[qa + 6];
-            R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - w * z); R[2] = 2.f * (x * z + w * y);
-            R[3] = 2.f * (x * y + w * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - w * x);
-            R[6] = 2.f * (x * z - w * y); R[7] = 2.f * (y * z + w * x); R[8] = 1.f - 2.f * (x * x + y * y);
-            float wl[3] = {qd[j + 3], qd[j + 4], qd[j + 5]}, ww[3];
-            matvec3(R, wl, ww);
-            const float vl[3] = {qd[j], qd[j + 1], qd[j + 2]};
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              float* St = Sd + (j + k) * kS6;
-              float* Sr = Sd + (j + 3 + k) * kS6;
-#pragma unroll
-              for (int i = 0; i < 6; ++i) { St[i] = 0.f; Sr[i] = 0.f; }
-              St[3 + k] = 1.f;
-              Sr[0] = R[k]; Sr[1] = R[3 + k]; Sr[2] = R[6 + k];   // column k of R, anchored at O
-            }
-            // translations: (v xm [0;e_k]) qd_k = [0 ; w x v_lin]; ball: sum_k (v_after xm S_k) qd_k =
-            // (v + v_trans) xm [ww;0] = [w x ww ; (v_lin_prev + v_lin) x ww]   (v = 0 for a root joint)
-            float c[3], vt[3] = {v[3] + vl[0], v[4] + vl[1], v[5] + vl[2]};
-            cross3(v, vl, c);
-            a[3] += c[0]; a[4] += c[1]; a[5] += c[2];
-            cross3(v, ww, c);
-            a[0] += c[0]; a[1] += c[1]; a[2] += c[2];
-            cross3(vt, ww, c);
-            a[3] += c[0]; a[4] += c[1]; a[5] += c[2];
-            v[0] += ww[0]; v[1] += ww[1]; v[2] += ww[2];
-            v[3] += vl[0]; v[4] += vl[1]; v[5] += vl[2];
-            j += 5;
-            continue;
-          }
-          float ax[3];
-          matvec3(R, m.d_axis[j], ax);
-          float S[6];
-          const float qj = q[m.d_qadr[j]], qdj = qd[j];
-          if (t == kSlide) {
-            S[0] = S[1] = S[2] = 0.f; S[3] = ax[0]; S[4] = ax[1]; S[5] = ax[2];
-            p[0] += ax[0] * qj; p[1] += ax[1] * qj; p[2] += ax[2] * qj;
-          } else {
-            if (!rel) { O[0] = p[0]; O[1] = p[1]; O[2] = p[2]; p[0] = p[1] = p[2] = 0.f; rel = true; }
-            float an[3];
-            matvec3(R, m.d_anchor[j], an);
-            an[0] += p[0]; an[1] += p[1]; an[2] += p[2];
-            // Rodrigues rotation about ax by qj
-            float sn, cs;
-            sincosf(qj, &sn, &cs);
-            const float C = 1.f - cs;
-            const float Rj[9] = {cs + ax[0] * ax[0] * C, ax[0] * ax[1] * C - ax[2] * sn, ax[0] * ax[2] * C + ax[1] * sn,
-                                 ax[1] * ax[0] * C + ax[2] * sn, cs + ax[1] * ax[1] * C, ax[1] * ax[2] * C - ax[0] * sn,
-                                 ax[2] * ax[0] * C - ax[1] * sn, ax[2] * ax[1] * C + ax[0] * sn, cs + ax[2] * ax[2] * C};
-            float Rn[9];
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-              for (int c = 0; c < 3; ++c)
-                Rn[r * 3 + c] = Rj[r * 3] * R[c] + Rj[r * 3 + 1] * R[3 + c] + Rj[r * 3 + 2] * R[6 + c];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) R[i] = Rn[i];
-            float dp[3] = {p[0] - an[0], p[1] - an[1], p[2] - an[2]}, rp[3];
-            matvec3(Rj, dp, rp);
-            p[0] = an[0] + rp[0]; p[1] = an[1] + rp[1]; p[2] = an[2] + rp[2];
-            S[0] = ax[0]; S[1] = ax[1]; S[2] = ax[2];
-            cross3(an, ax, S + 3);                 // velocity at O of a rotation about the anchored axis
-          }
-          // a += (v xm S) qd ; v += S qd      ([w1;v1] xm [w2;v2] = [w1 x w2 ; w1 x v2 + v1 x w2])
-          float c1[3], c2[3], c3[3];
-          cross3(v, S, c1);
-          cross3(v, S + 3, c2);
-          cross3(v + 3, S, c3);
-          a[0] += c1[0] * qdj; a[1] += c1[1] * qdj; a[2] += c1[2] * qdj;
-          a[3] += (c2[0] + c3[0]) * qdj; a[4] += (c2[1] + c3[1]) * qdj; a[5] += (c2[2] + c3[2]) * qdj;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            v[i] += S[i] * qdj;
-            Sd[j * kS6 + i] = S[i];
-          }
-        }
-        if (!rel) { O[0] = p[0]; O[1] = p[1]; O[2] = p[2]; p[0] = p[1] = p[2] = 0.f; }
+      }
+      if (depth == 0) {      // root: world frame; everything downstream is relative to O = root frame origin
+        O[0] = p[0]; O[1] = p[1]; O[2] = p[2];
+        p[0] = p[1] = p[2] = 0.f;
 #pragma unroll
         for (int i = 0; i < 9; ++i) Rb[b * kSR + i] = R[i];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) pb[b * kSP + i] = p[i];
+        for (int i = 0; i < 3; ++i) pb[b * kSP + i] = 0.f;
+      }
+    }
+    __syncwarp();
+
+    // ---- 1b. compose down the tree, one level at a time ----------------------------------------------------------
+    for (int L = 1; L <= m.max_depth; ++L) {
+      if (depth == L) {
+        const int b = lane, par = m.b_parent[b];
+        float Rp[9], Rn[9], off[3];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { vb[b * kS6 + i] = v[i]; ab[b * kS6 + i] = a[i]; }
+        for (int i = 0; i < 9; ++i) Rp[i] = Rb[par * kSR + i];
+        matmul3(Rp, R, Rn);
+        matvec3(Rp, p, off);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { R[i] = Rn[i]; Rb[b * kSR + i] = Rn[i]; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { p[i] = pb[par * kSP + i] + off[i]; pb[b * kSP + i] = p[i]; }
       }
       __syncwarp();
     }
+
+    // ---- 1c. lane = dof: motion axis in world coordinates ---------------------------------------------------------
+    float S[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float qdj = 0.f;
+    int dtype = -1;
+    if (is_dof) {
+      const int j = lane;
+      dtype = m.d_type[j];
+      qdj = qd[j];
+      if (dtype == kSlide || dtype == kHinge) {
+        const int par = m.b_parent[m.d_body[j]];
+        float ax[3] = {Sd[j * kS6], Sd[j * kS6 + 1], Sd[j * kS6 + 2]};
+        float an[3] = {Sd[j * kS6 + 3], Sd[j * kS6 + 4], Sd[j * kS6 + 5]};
+        if (par >= 0) {
+          float axw[3], anw[3];
+          matvec3(Rb + par * kSR, ax, axw);
+          matvec3(Rb + par * kSR, an, anw);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) { ax[i] = axw[i]; an[i] = anw[i] + pb[par * kSP + i]; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) an[i] -= O[i];
+        }
+        if (dtype == kSlide) {
+          S[3] = ax[0]; S[4] = ax[1]; S[5] = ax[2];
+        } else {
+          S[0] = ax[0]; S[1] = ax[1]; S[2] = ax[2];
+          cross3(an, ax, S + 3);               // velocity at O of a rotation about the anchored axis
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) S[i] = Sd[j * kS6 + i];
+      }
+    }
+    __syncwarp();
+    // ---- 1d. velocities and velocity-product accelerations: prefix sums along the dof chains ---------------------
+    float xv[6], ya[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xv[i] = S[i] * qdj;
+    if (is_dof) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { Sd[lane * kS6 + i] = S[i]; X[lane * kS6 + i] = xv[i]; }
+    }
+    __syncwarp();
+    chain_scan(X, xv, lane, is_dof);           // X[j] = velocity of the body right after joint j
+    {
+      float vf[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const int ref = is_dof ? m.d_vref[lane] : -1;
+      if (ref >= 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) vf[i] = X[ref * kS6 + i];
+      }
+      // (v xm S) qd      [w1;v1] xm [w2;v2] = [w1 x w2 ; w1 x v2 + v1 x w2]
+      float c1[3], c2[3], c3[3];
+      cross3(vf, S, c1);
+      cross3(vf, S + 3, c2);
+      cross3(vf + 3, S, c3);
+      ya[0] = c1[0] * qdj; ya[1] = c1[1] * qdj; ya[2] = c1[2] * qdj;
+      ya[3] = (c2[0] + c3[0]) * qdj; ya[4] = (c2[1] + c3[1]) * qdj; ya[5] = (c2[2] + c3[2]) * qdj;
+      if (is_dof) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Y[lane * kS6 + i] = ya[i];
+      }
+    }
+    __syncwarp();
+    chain_scan(Y, ya, lane, is_dof);           // Y[j] = velocity-product acceleration of the body after joint j
 
     // ---- 2. floor contacts: lane = contact sphere ---------------------------------------------------------------
     if (lane < m.nc) {
@@ -253,7 +328,12 @@ struct Articulated {
       const float pen = m.c_radius[lane] - (O[2] + x[2]);
       float wr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (pen > 0.f) {
-        const float* vv = vb + b * kS6;
+        const int e = m.b_last_dof[b];
+        float vv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (e >= 0) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) vv[i] = X[e * kS6 + i];
+        }
         float u[3];
         cross3(vv, x, u);
         u[0] += vv[3]; u[1] += vv[4]; u[2] += vv[5];
@@ -274,6 +354,13 @@ struct Articulated {
     // ---- 3. spatial inertia about O, Newton-Euler force: lane = body ---------------------------------------------
     if (is_body) {
       const int b = lane;
+      const int e = m.b_last_dof[b];
+      float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (e >= 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { v[i] = X[e * kS6 + i]; a[i] = Y[e * kS6 + i]; }
+      }
+      a[5] += m.gravity;                       // gravity as a fictitious base acceleration
       const float mass = m.b_mass[b];
       float c[3];
       matvec3(R, m.b_com[b], c);
@@ -282,11 +369,7 @@ struct Articulated {
       const float* I6 = m.b_inertia[b];
       const float Im[9] = {I6[0], I6[3], I6[4], I6[3], I6[1], I6[5], I6[4], I6[5], I6[2]};
       float T[9];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cc2 = 0; cc2 < 3; ++cc2)
-          T[r * 3 + cc2] = R[r * 3] * Im[cc2] + R[r * 3 + 1] * Im[3 + cc2] + R[r * 3 + 2] * Im[6 + cc2];
+      matmul3(R, Im, T);
       float Io[6];   // xx yy zz xy xz yz about O
       const float c2 = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
       Io[0] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2] + mass * (c2 - c[0] * c[0]);
@@ -322,62 +405,43 @@ struct Articulated {
       for (int k = c0; k < c1; ++k)
 #pragma unroll
         for (int i = 0; i < 6; ++i) f[i] -= cw[k * kS6 + i];
+      float* r = rec + b * kSRec;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) fb[b * kS6 + i] = f[i];
-      float* Ic = Ib + b * kSI;
-      Ic[0] = mass; Ic[1] = h[0]; Ic[2] = h[1]; Ic[3] = h[2];
+      for (int i = 0; i < 6; ++i) r[i] = f[i];
+      r[6] = mass; r[7] = h[0]; r[8] = h[1]; r[9] = h[2];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) Ic[4 + i] = Io[i];
+      for (int i = 0; i < 6; ++i) r[10 + i] = Io[i];
     }
     __syncwarp();
 
-    // ---- 3b. leaf -> root accumulation of forces and composite inertias (parents pull) -----------------------
+    // ---- 3b. leaf -> root accumulation, lane = (parent body, record component) ----------------------------------
     for (int L = m.max_depth - 1; L >= 0; --L) {
-      if (depth == L && m.b_nchild[lane] > 0) {
-        const int b = lane;
-        float f[6], Ic[10];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) f[i] = fb[b * kS6 + i];
-#pragma unroll
-        for (int i = 0; i < 10; ++i) Ic[i] = Ib[b * kSI + i];
-        for (int k = 0; k < m.b_nchild[b]; ++k) {
-          const int ch = m.b_child[b][k];
-#pragma unroll
-          for (int i = 0; i < 6; ++i) f[i] += fb[ch * kS6 + i];
-#pragma unroll
-          for (int i = 0; i < 10; ++i) Ic[i] += Ib[ch * kSI + i];
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) fb[b * kS6 + i] = f[i];
-#pragma unroll
-        for (int i = 0; i < 10; ++i) Ib[b * kSI + i] = Ic[i];
+      const int items = m.lvl_np[L] * 16;
+      for (int it = lane; it < items; it += 32) {
+        const int b = m.lvl_parent[L][it >> 4], comp = it & 15;
+        float acc = rec[b * kSRec + comp];
+        for (int k = 0; k < m.b_nchild[b]; ++k) acc += rec[m.b_child[b][k] * kSRec + comp];
+        rec[b * kSRec + comp] = acc;
       }
       __syncwarp();
     }
 
     // ---- 4. lane = dof: bias, applied torque, mass-matrix row -------------------------------------------------
     const int j = lane;
-    const bool is_dof = j < m.nv;
     float row[NVMAX];
 #pragma unroll
     for (int c = 0; c < NVMAX; ++c) row[c] = 0.f;
     float rhs = 0.f;
-    float qdj = 0.f;
     if (is_dof) {
-      const int b = m.d_body[j];
-      float S[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) S[i] = Sd[j * kS6 + i];
+      const float* r = rec + m.d_body[j] * kSRec;
       float bias = 0.f;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) bias += S[i] * fb[b * kS6 + i];
-      qdj = qd[j];
-      const int t = m.d_type[j];
+      for (int i = 0; i < 6; ++i) bias += S[i] * r[i];
       float tau = 0.f;
       const int act = m.d_act[j];
       if (act >= 0) tau = m.d_gear[j] * fminf(fmaxf(ctrl[act], -m.ctrl_limit), m.ctrl_limit);
       float keff = 0.f, beff = m.d_damp[j];
-      if (t == kSlide || t == kHinge) {
+      if (dtype == kSlide || dtype == kHinge) {
         const float qj = q[m.d_qadr[j]];
         keff = m.d_stiff[j];
         tau -= keff * qj;
@@ -392,15 +456,14 @@ struct Articulated {
       rhs = tau - (beff + dt * keff) * qdj - bias;
       const float diag_add = m.d_arm[j] + dt * beff + dt * dt * keff;
       // F = Ic_body(j) S_j
-      const float* Ic = Ib + b * kSI;
-      const float mass = Ic[0];
-      const float h[3] = {Ic[1], Ic[2], Ic[3]};
+      const float mass = r[6];
+      const float h[3] = {r[7], r[8], r[9]};
       float hv[3], hw[3], F[6];
       cross3(h, S + 3, hv);
       cross3(h, S, hw);
-      F[0] = Ic[4] * S[0] + Ic[7] * S[1] + Ic[8] * S[2] + hv[0];
-      F[1] = Ic[7] * S[0] + Ic[5] * S[1] + Ic[9] * S[2] + hv[1];
-      F[2] = Ic[8] * S[0] + Ic[9] * S[1] + Ic[6] * S[2] + hv[2];
+      F[0] = r[10] * S[0] + r[13] * S[1] + r[14] * S[2] + hv[0];
+      F[1] = r[13] * S[0] + r[11] * S[1] + r[15] * S[2] + hv[1];
+      F[2] = r[14] * S[0] + r[15] * S[1] + r[12] * S[2] + hv[2];
       F[3] = mass * S[3] - hw[0];
       F[4] = mass * S[4] - hw[1];
       F[5] = mass * S[5] - hw[2];
@@ -413,12 +476,10 @@ struct Articulated {
         }
       }
 #pragma unroll
-      for (int c = 0; c < NVMAX; ++c)
-        if (c == j) row[c] += diag_add;
+      for (int c = 0; c < NVMAX; ++c) row[c] += (c == j) ? diag_add : 0.f;
     } else {
 #pragma unroll
-      for (int c = 0; c < NVMAX; ++c)
-        if (c == j) row[c] = 1.f;           // padding rows: identity
+      for (int c = 0; c < NVMAX; ++c) row[c] = (c == j) ? 1.f : 0.f;      // padding rows: identity
     }
 
     // ---- 5. in-register Cholesky (lane i holds row i, columns 0..i) ---------------------------------------------
@@ -433,10 +494,10 @@ struct Articulated {
         row[c] = fmaf(-row[k], lck, row[c]);
       }
     }
-    float dinv = 1.f;
+    float diag = 1.f;
 #pragma unroll
-    for (int c = 0; c < NVMAX; ++c)
-      if (c == lane) dinv = 1.f / row[c];
+    for (int c = 0; c < NVMAX; ++c) diag = (c == lane) ? row[c] : diag;
+    const float dinv = 1.f / diag;
     // forward substitution  L y = rhs
     float y = rhs;
 #pragma unroll
@@ -444,26 +505,37 @@ struct Articulated {
       const float yk = __shfl_sync(0xffffffffu, y * dinv, k);
       y = (lane == k) ? yk : ((lane > k) ? fmaf(-row[k], yk, y) : y);
     }
+    // transpose the factor through shared memory: lane i then holds column i of L (= row i of L^T)
+    float* Lt = w + oRb;
+    __syncwarp();
+    if (lane < NVMAX) {
+#pragma unroll
+      for (int c = 0; c < NVMAX; ++c) Lt[lane * kLd + c] = row[c];
+    }
+    __syncwarp();
+    if (lane < NVMAX) {
+#pragma unroll
+      for (int c = 0; c < NVMAX; ++c) row[c] = Lt[c * kLd + lane];     // row[c] = L[c][lane], nonzero for c >= lane
+    }
     // back substitution  L^T x = y
-    float xs = 0.f;
+    float xs = y;
 #pragma unroll
     for (int k = NVMAX - 1; k >= 0; --k) {
-      const float s = warp_sum((lane > k) ? row[k] * xs : 0.f);
-      if (lane == k) xs = (y - s) * dinv;
+      const float xk = __shfl_sync(0xffffffffu, xs * dinv, k);
+      xs = (lane == k) ? xk : ((lane < k) ? fmaf(-row[k], xk, xs) : xs);
     }
 
     // ---- 6. semi-implicit Euler -----------------------------------------------------------------------------------
     __syncwarp();
-    float* qw = st;
-    float* qdw = st + m.nq;
+    float* qw = w + oState;
+    float* qdw = w + oState + m.nq;
     if (is_dof) {
       const float qdn = qdj + dt * xs;
       qdw[j] = qdn;
-      const int t = m.d_type[j];
-      if (t != kFreeRot) qw[m.d_qadr[j]] += dt * qdn;
+      if (dtype != kFreeRot) qw[m.d_qadr[j]] += dt * qdn;
     }
     __syncwarp();
-    if (is_dof && m.d_type[j] == kFreeRot && (j == 0 || m.d_type[j - 1] != kFreeRot)) {
+    if (is_dof && dtype == kFreeRot && (j == 0 || m.d_type[j - 1] != kFreeRot)) {
       const int qa = m.d_qadr[j];
       const float w0 = qdw[j], w1 = qdw[j + 1], w2 = qdw[j + 2];
       const float n = sqrtf(w0 * w0 + w1 * w1 + w2 * w2);

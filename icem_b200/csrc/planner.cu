@@ -708,6 +708,37 @@ int icem_set_articulated_model(icem_planner_t* p, const icem_articulated_model_t
         throw InvalidArg("free joint must be 3 translation dofs followed by 3 rotation dofs");
     j += 5;
   }
+  // derived tables: chain ends, per-level parents, pointer-doubling jumps, frame-velocity references
+  if (m.max_depth >= kArtMaxDepth) throw InvalidArg("kinematic tree deeper than 8 levels");
+  for (int b = 0; b < m.nb; ++b) {
+    m.b_last_dof[b] = m.b_dof_count[b] > 0 ? m.b_dof_start[b] + m.b_dof_count[b] - 1
+                                            : (m.b_parent[b] >= 0 ? m.b_last_dof[m.b_parent[b]] : -1);
+    if (m.b_nchild[b] > 0) {
+      int& np = m.lvl_np[m.b_depth[b]];
+      if (np >= kArtMaxLevelParents) throw InvalidArg("more than 8 bodies with children on one tree level");
+      m.lvl_parent[m.b_depth[b]][np++] = b;
+    }
+  }
+  int max_chain = 1;
+  for (int j = 0; j < m.nv; ++j) {
+    m.d_jump[0][j] = a->dof_parent[j];
+    max_chain = std::max(max_chain, __builtin_popcount(m.d_chain[j]));
+    if (m.d_type[j] == kFreeRot) {
+      int last = j;
+      while (last + 1 < m.nv && m.d_type[last + 1] == kFreeRot && m.d_body[last + 1] == m.d_body[j]) ++last;
+      m.d_vref[j] = last;
+    } else {
+      m.d_vref[j] = a->dof_parent[j];
+    }
+  }
+  for (int r = 1; r < kArtScanRounds; ++r)
+    for (int j = 0; j < m.nv; ++j) {
+      const int mid = m.d_jump[r - 1][j];
+      m.d_jump[r][j] = mid >= 0 ? m.d_jump[r - 1][mid] : -1;
+    }
+  m.scan_rounds = 0;
+  while ((1 << m.scan_rounds) < max_chain) ++m.scan_rounds;
+  if (m.scan_rounds > kArtScanRounds) throw InvalidArg("dof chain longer than 32");
   int prev_body = -1;
   for (int c = 0; c < m.nc; ++c) {
     const int b = a->con_body[c];
