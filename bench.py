@@ -232,7 +232,9 @@ def run_ours(args):
     if ctrl is not None:
         obs = env.reset()
         state = env.get_GT_state()
-        ctrl.beginning_of_rollout(observation=obs, state=state, mode="train")
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):      # keep stdout to the ONE JSON line (the reference prints here)
+            ctrl.beginning_of_rollout(observation=obs, state=state, mode="train")
         t_sum = 0.0
         for i in range(args.warmup + args.steps):
             t0 = time.perf_counter()

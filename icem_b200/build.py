@@ -24,19 +24,22 @@ def _newest_input():
     return max(os.path.getmtime(p) for p in paths)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None, defines=()):
+    """`out` / `defines`: A/B variants of the library for kernel experiments (loaded with ICEM_B200_LIB=<path>)."""
     os.makedirs(LIB_DIR, exist_ok=True)
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _newest_input():
-        return LIB_PATH
+    target = out or LIB_PATH
+    if not force and os.path.exists(target) and os.path.getmtime(target) >= _newest_input():
+        return target
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", LIB_PATH, "-ldl"]
+    cmd = ([nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + sources()
+           + ["-o", target, "-ldl"])
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed building libicem_b200.so")
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB_PATH
+    return target
 
 
 if __name__ == "__main__":

@@ -81,25 +81,36 @@ constexpr int kSR = 9, kSP = 3, kS6 = 7, kSRec = 17;
 template <int NVMAX>
 struct Articulated {
   static constexpr int kWarpsPerCta = 8;
+#ifndef ICEM_ART_MIN_CTAS
+#define ICEM_ART_MIN_CTAS 3
+#endif
+#ifndef ICEM_ART_LOCKSTEP
+#define ICEM_ART_LOCKSTEP 1
+#endif
+  static constexpr int kMinCtasPerSm = NVMAX <= 24 ? ICEM_ART_MIN_CTAS : 2;   // register cap: 85 / 128 per thread
+  static constexpr bool kCtaLockstep = ICEM_ART_LOCKSTEP != 0;
   static constexpr int kLd = NVMAX + 1;           // row stride of the transposition buffer (odd for NVMAX even)
   struct Params {
     const ArtModel* model;   // device global memory
-    int act_dim, nq, nv;
+    int act_dim, nq, nv, nb, nc;
   };
-  // per-warp scratch layout (floats)
-  static constexpr int oState = 0;                                  // [64]  qpos, qvel
-  static constexpr int oO = 64;                                     // [4]   root origin (absolute)
-  static constexpr int oRb = oO + 4;                                // [16][9]
-  static constexpr int oPb = oRb + kArtMaxBodies * kSR;             // [16][3]
-  static constexpr int oRec = oPb + kArtMaxBodies * kSP;            // [16][17]  f(6) + composite inertia(10)
-  static constexpr int oSd = oRec + kArtMaxBodies * kSRec;          // [32][7]   S_j
-  static constexpr int oX = oSd + kArtMaxDofs * kS6;                // [32][7]   prefix sums of S qd
-  static constexpr int oY = oX + kArtMaxDofs * kS6;                 // [32][7]   prefix sums of (v x S) qd
-  static constexpr int oCw = oY + kArtMaxDofs * kS6;                // [32][7]   contact wrenches
-  static constexpr int oEnd = oCw + kArtMaxContacts * kS6;
+  // per-warp scratch layout (floats): compile-time offsets for this size class (NBMAX bodies, NVMAX dofs, NCMAX
+  // contact spheres) -- runtime-computed offsets cost ~7 % in address arithmetic
+  static constexpr int NBMAX = NVMAX <= 12 ? 8 : kArtMaxBodies;
+  static constexpr int NCMAX = NVMAX <= 12 ? 16 : kArtMaxContacts;
+  static constexpr int oO = 64;                               // [0,64): qpos, qvel
+  static constexpr int oRb = oO + 4;                          // [nb][9]
+  static constexpr int oPb = oRb + NBMAX * kSR;               // [nb][3]
+  static constexpr int oRec = oPb + NBMAX * kSP;              // [nb][17]  f(6) + composite inertia(10)
+  static constexpr int oSd = oRec + NBMAX * kSRec;            // [nv][7]   S_j
+  static constexpr int oX = oSd + NVMAX * kS6;                // [nv][7]   prefix sums of S qd
+  static constexpr int oY = oX + NVMAX * kS6;                 // [nv][7]   prefix sums of (v x S) qd
+  static constexpr int oCw = oY + NVMAX * kS6;                // [nc][7]   contact wrenches
+  static constexpr int oEnd0 = oCw + NCMAX * kS6;
   // the transposition buffer of the Cholesky factor aliases Rb.. (dead by then)
-  static_assert(NVMAX * kLd <= oEnd - oRb, "transposition buffer does not fit");
-
+  static constexpr int oEnd = oEnd0 > oRb + NVMAX * kLd ? oEnd0 : oRb + NVMAX * kLd;
+  __host__ __device__ static bool fits(int nb, int nv, int nc) { return nb <= NBMAX && nv <= NVMAX && nc <= NCMAX; }
+  static constexpr int oState = 0;
   __host__ __device__ static int cta_floats(const Params&) { return (int)((sizeof(ArtModel) + 3) / 4); }
   __host__ __device__ static int warp_floats(const Params&) { return oEnd; }
   __host__ __device__ static int state_dim(const Params& p) { return p.nq + p.nv; }

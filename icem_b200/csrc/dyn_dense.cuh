@@ -8,6 +8,8 @@ namespace icem {
 
 struct DenseTanh {
   static constexpr int kWarpsPerCta = 8;
+  static constexpr int kMinCtasPerSm = 2;
+  static constexpr bool kCtaLockstep = false;
   struct Params {
     int obs_dim, act_dim;
     const float* w_obs;   // [obs_dim][obs_dim] row-major (device)

@@ -211,6 +211,7 @@ template <int NVMAX>
 static typename Articulated<NVMAX>::Params art_params(icem_planner* p) {
   typename Articulated<NVMAX>::Params q{};
   q.model = p->art.model; q.act_dim = p->art.act_dim; q.nq = p->art.nq; q.nv = p->art.nv;
+  q.nb = p->art.nb; q.nc = p->art.nc;
   return q;
 }
 
@@ -244,9 +245,9 @@ static void launch_rollout_dyn(icem_planner* p, const RolloutArgs& a, int rows_m
       break;
     case ICEM_DYN_HALFCHEETAH:
     case ICEM_DYN_HUMANOID_STANDUP:
-      if (p->art.nv <= 12)
+      if (Articulated<12>::fits(p->art.nb, p->art.nv, p->art.nc))
         launch_rollout<Articulated<12>, kSample, kRollout>(p, a, art_params<12>(p), rows_max);
-      else if (p->art.nv <= 24)
+      else if (Articulated<24>::fits(p->art.nb, p->art.nv, p->art.nc))
         launch_rollout<Articulated<24>, kSample, kRollout>(p, a, art_params<24>(p), rows_max);
       else
         launch_rollout<Articulated<32>, kSample, kRollout>(p, a, art_params<32>(p), rows_max);
@@ -397,9 +398,9 @@ static void advance_dyn(icem_planner* p, float* state, const float* action, floa
       break;
     case ICEM_DYN_HALFCHEETAH:
     case ICEM_DYN_HUMANOID_STANDUP:
-      if (p->art.nv <= 12)
+      if (Articulated<12>::fits(p->art.nb, p->art.nv, p->art.nc))
         launch_advance<Articulated<12>>(p, art_params<12>(p), state, action, next_state, obs_out, obs_dim);
-      else if (p->art.nv <= 24)
+      else if (Articulated<24>::fits(p->art.nb, p->art.nv, p->art.nc))
         launch_advance<Articulated<24>>(p, art_params<24>(p), state, action, next_state, obs_out, obs_dim);
       else
         launch_advance<Articulated<32>>(p, art_params<32>(p), state, action, next_state, obs_out, obs_dim);
@@ -753,7 +754,7 @@ int icem_set_articulated_model(icem_planner_t* p, const icem_articulated_model_t
   p->art_model.alloc(1);
   ICEM_CUDA(cudaMemcpy(p->art_model.p, &m, sizeof m, cudaMemcpyHostToDevice));
   p->art.model = p->art_model.p;
-  p->art.act_dim = p->d; p->art.nq = m.nq; p->art.nv = m.nv;
+  p->art.act_dim = p->d; p->art.nq = m.nq; p->art.nv = m.nv; p->art.nb = m.nb; p->art.nc = m.nc;
   p->state_dim = m.nq + m.nv;
   if (p->obs_dim <= 0) p->obs_dim = p->state_dim - m.obs_offset;
   p->model_ready = true;

@@ -108,7 +108,7 @@ __device__ __forceinline__ void fill_normals(float* dst, int count, uint32_t gro
 }
 
 template <class Dyn, bool kSample, bool kRollout>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(Dyn::kWarpsPerCta * 32, Dyn::kMinCtasPerSm)
 rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Params dp) {
   extern __shared__ __align__(128) float smem[];
   const int warps = blockDim.x >> 5;
@@ -129,14 +129,17 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
   float* s_warp0 = s_dyn + ((Dyn::cta_floats(dp) + 3) & ~3);
   // ---- per-warp ----
   const int tile_floats = a.stride;                    // 16-B multiple
+  // the sampler's normal-draw scratch (z) is dead once the tile is built: it aliases the dynamics scratch
   const int z_floats = kSample ? ((sc.white ? 0 : d * zs) + 3) & ~3 : 0;
+  const int dyn_floats = (Dyn::warp_floats(dp) + 3) & ~3;
+  const int scratch_floats = z_floats > dyn_floats ? z_floats : dyn_floats;
   const int ntile = kSample ? 1 : 2;                   // loads are double-buffered
-  const int warp_floats = ntile * tile_floats + z_floats + ((Dyn::warp_floats(dp) + 3) & ~3) + 4;
+  const int warp_floats = ntile * tile_floats + scratch_floats + 4;
   float* w_base = s_warp0 + (size_t)warp * warp_floats;
   float* w_tile = w_base;
   float* w_z = w_tile + ntile * tile_floats;
-  float* w_dyn = w_z + z_floats;
-  uint64_t* w_bar = reinterpret_cast<uint64_t*>(w_dyn + ((Dyn::warp_floats(dp) + 3) & ~3));   // 2 x 8 B
+  float* w_dyn = w_z;
+  uint64_t* w_bar = reinterpret_cast<uint64_t*>(w_dyn + scratch_floats);   // 2 x 8 B
 
   if (kSample && !sc.white)
     for (int i = threadIdx.x; i < h * K2; i += blockDim.x) s_G[(i / K2) * gs + (i % K2)] = sc.G[i];
@@ -158,22 +161,35 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
 
   const StepState ss = *a.ss;
   const int n_rows = a.n_fresh_local + ((a.iteration == 0 && ss.has_prev_elites) ? a.n_shift_local : 0);
-  const int warp_global = blockIdx.x * warps + warp;
-  const int warp_stride = gridDim.x * warps;
+  // rows are dealt to CTAs in equal contiguous blocks (every SM gets the same number of trajectories +-1), and
+  // round-robin to the warps inside a CTA
+  const int cta_lo = (int)((long long)n_rows * blockIdx.x / gridDim.x);
+  const int cta_hi = (int)((long long)n_rows * (blockIdx.x + 1) / gridDim.x);
   const uint32_t tile_bytes = (uint32_t)tile_floats * 4u;
   Dyn dyn;
   dyn.bind(dp, s_dyn, w_dyn);
 
   if (!kSample) {   // prologue of the TMA load pipeline
-    if (warp_global < n_rows && lane == 0) {
+    if (cta_lo + warp < cta_hi && lane == 0) {
       mbar_expect_tx(&w_bar[0], tile_bytes);
-      tma_load_1d(w_tile, a.actions + (size_t)warp_global * a.stride, tile_bytes, &w_bar[0]);
+      tma_load_1d(w_tile, a.actions + (size_t)(cta_lo + warp) * a.stride, tile_bytes, &w_bar[0]);
     }
   }
 
+  // Dyn::kCtaLockstep: every warp of the CTA makes the same number of trips and meets at a CTA barrier before each
+  // control step, so the 8 warps run the (large, fully unrolled) dynamics code at the same time and share
+  // instruction-cache lines; warps whose row is past the end only take part in the barriers.
   int it = 0;
-  for (int row = warp_global; row < n_rows; row += warp_stride, ++it) {
+  for (int base = cta_lo; base < cta_hi; base += warps, ++it) {
+    const int row = base + warp;
+    const bool active = row < cta_hi;
+    if (!active && !Dyn::kCtaLockstep) break;
     float* tile = w_tile;
+    if (!active) {
+      if (kRollout)
+        for (int t = 0; t < h; ++t) __syncthreads();
+      continue;
+    }
     if (kSample) {
       const bool shifted = row >= a.n_fresh_local;
       // global trajectory index: fresh rows are contiguous per rank, shifted rows follow N_i
@@ -237,8 +253,8 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
       // consume buffer (it&1); prefetch the next row into the other buffer
       const int buf = it & 1;
       tile = w_tile + buf * tile_floats;
-      const int nxt = row + warp_stride;
-      if (nxt < n_rows && lane == 0) {
+      const int nxt = row + warps;
+      if (nxt < cta_hi && lane == 0) {
         mbar_expect_tx(&w_bar[buf ^ 1], tile_bytes);
         tma_load_1d(w_tile + (buf ^ 1) * tile_floats, a.actions + (size_t)nxt * a.stride, tile_bytes,
                     &w_bar[buf ^ 1]);
@@ -251,6 +267,7 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
       dyn.reset(a.start_state);
       float total = (cc.reduce == 1) ? INFINITY : 0.f;
       for (int t = 0; t < h; ++t) {
+        if (Dyn::kCtaLockstep) __syncthreads();
         const float* act = tile + t * d;
         const float c = step_cost(cc, dyn, act, d);
         if (cc.reduce == 0) total += c;
@@ -271,8 +288,9 @@ inline size_t rollout_smem_bytes(const SamplerConst& sc, const typename Dyn::Par
   const int h = sc.h, d = sc.d, hd = h * d, K2 = 2 * sc.K, gs = K2 + 1;
   size_t f = ((h * gs + 3) & ~3) + 2 * ((hd + 3) & ~3) + 2 * ((d + 3) & ~3) + ((Dyn::cta_floats(dp) + 3) & ~3);
   const int z_floats = kSample ? ((sc.white ? 0 : d * gs) + 3) & ~3 : 0;
+  const int dyn_floats = (Dyn::warp_floats(dp) + 3) & ~3;
   const int ntile = kSample ? 1 : 2;
-  const size_t warp_floats = (size_t)ntile * stride + z_floats + ((Dyn::warp_floats(dp) + 3) & ~3) + 4;
+  const size_t warp_floats = (size_t)ntile * stride + (z_floats > dyn_floats ? z_floats : dyn_floats) + 4;
   return (f + warps * warp_floats) * sizeof(float);
 }
 
