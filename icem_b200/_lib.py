@@ -90,6 +90,7 @@ SIGNATURES = {
     "icem_comm_get_unique_id": (C.c_int, [C.c_char_p]),
     "icem_comm_init": (C.c_int, [_H, C.c_char_p]),
     "icem_bench_device": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, _F, _F, _I]),
+    "icem_bench_op": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _F]),
 }
 
 _lib = None

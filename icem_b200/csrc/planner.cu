@@ -1162,4 +1162,57 @@ int icem_bench_device(icem_planner_t* p, int32_t steps, int32_t warmup, int32_t 
   ICEM_API_END
 }
 
+int icem_bench_op(icem_planner_t* p, int32_t op, int32_t n, int32_t reps, int32_t flush_l2, float* ms_avg) {
+  ICEM_API_BEGIN
+  if (!p || !ms_avg) throw InvalidArg("null argument");
+  if (n < p->k || reps < 1 || op < 0 || op > 2) throw InvalidArg("bad n / reps / op");
+  require_model(p);
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  DevBuf<float> d_act, d_cost;
+  d_act.alloc((size_t)n * p->stride);
+  d_cost.alloc(n);
+  const size_t flush_bytes = 256u << 20;
+  if (flush_l2 && p->flush.n != flush_bytes) p->flush.alloc(flush_bytes);
+  reset_distribution(p);
+  write_step_in(p, nullptr);
+  ICEM_CUDA(cudaMemcpyAsync(p->step_in.p, p->h_in, sizeof(StepState), cudaMemcpyHostToDevice, p->stream));
+  RolloutArgs a{};
+  a.n_fresh_local = n; a.n_fresh_global = n; a.stride = p->stride;
+  a.actions = d_act.p; a.costs = d_cost.p; a.mean = p->mean.p; a.std = p->stdv.p;
+  a.prev_elites = p->elite_actions[0].p;
+  a.start_state = start_state_dev(p);
+  a.ss = step_state_dev(p);
+  a.seed_lo = (uint32_t)p->cfg.seed; a.seed_hi = (uint32_t)(p->cfg.seed >> 32);
+  SelectArgs s{};
+  s.n_fresh_local = n; s.n_fresh_global = n; s.k = p->k; s.stride = p->stride;
+  s.costs = d_cost.p; s.actions = d_act.p; s.ss = a.ss; s.cand = p->cand.p; s.ticket = p->ticket.p;
+  RefitArgs r = refit_args(p, 0);
+  r.n_keep = 0; r.n_fresh_global = n; r.local_actions = d_act.p; r.local_n_fresh = n; r.local_offset = 0;
+  r.world = 1; r.rec_keys = nullptr; r.last_iteration = 0;
+  if (op == 2) {   // costs and actions to select from
+    launch_rollout_dyn<true, true>(p, a, n);
+  }
+  double tot = 0;
+  for (int it = 0; it < reps + 3; ++it) {
+    if (flush_l2) ICEM_CUDA(cudaMemsetAsync(p->flush.p, it & 0xff, flush_bytes, p->stream));
+    ICEM_CUDA(cudaEventRecord(p->ev_a, p->stream));
+    if (op == 0) launch_rollout_dyn<true, false>(p, a, n);
+    else if (op == 1) launch_rollout_dyn<true, true>(p, a, n);
+    else {
+      select_kernel<<<select_grid(p, n), kSelectThreads, (size_t)p->k * sizeof(unsigned long long), p->stream>>>(s, r, 1);
+      ICEM_CUDA(cudaGetLastError());
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    ICEM_CUDA(cudaEventRecord(p->ev_b, p->stream));
+    ICEM_CUDA(cudaStreamSynchronize(p->stream));
+    float ms = 0;
+    ICEM_CUDA(cudaEventElapsedTime(&ms, p->ev_a, p->ev_b));
+    if (it >= 3) tot += ms;
+  }
+  *ms_avg = (float)(tot / reps);
+  reset_distribution(p);
+  ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  ICEM_API_END
+}
+
 }  // extern "C"

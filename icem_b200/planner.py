@@ -251,6 +251,13 @@ class Planner:
         check(self._lib.icem_comm_init(self._h, C.create_string_buffer(unique_id, _lib.UNIQUE_ID_BYTES)))
 
     # ---- bench --------------------------------------------------------------------------------
+    def bench_op(self, op, n, reps=20, flush_l2=True):
+        """Average launch duration (ms) of one kernel in isolation: op 0 sampler, 1 fused rollout, 2 select+refit."""
+        ms = C.c_float()
+        check(self._lib.icem_bench_op(self._h, {"sample": 0, "fused": 1, "select": 2}.get(op, op), int(n), int(reps),
+                                      int(bool(flush_l2)), C.byref(ms)))
+        return ms.value
+
     def bench_device(self, steps, warmup, flush_l2=True):
         tot, roll, n = C.c_float(), C.c_float(), C.c_int32()
         check(self._lib.icem_bench_device(self._h, steps, warmup, int(bool(flush_l2)), C.byref(tot), C.byref(roll),

@@ -203,6 +203,14 @@ int icem_comm_init(icem_planner_t* p, const char id[ICEM_UNIQUE_ID_BYTES]);
 int icem_bench_device(icem_planner_t* p, int32_t steps, int32_t warmup, int32_t flush_l2, float* total_ms,
                       float* rollout_ms, int32_t* rollout_launches);
 
+/* Time ONE kernel of the plan step in isolation on `n` trajectories (production Philox noise), `reps` launches after
+ * 3 warm-ups, CUDA events on the planner's stream; *ms_avg = average launch duration.
+ *   op 0: sampler only (colored-noise synthesis + clip -> actions[n][h*d] in HBM; controllers/icem.py:61-82)
+ *   op 1: fused sample -> rollout -> cost (one CEM iteration's dominant kernel)
+ *   op 2: elite selection + refit on n costs (controllers/icem.py:194-211)
+ * flush_l2 != 0 writes a 256 MiB buffer between launches. */
+int icem_bench_op(icem_planner_t* p, int32_t op, int32_t n, int32_t reps, int32_t flush_l2, float* ms_avg);
+
 #ifdef __cplusplus
 }
 #endif
