@@ -144,13 +144,19 @@ def build_controller(name, world, rank, device):
     """The reference-facing plugin object (MpcICemB200) on a stand-in env + CUDA model, like main.py builds them."""
     from icem_b200 import envs, workloads
     from icem_b200.controller import MpcICemB200
-    from icem_b200.models import CudaDenseTanhModel, CudaGroundTruthModel
+    from icem_b200.models import CudaDenseTanhModel, CudaGroundTruthModel, CudaMlpModel
     w = workloads.get_workload(name)
     st = dict(w["settings"])
     sampler = {k: st[k] for k in ("alpha", "elites_size", "opt_iterations", "init_std", "use_mean_actions",
                                   "keep_previous_elites", "shift_elites_over_time", "fraction_elites_reused",
                                   "noise_beta")}
-    if w["env"] is None:
+    if w.get("mlp"):
+        ws, bs = workloads.mlp_model_weights(*w["mlp"])
+        env = envs.MlpStandInEnv(name="mlp", act_dim=w["act_dim"], bound=w["bound"], cost=st["cost"],
+                                 obs_dim=st["obs_dim"], penalise_flipping=st.get("penalise_flipping", False),
+                                 mlp=(ws, bs))
+        model = CudaMlpModel(env=env, weights=ws, biases=bs)
+    elif w["env"] is None:
         wts = workloads.dense_model_weights(*w["dense"])
         env = envs.DenseStandInEnv(name="dense", act_dim=w["act_dim"], bound=w["bound"], cost=st["cost"],
                                    obs_dim=st["obs_dim"], penalise_flipping=st.get("penalise_flipping", False),
@@ -182,6 +188,8 @@ def run_ours(args):
     planner = Planner(s)
     if w.get("dense"):
         planner.set_dense_model(*workloads.dense_model_weights(*w["dense"]))
+    if w.get("mlp"):
+        planner.set_mlp_model(*workloads.mlp_model_weights(*w["mlp"]))
     if world > 1:
         from icem_b200.distributed import init_planner_comm
         init_planner_comm(planner)
@@ -224,6 +232,21 @@ def run_ours(args):
                 if world == 1 else None,
                 "algorithmic_bytes_per_trajectory": bytes_per_traj,
                 "note": "compute/latency-bound kernel (fp32 dynamics); HBM fraction reported as the contract asks"}
+    if w.get("mlp"):
+        # tensor-core rollout: FLOP roofline of mlp_rollout_kernel timed alone (sampler excluded)
+        od, ad, hid, _ = w["mlp"]
+        n0 = local_rows[0]
+        ms = planner.bench_op("rollout", n0, reps=10)
+        flops = 2.0 * (h - 1) * ((od + ad) * hid + hid * hid + hid * od) * n0
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1590.0) \
+            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
+        ach = flops / (ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
+                    "traffic": None, "peak_source": peak_src + " (bf16 burst: kernel timed alone)",
+                    "kernel": "mlp_rollout_kernel (tcgen05.mma, bf16 operands, fp32 accumulate in TMEM)",
+                    "kernel_ms_avg": ms, "kernel_rows": n0,
+                    "algorithmic_flops_per_trajectory": flops / n0,
+                    "note": "epilogue-bound: 2*H tanh + bf16 pack per trajectory-step on CUDA cores between MMAs"}
     planner.close()
 
     # ---- end to end through the plugin API with host buffers: `e2e` ------------------------------------
@@ -254,6 +277,8 @@ def run_ours(args):
         planner2 = Planner(s)
         if w.get("dense"):
             planner2.set_dense_model(*workloads.dense_model_weights(*w["dense"]))
+        if w.get("mlp"):
+            planner2.set_mlp_model(*workloads.mlp_model_weights(*w["mlp"]))
         from icem_b200.distributed import init_planner_comm
         init_planner_comm(planner2)
         planner2.begin_rollout()

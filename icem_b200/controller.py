@@ -71,6 +71,8 @@ class MpcICemB200(*_Bases):
             noise_beta=self.noise_beta, seed=seed, device=device, world_size=world_size, rank=rank))
         if spec.get("dense") is not None:
             self._planner.set_dense_model(*spec["dense"])
+        if spec.get("mlp") is not None:
+            self._planner.set_mlp_model(*spec["mlp"])
         if world_size > 1:
             from .distributed import init_planner_comm
             init_planner_comm(self._planner)

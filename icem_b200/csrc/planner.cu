@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "dyn_articulated.cuh"
 #include "dyn_dense.cuh"
+#include "mlp_rollout.cuh"
 #include "rollout.cuh"
 #include "select_refit.cuh"
 
@@ -49,6 +50,22 @@ struct DevBuf {
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
+};
+
+// sampler-only launches of the fused kernel (ICEM_DYN_MLP samples with it, then rolls out on the tensor cores)
+struct NoDyn {
+  static constexpr int kWarpsPerCta = 8;
+  static constexpr int kMinCtasPerSm = 2;
+  static constexpr bool kCtaLockstep = false;
+  struct Params { int act_dim; };
+  __host__ __device__ static int cta_floats(const Params&) { return 0; }
+  __host__ __device__ static int warp_floats(const Params&) { return 0; }
+  __device__ static void cta_init(const Params&, float*) {}
+  __device__ void bind(const Params&, const float*, float*) {}
+  __device__ void reset(const float*) {}
+  __device__ float obs(int) const { return 0.f; }
+  __device__ void step(const float*) {}
+  __device__ void export_state(float*) const {}
 };
 
 struct IterPlan {
@@ -105,6 +122,9 @@ struct icem_planner {
   bool model_ready = false;
   Articulated<32>::Params art{};      // Params is layout-identical for every NVMAX instantiation
   DevBuf<ArtModel> art_model;
+  MlpParams mlp{};
+  DevBuf<__nv_bfloat16> mlp_w1, mlp_w2, mlp_w3;
+  DevBuf<float> mlp_bias;
 
   // run state
   bool was_reset = false;
@@ -237,9 +257,33 @@ static void launch_rollout(icem_planner* p, const RolloutArgs& a, const typename
   g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
+static void launch_mlp(icem_planner* p, const RolloutArgs& a, int rows_max) {
+  const SamplerConst sc = sampler_const(p);
+  const CostConst cc = cost_const(p);
+  const size_t smem = mlp_smem_bytes(p->mlp.hidden);
+  static thread_local size_t configured = 0;
+  if (smem > configured) {
+    ICEM_CUDA(cudaFuncSetAttribute(mlp_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int tiles = (rows_max + kMlpTile - 1) / kMlpTile;
+  const int grid = std::max(1, std::min(tiles, p->sm_count));     // one resident CTA per SM (weights fill smem)
+  mlp_rollout_kernel<<<grid, kMlpTile, smem, p->stream>>>(a, sc, cc, p->mlp);
+  ICEM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
 template <bool kSample, bool kRollout>
 static void launch_rollout_dyn(icem_planner* p, const RolloutArgs& a, int rows_max) {
   switch (p->cfg.dynamics) {
+    case ICEM_DYN_MLP: {
+      if (kSample) {
+        NoDyn::Params np{p->d};
+        launch_rollout<NoDyn, true, false>(p, a, np, rows_max);
+      }
+      if (kRollout) launch_mlp(p, a, rows_max);
+      break;
+    }
     case ICEM_DYN_DENSE_TANH:
       launch_rollout<DenseTanh, kSample, kRollout>(p, a, p->dense, rows_max);
       break;
@@ -393,6 +437,11 @@ static void launch_advance(icem_planner* p, const typename Dyn::Params& dp, floa
 static void advance_dyn(icem_planner* p, float* state, const float* action, float* next_state, float* obs_out,
                         int obs_dim) {
   switch (p->cfg.dynamics) {
+    case ICEM_DYN_MLP:
+      mlp_advance_kernel<<<1, 256, 0, p->stream>>>(p->mlp, state, action, next_state, obs_out, obs_dim);
+      ICEM_CUDA(cudaGetLastError());
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      break;
     case ICEM_DYN_DENSE_TANH:
       launch_advance<DenseTanh>(p, p->dense, state, action, next_state, obs_out, obs_dim);
       break;
@@ -594,7 +643,7 @@ int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
 
   if (cfg->dynamics == ICEM_DYN_HALFCHEETAH || cfg->dynamics == ICEM_DYN_HUMANOID_STANDUP) {
     p->state_dim = 0;   // known once icem_set_articulated_model provides the tables
-  } else if (cfg->dynamics == ICEM_DYN_DENSE_TANH) {
+  } else if (cfg->dynamics == ICEM_DYN_DENSE_TANH || cfg->dynamics == ICEM_DYN_MLP) {
     p->state_dim = 0;   // known once the model is set
   } else {
     throw Unsupported("dynamics id not supported by this build");
@@ -762,9 +811,41 @@ int icem_set_articulated_model(icem_planner_t* p, const icem_articulated_model_t
   ICEM_API_END
 }
 
-int icem_set_mlp_model(icem_planner_t*, int32_t, const int32_t*, const float* const*, const float* const*) {
-  icem::g_last_error = "ICEM_DYN_MLP is not available in this build";
-  return ICEM_ERR_UNSUPPORTED;
+int icem_set_mlp_model(icem_planner_t* p, int32_t n_layers, const int32_t* dims, const float* const* weights,
+                       const float* const* biases) {
+  ICEM_API_BEGIN
+  if (!p || !dims || !weights || !biases) throw InvalidArg("null argument");
+  if (p->cfg.dynamics != ICEM_DYN_MLP) throw InvalidArg("planner was not created with ICEM_DYN_MLP");
+  if (n_layers != 3) throw Unsupported("the tensor-core rollout supports exactly two hidden layers (n_layers == 3)");
+  const int in = dims[0], H = dims[1], out = dims[3];
+  if (dims[2] != H || (H != 64 && H != 128 && H != 256))
+    throw Unsupported("hidden widths must be equal and one of 64, 128, 256");
+  if (out < 1 || out > kMlpOutPad) throw Unsupported("observation width must be in [1, 32]");
+  if (in != out + p->d || in > kMlpInPad) throw InvalidArg("input width must be obs_dim + act_dim <= 32");
+  for (int l = 0; l < 3; ++l)
+    if (!weights[l] || !biases[l]) throw InvalidArg("null layer parameters");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  auto pack = [](const float* w, int rows, int cols, int rows_pad, int K, DevBuf<__nv_bfloat16>& dst) {
+    std::vector<__nv_bfloat16> h((size_t)rows_pad * K, __float2bfloat16_rn(0.f));
+    for (int n = 0; n < rows; ++n)
+      for (int k = 0; k < cols; ++k) h[umma_pack_index(n, k, K)] = __float2bfloat16_rn(w[(size_t)n * cols + k]);
+    dst.alloc(h.size());
+    ICEM_CUDA(cudaMemcpy(dst.p, h.data(), h.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  };
+  pack(weights[0], H, in, H, kMlpInPad, p->mlp_w1);
+  pack(weights[1], H, H, H, H, p->mlp_w2);
+  pack(weights[2], out, H, kMlpOutPad, H, p->mlp_w3);
+  std::vector<float> b((size_t)2 * H + kMlpOutPad, 0.f);
+  for (int i = 0; i < H; ++i) { b[i] = biases[0][i]; b[H + i] = biases[1][i]; }
+  for (int i = 0; i < out; ++i) b[2 * H + i] = biases[2][i];
+  upload(p->mlp_bias, b);
+  p->mlp.obs_dim = out; p->mlp.act_dim = p->d; p->mlp.hidden = H;
+  p->mlp.w1 = p->mlp_w1.p; p->mlp.w2 = p->mlp_w2.p; p->mlp.w3 = p->mlp_w3.p; p->mlp.bias = p->mlp_bias.p;
+  p->state_dim = out;
+  if (p->obs_dim <= 0) p->obs_dim = out;
+  p->model_ready = true;
+  if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+  ICEM_API_END
 }
 
 int icem_begin_rollout(icem_planner_t* p) {
@@ -1165,7 +1246,7 @@ int icem_bench_device(icem_planner_t* p, int32_t steps, int32_t warmup, int32_t 
 int icem_bench_op(icem_planner_t* p, int32_t op, int32_t n, int32_t reps, int32_t flush_l2, float* ms_avg) {
   ICEM_API_BEGIN
   if (!p || !ms_avg) throw InvalidArg("null argument");
-  if (n < p->k || reps < 1 || op < 0 || op > 2) throw InvalidArg("bad n / reps / op");
+  if (n < p->k || reps < 1 || op < 0 || op > 3) throw InvalidArg("bad n / reps / op");
   require_model(p);
   ICEM_CUDA(cudaSetDevice(p->cfg.device));
   DevBuf<float> d_act, d_cost;
@@ -1189,7 +1270,7 @@ int icem_bench_op(icem_planner_t* p, int32_t op, int32_t n, int32_t reps, int32_
   RefitArgs r = refit_args(p, 0);
   r.n_keep = 0; r.n_fresh_global = n; r.local_actions = d_act.p; r.local_n_fresh = n; r.local_offset = 0;
   r.world = 1; r.rec_keys = nullptr; r.last_iteration = 0;
-  if (op == 2) {   // costs and actions to select from
+  if (op == 2 || op == 3) {   // costs / actions the timed kernel consumes
     launch_rollout_dyn<true, true>(p, a, n);
   }
   double tot = 0;
@@ -1198,6 +1279,7 @@ int icem_bench_op(icem_planner_t* p, int32_t op, int32_t n, int32_t reps, int32_
     ICEM_CUDA(cudaEventRecord(p->ev_a, p->stream));
     if (op == 0) launch_rollout_dyn<true, false>(p, a, n);
     else if (op == 1) launch_rollout_dyn<true, true>(p, a, n);
+    else if (op == 3) launch_rollout_dyn<false, true>(p, a, n);
     else {
       select_kernel<<<select_grid(p, n), kSelectThreads, (size_t)p->k * sizeof(unsigned long long), p->stream>>>(s, r, 1);
       ICEM_CUDA(cudaGetLastError());

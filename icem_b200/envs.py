@@ -126,6 +126,27 @@ class DenseStandInEnv(_EnvBase):
         pass
 
 
+class MlpStandInEnv(DenseStandInEnv):
+    """Environment whose true dynamics IS the MLP forward model (float64 host evaluation of one transition)."""
+
+    def __init__(self, *, name="mlp", act_dim, bound, cost, obs_dim, penalise_flipping=False, mlp=None, **kwargs):
+        super().__init__(name=name, act_dim=act_dim, bound=bound, cost=cost, obs_dim=obs_dim,
+                         penalise_flipping=penalise_flipping, **kwargs)
+        self.mlp = mlp
+
+    def step(self, action):
+        ws, bs = self.mlp
+        a = np.asarray(action, np.float64)
+        cost = float(self.cost_fn(self._obs, a, None))
+        x = np.concatenate([self._obs, a])
+        for l, (w, b) in enumerate(zip(ws, bs)):
+            x = np.asarray(w, np.float64) @ x + np.asarray(b, np.float64)
+            if l + 1 < len(ws):
+                x = np.tanh(x)
+        self._obs = self._obs + x
+        return self._obs.copy(), -cost, False, {}
+
+
 # ---- articulated ground-truth stand-ins --------------------------------------------------------------------------
 _ARTICULATED = {
     # name -> (dynamics id string, nq, nv, act_dim, ctrl bound, obs_dim (reference layout), reset noise)

@@ -66,6 +66,30 @@ class CudaDenseTanhModel(_FMBase):
         pass
 
 
+class CudaMlpModel(CudaDenseTanhModel):
+    """Dense MLP forward model rolled out on the tensor cores (csrc/mlp_rollout.cuh):
+    obs' = obs + W3 tanh(W2 tanh(W1 [obs, act] + b1) + b2) + b3.  The reference ships no learned model
+    (icem/models/__init__.py:5-8); this is the hook `forward_model_from_string` would resolve for one."""
+
+    def __init__(self, *, env, weights, biases, **kwargs):
+        _FMBase.__init__(self, env=env, **kwargs)
+        self.weights = [np.asarray(w, np.float32) for w in weights]
+        self.biases = [np.asarray(b, np.float32) for b in biases]
+        self.is_trained = True
+
+    def cuda_spec(self):
+        return dict(dynamics="mlp", dense=None, mlp=(self.weights, self.biases), obs_dim=self.weights[-1].shape[0])
+
+    def predict(self, *, observations, states, actions):
+        o = np.asarray(observations, np.float64)
+        x = np.concatenate([o, np.asarray(actions, np.float64)], axis=-1)
+        for l, (w, b) in enumerate(zip(self.weights, self.biases)):
+            x = x @ w.T.astype(np.float64) + b
+            if l + 1 < len(self.weights):
+                x = np.tanh(x)
+        return o + x, states, np.zeros(o.shape[:-1] + (1,))
+
+
 class CudaGroundTruthModel(_GTBase):
     """Ground-truth model of a device-simulated stand-in env (envs.py): the role of
     `ParallelGroundTruthModel` (icem/models/gt_par_model.py:17-100) with the worker pool replaced by the GPU."""

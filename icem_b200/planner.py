@@ -102,6 +102,19 @@ class Planner:
         b = f32(bias) if bias is not None else None
         check(self._lib.icem_set_dense_model(self._h, n, fptr(w_obs), fptr(w_act), fptr(b) if b is not None else None))
 
+    def set_mlp_model(self, weights, biases):
+        """Dense MLP forward model obs' = obs + W3 tanh(W2 tanh(W1 [obs, act] + b1) + b2) + b3 (icem_set_mlp_model);
+        `weights[l]` is [out_l, in_l] row-major."""
+        ws = [f32(w) for w in weights]
+        bs = [f32(b) for b in biases]
+        dims = np.ascontiguousarray([ws[0].shape[1]] + [w.shape[0] for w in ws], dtype=np.int32)
+        for l, (w, b) in enumerate(zip(ws, bs)):
+            if w.ndim != 2 or b.shape != (w.shape[0],) or (l and w.shape[1] != ws[l - 1].shape[0]):
+                raise ValueError("inconsistent MLP layer shapes")
+        wp = (C.POINTER(C.c_float) * len(ws))(*[fptr(w) for w in ws])
+        bp = (C.POINTER(C.c_float) * len(bs))(*[fptr(b) for b in bs])
+        check(self._lib.icem_set_mlp_model(self._h, len(ws), iptr(dims), wp, bp))
+
     def set_articulated_model(self, m, obs_offset=0):
         """Upload robots.CompiledModel tables (icem_set_articulated_model)."""
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
@@ -254,7 +267,7 @@ class Planner:
     def bench_op(self, op, n, reps=20, flush_l2=True):
         """Average launch duration (ms) of one kernel in isolation: op 0 sampler, 1 fused rollout, 2 select+refit."""
         ms = C.c_float()
-        check(self._lib.icem_bench_op(self._h, {"sample": 0, "fused": 1, "select": 2}.get(op, op), int(n), int(reps),
+        check(self._lib.icem_bench_op(self._h, {"sample": 0, "fused": 1, "select": 2, "rollout": 3}.get(op, op), int(n), int(reps),
                                       int(bool(flush_l2)), C.byref(ms)))
         return ms.value
 

@@ -12,6 +12,19 @@ _BLITZ = dict(alpha=0.1, elites_size=10, fraction_elites_reused=0.3, init_std=0.
               cost_along_trajectory="sum")
 
 
+def mlp_model_weights(obs_dim, act_dim, hidden, seed):
+    """Random-init 2-hidden-layer MLP (no checkpoint exists: the reference has no learned model):
+    ([W1, W2, W3], [b1, b2, b3]) with W_l [out, in]; scaled so that 12-step rollouts stay O(1)."""
+    rs = np.random.RandomState(seed)
+    dims = [obs_dim + act_dim, hidden, hidden, obs_dim]
+    ws, bs = [], []
+    for i in range(3):
+        ws.append((rs.randn(dims[i + 1], dims[i]) / np.sqrt(dims[i])).astype(np.float32))
+        bs.append((0.05 * rs.randn(dims[i + 1])).astype(np.float32))
+    ws[2] *= 0.3
+    return ws, bs
+
+
 def dense_model_weights(obs_dim, act_dim, seed):
     """Deterministic toy dense model (SURVEY Appendix C recipe)."""
     rs = np.random.RandomState(seed)
@@ -41,6 +54,12 @@ WORKLOADS = {
         settings=dict(_BLITZ, num_simulated_trajectories=4096, opt_iterations=5, noise_beta=0.25,
                       dynamics="dense_tanh", cost="halfcheetah", obs_dim=17, penalise_flipping=True),
         act_dim=6, bound=1.0, env=None, dense=(17, 6, 7)),
+    # BASELINE configs[3]: cheetah-sized learned MLP forward model (obs 18 + act 6 -> 256 -> 256 -> 18), h=12,
+    # N=65536: tensor-core rollout path
+    "mlp_cheetah_n65536": dict(
+        settings=dict(_BLITZ, horizon=12, num_simulated_trajectories=65536, opt_iterations=3, noise_beta=0.25,
+                      dynamics="mlp", cost="halfcheetah", obs_dim=18, penalise_flipping=True),
+        act_dim=6, bound=1.0, env=None, mlp=(18, 6, 256, 21)),
     "dense_tanh_humanoid_n16384": dict(
         settings=dict(_BLITZ, num_simulated_trajectories=16384, opt_iterations=3, noise_beta=2.0,
                       dynamics="dense_tanh", cost="humanoid_standup", obs_dim=47),
@@ -94,5 +113,5 @@ def start_state(name, seed=0):
         qpos = humanoid_standup_qpos0() + rs.uniform(-0.01, 0.01, 24)
         qvel = rs.uniform(-0.01, 0.01, 23)
         return np.concatenate([qpos, qvel])
-    obs_dim = w["dense"][0]
+    obs_dim = w["dense"][0] if w.get("dense") else w["mlp"][0]
     return 0.1 * rs.randn(obs_dim)

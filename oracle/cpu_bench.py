@@ -59,6 +59,9 @@ def build_oracle(name, population=None):
     if w.get("dense"):
         from oracle.dynamics_np import DenseTanhModel
         model = DenseTanhModel(*workloads.dense_model_weights(*w["dense"]))
+    elif w.get("mlp"):
+        from oracle.dynamics_np import MlpModel
+        model = MlpModel(*workloads.mlp_model_weights(*w["mlp"]))
     else:
         from oracle.articulated_np import make_model
         model = make_model(s.dynamics)

@@ -42,3 +42,46 @@ class DenseTanhModel:
             out[:, t] = obs
             obs = self.step(obs, actions[:, t])
         return out
+
+
+def bf16_round(x):
+    """Round float64/float32 values to the nearest bfloat16 (ties to even), returned as float64."""
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    u = a.view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32).astype(np.float64).reshape(a.shape)
+
+
+class MlpModel:
+    """obs' = obs + W3 tanh(W2 tanh(W1 [obs, act] + b1) + b2) + b3 with the tensor-core path's operand roundings
+    restated: weights, the layer-1 input and both hidden activations are rounded to bfloat16 (what csrc/
+    mlp_rollout.cuh feeds tcgen05.mma), products accumulate in >= fp32, biases and the state stay fp32/f64.
+    Not restated: the accumulation order inside the tensor core and tanh.approx (rel. error ~5e-4), so agreement
+    is at bf16 resolution, not bit level (tests/test_gpu_mlp.py states the tolerance)."""
+
+    def __init__(self, weights, biases):
+        self.w = [bf16_round(w) for w in weights]
+        self.b = [np.asarray(b, np.float32).astype(np.float64) for b in biases]
+        self.obs_dim = self.w[2].shape[0]
+        self.act_dim = self.w[0].shape[1] - self.obs_dim
+        self.state_dim = self.obs_dim
+
+    def step(self, obs, act):
+        x = bf16_round(np.concatenate([obs, act], axis=-1))
+        h1 = bf16_round(np.tanh(x @ self.w[0].T + self.b[0]))
+        h2 = bf16_round(np.tanh(h1 @ self.w[1].T + self.b[1]))
+        return obs + h2 @ self.w[2].T + self.b[2]
+
+    def observe(self, state):
+        return np.asarray(state, dtype=np.float64)
+
+    def rollout(self, start_state, actions):
+        p, h, _ = actions.shape
+        obs = np.broadcast_to(np.asarray(start_state, np.float32).astype(np.float64), (p, self.obs_dim)).copy()
+        out = np.empty((p, h, self.obs_dim))
+        for t in range(h):
+            out[:, t] = obs
+            if t + 1 < h:
+                obs = self.step(obs, np.asarray(actions[:, t], np.float32).astype(np.float64))
+                obs = obs.astype(np.float32).astype(np.float64)      # the device keeps the state in fp32
+        return out
