@@ -6,7 +6,9 @@
 //     obs' = obs + W3 tanh(W2 tanh(W1 [obs, act] + b1) + b2) + b3            (2 hidden layers of width H)
 // followed by the per-step cost on the PRE-action observation (controllers/abstract_controller.py:74-91).
 //
-// One CTA = one tile of 128 trajectories (thread r <-> trajectory row r <-> TMEM lane r).  The three weight
+// One CTA = one tile of 128 trajectories; 512 threads: thread (q, lane, g) with warp = 4 g + q owns trajectory row
+// r = 32 q + lane (TMEM lane r; a warp may only touch the lane quarter warp % 4) and every 4th 32-column chunk
+// of the hidden layer in the epilogues; the fp32 observation is replicated in the 4 threads of a row.  The three weight
 // matrices stay RESIDENT in shared memory as bf16 in the tcgen05 K-major no-swizzle core-matrix layout
 // ([n/8][k/8][n%8][k%8], 128-byte core matrices) for the whole kernel; per control step:
 //     X[128 x 32] (bf16, smem)  --tcgen05.mma M128 N=H K=16 x2-->  D[128 x H] fp32 in TMEM
@@ -23,6 +25,8 @@
 namespace icem {
 
 constexpr int kMlpTile = 128;     // trajectories per CTA tile (UMMA M)
+constexpr int kMlpColGroups = 4;  // threads per trajectory row: each takes every 4th 32-column chunk in the epilogues
+constexpr int kMlpThreads = kMlpTile * kMlpColGroups;   // 16 warps: 4 per scheduler hide the TMEM / MUFU latency
 constexpr int kMlpInPad = 32;     // padded input width (obs + act <= 32)
 constexpr int kMlpOutPad = 32;    // padded output width (obs <= 32)
 
@@ -109,7 +113,7 @@ inline size_t mlp_smem_bytes(int hidden) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMlpTile, 1)
+__global__ void __launch_bounds__(kMlpThreads, 1)
 mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int H = mp.hidden;
@@ -122,6 +126,8 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int q = warp & 3, g = warp >> 2;             // TMEM lane quarter, column group
+  const int r = q * 32 + (tid & 31);                 // trajectory row inside the tile
   const int h = sc.h, d = sc.d, od = mp.obs_dim;
 
   // ---- one-time: resident weights, barrier, TMEM ----
@@ -148,7 +154,7 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's 32 lanes
+  const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);      // this warp's 32 lanes
 
   const uint32_t idesc_h = umma_idesc_bf16(kMlpTile, H);
   const uint32_t idesc_o = umma_idesc_bf16(kMlpTile, kMlpOutPad);
@@ -157,10 +163,10 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
 
   const StepState ss = *a.ss;
   const int n_rows = a.n_fresh_local + ((a.iteration == 0 && ss.has_prev_elites) ? a.n_shift_local : 0);
-  unsigned char* rowA = reinterpret_cast<unsigned char*>(sA) + (size_t)(tid & 7) * 16;   // + (tid/8)*SBO + chunk*128
+  unsigned char* rowA = reinterpret_cast<unsigned char*>(sA) + (size_t)(r & 7) * 16;     // + (r/8)*SBO + chunk*128
 
   for (int tile0 = blockIdx.x * kMlpTile; tile0 < n_rows; tile0 += gridDim.x * kMlpTile) {
-    const int row = tile0 + tid;
+    const int row = tile0 + r;
     const bool valid = row < n_rows;
     float x[kMlpInPad];                      // [obs(od), act(d), 0...]: the fp32 state of this trajectory
 #pragma unroll
@@ -192,19 +198,21 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
       else total = c;
       if (t + 1 == h) break;                 // the final predicted state is never scored
 
-      // ---- X row -> smem (bf16, K-major core matrices), layer 1 ----
+      // ---- X row -> smem (bf16, K-major core matrices), layer 1: thread g writes 16-byte chunk g ----
       {
-        unsigned char* dst = rowA + (size_t)(tid >> 3) * sbo_in;
+        unsigned char* dst = rowA + (size_t)(r >> 3) * sbo_in;
 #pragma unroll
         for (int ch = 0; ch < kMlpInPad / 8; ++ch) {
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(x[8 * ch], x[8 * ch + 1]);
-          __nv_bfloat162 p1 = __floats2bfloat162_rn(x[8 * ch + 2], x[8 * ch + 3]);
-          __nv_bfloat162 p2 = __floats2bfloat162_rn(x[8 * ch + 4], x[8 * ch + 5]);
-          __nv_bfloat162 p3 = __floats2bfloat162_rn(x[8 * ch + 6], x[8 * ch + 7]);
-          uint4 v;
-          v.x = *reinterpret_cast<uint32_t*>(&p0); v.y = *reinterpret_cast<uint32_t*>(&p1);
-          v.z = *reinterpret_cast<uint32_t*>(&p2); v.w = *reinterpret_cast<uint32_t*>(&p3);
-          *reinterpret_cast<uint4*>(dst + ch * 128) = v;
+          if (ch == g) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(x[8 * ch], x[8 * ch + 1]);
+            __nv_bfloat162 p1 = __floats2bfloat162_rn(x[8 * ch + 2], x[8 * ch + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(x[8 * ch + 4], x[8 * ch + 5]);
+            __nv_bfloat162 p3 = __floats2bfloat162_rn(x[8 * ch + 6], x[8 * ch + 7]);
+            uint4 v;
+            v.x = *reinterpret_cast<uint32_t*>(&p0); v.y = *reinterpret_cast<uint32_t*>(&p1);
+            v.z = *reinterpret_cast<uint32_t*>(&p2); v.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(dst + ch * 128) = v;
+          }
         }
       }
       fence_proxy_async_smem();
@@ -224,8 +232,8 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
         phase ^= 1;
         tc_fence_after();
         const float* bs = sBias + layer * H;
-        unsigned char* dst = rowA + (size_t)(tid >> 3) * sbo_h;
-        for (int c0 = 0; c0 < H; c0 += 32) {
+        unsigned char* dst = rowA + (size_t)(r >> 3) * sbo_h;
+        for (int c0 = g * 32; c0 < H; c0 += 32 * kMlpColGroups) {      // 32-column chunks dealt round-robin
           float v[32];
           tmem_ld32(taddr + (uint32_t)c0, v);
 #pragma unroll
@@ -268,7 +276,7 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
       }
       tc_fence_before();      // the next step's MMA overwrites these TMEM columns after the CTA barrier above it
     }
-    if (valid) a.costs[row] = total;
+    if (valid && g == 0) a.costs[row] = total;
     __syncthreads();
   }
   tc_fence_before();

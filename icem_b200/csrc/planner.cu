@@ -268,7 +268,7 @@ static void launch_mlp(icem_planner* p, const RolloutArgs& a, int rows_max) {
   }
   const int tiles = (rows_max + kMlpTile - 1) / kMlpTile;
   const int grid = std::max(1, std::min(tiles, p->sm_count));     // one resident CTA per SM (weights fill smem)
-  mlp_rollout_kernel<<<grid, kMlpTile, smem, p->stream>>>(a, sc, cc, p->mlp);
+  mlp_rollout_kernel<<<grid, kMlpThreads, smem, p->stream>>>(a, sc, cc, p->mlp);
   ICEM_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
 }
