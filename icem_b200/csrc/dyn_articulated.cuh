@@ -45,6 +45,7 @@ struct ArtModel {
   int b_con_start[kArtMaxBodies], b_con_count[kArtMaxBodies];
   int b_last_dof[kArtMaxBodies];      // last dof on the path root -> body (-1: none)
   int lvl_np[kArtMaxDepth], lvl_parent[kArtMaxDepth][kArtMaxLevelParents];   // bodies with children, per depth
+  int lvl_child[kArtMaxDepth][kArtMaxLevelParents][kArtMaxChildren];         // their children, padded with -1
   float b_pos[kArtMaxBodies][3], b_mass[kArtMaxBodies], b_com[kArtMaxBodies][3], b_inertia[kArtMaxBodies][6];
   int d_body[kArtMaxDofs], d_type[kArtMaxDofs], d_qadr[kArtMaxDofs], d_limited[kArtMaxDofs], d_act[kArtMaxDofs];
   int d_vref[kArtMaxDofs];            // dof whose inclusive velocity sum is the velocity of the frame S_j is fixed in
@@ -102,13 +103,15 @@ struct Articulated {
   static constexpr int oRb = oO + 4;                          // [nb][9]
   static constexpr int oPb = oRb + NBMAX * kSR;               // [nb][3]
   static constexpr int oRec = oPb + NBMAX * kSP;              // [nb][17]  f(6) + composite inertia(10)
-  static constexpr int oSd = oRec + NBMAX * kSRec;            // [nv][7]   S_j
-  static constexpr int oX = oSd + NVMAX * kS6;                // [nv][7]   prefix sums of S qd
-  static constexpr int oY = oX + NVMAX * kS6;                 // [nv][7]   prefix sums of (v x S) qd
+  static constexpr int kZeroRec = NBMAX;                      // an all-zero record: padding child in 3b
+  static constexpr int oSd = oRec + (NBMAX + 1) * kSRec;      // [nv][7]   S_j
+  static constexpr int oX = (oSd + NVMAX * kS6 + 3) & ~3;     // [nv][7]   prefix sums of S qd       (16-B aligned)
+  static constexpr int oY = (oX + NVMAX * kS6 + 3) & ~3;      // [nv][7]   prefix sums of (v x S) qd (16-B aligned)
   static constexpr int oCw = oY + NVMAX * kS6;                // [nc][7]   contact wrenches
   static constexpr int oEnd0 = oCw + NCMAX * kS6;
   // the transposition buffer of the Cholesky factor aliases Rb.. (dead by then)
   static constexpr int oEnd = oEnd0 > oRb + NVMAX * kLd ? oEnd0 : oRb + NVMAX * kLd;
+  static_assert(oX % 4 == 0 && oY % 4 == 0 && NVMAX % 4 == 0, "Cholesky column buffers must be 16-byte aligned");
   __host__ __device__ static bool fits(int nb, int nv, int nc) { return nb <= NBMAX && nv <= NVMAX && nc <= NCMAX; }
   static constexpr int oState = 0;
   __host__ __device__ static int cta_floats(const Params&) { return (int)((sizeof(ArtModel) + 3) / 4); }
@@ -423,15 +426,19 @@ struct Articulated {
 #pragma unroll
       for (int i = 0; i < 6; ++i) r[10 + i] = Io[i];
     }
+    if (lane >= 16) rec[kZeroRec * kSRec + (lane - 16)] = 0.f;     // (the transposition buffer of step 5 aliases it)
     __syncwarp();
 
     // ---- 3b. leaf -> root accumulation, lane = (parent body, record component) ----------------------------------
+    // child lists are padded to 4 with the all-zero record, so every item is 5 loads + 4 adds without branches
     for (int L = m.max_depth - 1; L >= 0; --L) {
       const int items = m.lvl_np[L] * 16;
       for (int it = lane; it < items; it += 32) {
-        const int b = m.lvl_parent[L][it >> 4], comp = it & 15;
-        float acc = rec[b * kSRec + comp];
-        for (int k = 0; k < m.b_nchild[b]; ++k) acc += rec[m.b_child[b][k] * kSRec + comp];
+        const int slot = it >> 4, comp = it & 15;
+        const int b = m.lvl_parent[L][slot];
+        const int4 ch = *reinterpret_cast<const int4*>(m.lvl_child[L][slot]);
+        const float acc = rec[b * kSRec + comp] + rec[ch.x * kSRec + comp] + rec[ch.y * kSRec + comp] +
+                          rec[ch.z * kSRec + comp] + rec[ch.w * kSRec + comp];
         rec[b * kSRec + comp] = acc;
       }
       __syncwarp();
@@ -494,17 +501,26 @@ struct Articulated {
     }
 
     // ---- 5. in-register Cholesky (lane i holds row i, columns 0..i) ---------------------------------------------
+    // step k: every lane publishes its (unscaled) column-k entry in shared memory, then all lanes read the whole
+    // column with broadcast 128-bit loads: row_i[c] -= A_ik A_ck / A_kk.  Two alternating buffers, one sync per step.
 #pragma unroll
     for (int k = 0; k < NVMAX; ++k) {
-      const float akk = __shfl_sync(0xffffffffu, row[k], k);
-      const float inv = rsqrtf(akk);
+      float* col = w + ((k & 1) ? oY : oX);
+      if (lane < NVMAX) col[lane] = row[k];
+      __syncwarp();
+      float cv[NVMAX];
+#pragma unroll
+      for (int m4 = k / 4; m4 < NVMAX / 4; ++m4) {
+        const float4 v = *reinterpret_cast<const float4*>(col + 4 * m4);
+        cv[4 * m4] = v.x; cv[4 * m4 + 1] = v.y; cv[4 * m4 + 2] = v.z; cv[4 * m4 + 3] = v.w;
+      }
+      const float inv = rsqrtf(cv[k]);
+      const float t = (lane > k) ? row[k] * inv * inv : 0.f;
       row[k] = (lane >= k) ? row[k] * inv : 0.f;      // lane k: sqrt(akk); lanes > k: l_ik
 #pragma unroll
-      for (int c = k + 1; c < NVMAX; ++c) {
-        const float lck = __shfl_sync(0xffffffffu, row[k], c);
-        row[c] = fmaf(-row[k], lck, row[c]);
-      }
+      for (int c = k + 1; c < NVMAX; ++c) row[c] = fmaf(-t, cv[c], row[c]);
     }
+    __syncwarp();
     float diag = 1.f;
 #pragma unroll
     for (int c = 0; c < NVMAX; ++c) diag = (c == lane) ? row[c] : diag;

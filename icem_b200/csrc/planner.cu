@@ -766,6 +766,7 @@ int icem_set_articulated_model(icem_planner_t* p, const icem_articulated_model_t
     if (m.b_nchild[b] > 0) {
       int& np = m.lvl_np[m.b_depth[b]];
       if (np >= kArtMaxLevelParents) throw InvalidArg("more than 8 bodies with children on one tree level");
+      for (int k = 0; k < kArtMaxChildren; ++k) m.lvl_child[m.b_depth[b]][np][k] = k < m.b_nchild[b] ? m.b_child[b][k] : -1;
       m.lvl_parent[m.b_depth[b]][np++] = b;
     }
   }
@@ -799,6 +800,14 @@ int icem_set_articulated_model(icem_planner_t* p, const icem_articulated_model_t
     m.c_body[c] = b;
     for (int i = 0; i < 3; ++i) m.c_pos[c][i] = a->con_pos[3 * c + i];
     m.c_radius[c] = a->con_radius[c];
+  }
+  {   // padding children point at the all-zero record of the size class that will run this model
+    const int zero_rec = Articulated<12>::fits(m.nb, m.nv, m.nc) ? Articulated<12>::kZeroRec
+                         : (Articulated<24>::fits(m.nb, m.nv, m.nc) ? Articulated<24>::kZeroRec : Articulated<32>::kZeroRec);
+    for (int L = 0; L < kArtMaxDepth; ++L)
+      for (int s2 = 0; s2 < kArtMaxLevelParents; ++s2)
+        for (int k = 0; k < kArtMaxChildren; ++k)
+          if (m.lvl_child[L][s2][k] < 0) m.lvl_child[L][s2][k] = zero_rec;
   }
   p->art_model.alloc(1);
   ICEM_CUDA(cudaMemcpy(p->art_model.p, &m, sizeof m, cudaMemcpyHostToDevice));
