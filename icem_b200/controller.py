@@ -64,11 +64,9 @@ class MpcICemB200(*_Bases):
             horizon=horizon, num_simulated_trajectories=num_simulated_trajectories,
             action_low=self.env.action_space.low, action_high=self.env.action_space.high,
             dynamics=spec["dynamics"], cost=cost, obs_dim=spec["obs_dim"], penalise_flipping=penalise,
-            factor_decrease_num=factor_decrease_num, cost_along_trajectory=self.cost_along_trajectory,
-            alpha=self.alpha, elites_size=self.elites_size, opt_iterations=self.opt_iter, init_std=self.init_std,
-            use_mean_actions=self.use_mean_actions, keep_previous_elites=self.keep_previous_elites,
-            shift_elites_over_time=self.shift_elites_over_time, fraction_elites_reused=self.fraction_elites_reused,
-            noise_beta=self.noise_beta, seed=seed, device=device, world_size=world_size, rank=rank))
+            cost_along_trajectory=self.cost_along_trajectory, alpha=self.alpha, elites_size=self.elites_size,
+            opt_iterations=self.opt_iter, init_std=self.init_std, seed=seed, device=device, world_size=world_size,
+            rank=rank, **self._sampler_settings()))
         if spec.get("dense") is not None:
             self._planner.set_dense_model(*spec["dense"])
         if spec.get("mlp") is not None:
@@ -77,6 +75,18 @@ class MpcICemB200(*_Bases):
             from .distributed import init_planner_comm
             init_planner_comm(self._planner)
         self.expected_cost = None
+
+    def _sampler_settings(self):
+        return dict(planner="icem", factor_decrease_num=self.factor_decrease_num,
+                    use_mean_actions=self.use_mean_actions, keep_previous_elites=self.keep_previous_elites,
+                    shift_elites_over_time=self.shift_elites_over_time,
+                    fraction_elites_reused=self.fraction_elites_reused, noise_beta=self.noise_beta)
+
+    def _evals_per_timestep(self):      # controllers/icem.py:38-41
+        return sum([max(self.elites_size * 2, int(self.num_sim_traj / (self.factor_decrease_num ** i)))
+                    for i in range(0, self.opt_iter)]) * self.horizon
+
+    _banner = "iCEM"
 
     # ---- settings (controllers/icem.py:213-247) ------------------------------------------------
     def _parse_action_sampler_params(self, *, alpha, elites_size, opt_iterations, init_std, use_mean_actions,
@@ -126,11 +136,9 @@ class MpcICemB200(*_Bases):
         self.was_reset = True
         self._elite_cache = None
         self._steps_since_reset = 0
-        # controllers/icem.py:38-43
-        self.model_evals_per_timestep = sum(
-            [max(self.elites_size * 2, int(self.num_sim_traj / (self.factor_decrease_num ** i)))
-             for i in range(0, self.opt_iter)]) * self.horizon
-        print(f"iCEM using {self.model_evals_per_timestep} evaluations per step "
+        # controllers/icem.py:38-43 / controllers/mpc.py:172-175
+        self.model_evals_per_timestep = self._evals_per_timestep()
+        print(f"{self._banner} using {self.model_evals_per_timestep} evaluations per step "
               f"and {self.model_evals_per_timestep / self.horizon} trajectories per step")
 
     def end_of_rollout(self, total_time, total_return, mode):
@@ -176,9 +184,11 @@ class MpcICemB200(*_Bases):
 
             def display_cost(cost):
                 return cost / self.horizon if self.cost_along_trajectory == "sum" else cost
-            print('iter {}:{} --- best cost: {:.2f} --- mean: {:.2f} --- worst: {:.2f}  elites: {}...'
+            print(self._iter_format
                   .format(i, n_local, display_cost(min(np.amin(costs), rec["elite_costs"][0])),
                           display_cost(np.mean(costs)), display_cost(np.amax(costs)), rec["elite_idx"][0:6]))
+
+    _iter_format = 'iter {}:{} --- best cost: {:.2f} --- mean: {:.2f} --- worst: {:.2f}  elites: {}...'
 
     # ---- observable attributes -----------------------------------------------------------------
     @property
@@ -208,3 +218,32 @@ class MpcICemB200(*_Bases):
 
     def close(self):
         self._planner.close()
+
+
+
+class MpcCemStdB200(MpcICemB200):
+    """Drop-in for the reference's vanilla CEM `MpcCemStd` (icem/controllers/mpc.py:142-327): truncated-normal
+    sampling inside the action bounds, constant population, no elite reuse / mean injection, `_update_bounds`
+    (optionally "like Levine"), `execute_best_elite` and `shift_means` switches -- on the same kernels
+    (SURVEY 8f-1).  Same constructor keywords as the reference class."""
+    _banner = "CEM-Standard"
+    _iter_format = 'iter {}:{} --- best cost: {:.2f} --- mean: {:.2f} --- worst: {:.2f}  elites: {}...'
+
+    def _parse_action_sampler_params(self, *, alpha, elites_size, opt_iterations, init_std, shift_means,
+                                     execute_best_elite, bounds_like_levine):
+        self.alpha = alpha
+        self.elites_size = elites_size
+        self.opt_iter = opt_iterations
+        self.init_std = init_std
+        self.execute_best_elite = execute_best_elite
+        self.like_levine = bounds_like_levine
+        self.shift_means = shift_means
+
+    def _sampler_settings(self):
+        return dict(planner="cem_std", factor_decrease_num=1.0, use_mean_actions=False, keep_previous_elites=False,
+                    shift_elites_over_time=False, fraction_elites_reused=0.0, noise_beta=0.0,
+                    execute_best_elite=self.execute_best_elite, shift_means=self.shift_means,
+                    bounds_like_levine=self.like_levine)
+
+    def _evals_per_timestep(self):      # controllers/mpc.py:172
+        return self.num_sim_traj * self.opt_iter * self.horizon

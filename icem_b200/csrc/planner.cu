@@ -94,7 +94,7 @@ struct icem_planner {
   cudaStream_t stream = nullptr;
 
   // device state
-  DevBuf<float> actions, costs, G, d_low, d_high, mean, stdv, init_mean, init_std;
+  DevBuf<float> actions, costs, G, d_low, d_high, mean, stdv, init_mean, init_std, reset_std;
   DevBuf<float> elite_actions[2], elite_costs[2];
   DevBuf<int32_t> elite_idx[2];
   DevBuf<float> trace_mean, trace_std, trace_costs;
@@ -204,6 +204,10 @@ static void upload(DevBuf<float>& b, const std::vector<float>& v) {
 static SamplerConst sampler_const(icem_planner* p) {
   SamplerConst sc{};
   sc.h = p->h; sc.d = p->d; sc.K = p->K; sc.white = p->white;
+  sc.trunc = p->cfg.planner == ICEM_PLANNER_CEM_STD;
+  sc.levine = p->cfg.bounds_like_levine;
+  sc.magic_d = (uint32_t)((0x100000000ull + p->d - 1) / p->d);
+  sc.magic_K = (uint32_t)((0x100000000ull + p->K - 1) / p->K);
   sc.G = p->G.p; sc.low = p->d_low.p; sc.high = p->d_high.p;
   return sc;
 }
@@ -357,6 +361,11 @@ static RefitArgs refit_args(icem_planner* p, int i) {
   r.trace_std = p->trace_std.p + (size_t)i * p->hd;
   r.trace_costs = p->trace_costs.p + (size_t)i * p->k;
   r.trace_idx = p->trace_idx.p + (size_t)i * p->k;
+  r.cem_std = p->cfg.planner == ICEM_PLANNER_CEM_STD;
+  r.execute_mean = r.cem_std && !p->cfg.execute_best_elite;
+  r.mean_to_zero = r.cem_std && !p->cfg.shift_means;
+  r.levine = r.cem_std && p->cfg.bounds_like_levine;
+  r.low = p->d_low.p; r.high = p->d_high.p;
   r.out_action = p->out.p;
   r.out_best_cost = p->out.p + p->d;
   return r;
@@ -492,7 +501,7 @@ static void build_plan(icem_planner* p) {
 
 static void reset_distribution(icem_planner* p) {
   ICEM_CUDA(cudaMemcpyAsync(p->mean.p, p->init_mean.p, p->hd * sizeof(float), cudaMemcpyDeviceToDevice, p->stream));
-  ICEM_CUDA(cudaMemcpyAsync(p->stdv.p, p->init_std.p, p->hd * sizeof(float), cudaMemcpyDeviceToDevice, p->stream));
+  ICEM_CUDA(cudaMemcpyAsync(p->stdv.p, p->reset_std.p, p->hd * sizeof(float), cudaMemcpyDeviceToDevice, p->stream));
 }
 
 static void write_step_in(icem_planner* p, const double* state) {
@@ -590,7 +599,16 @@ int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
   p->sm_count = prop.multiProcessorCount;
   p->h = cfg->horizon; p->d = cfg->act_dim; p->hd = p->h * p->d; p->K = p->h / 2 + 1;
   p->iters = cfg->opt_iterations;
-  p->white = !(cfg->noise_beta > 0);
+  if (cfg->planner != ICEM_PLANNER_ICEM && cfg->planner != ICEM_PLANNER_CEM_STD) throw Unsupported("unknown planner id");
+  const bool cem_std = cfg->planner == ICEM_PLANNER_CEM_STD;
+  if (cem_std) {
+    // MpcCemStd has no population decay, elite reuse or mean injection (controllers/mpc.py:212-233)
+    p->cfg.factor_decrease_num = 1.0;
+    p->cfg.use_mean_actions = p->cfg.keep_previous_elites = p->cfg.shift_elites_over_time = 0;
+  } else {
+    p->cfg.execute_best_elite = 1; p->cfg.shift_means = 1; p->cfg.bounds_like_levine = 0;
+  }
+  p->white = cem_std || !(cfg->noise_beta > 0);
   p->low.assign(cfg->action_low, cfg->action_low + p->d);
   p->high.assign(cfg->action_high, cfg->action_high + p->d);
   p->cfg.action_low = p->low.data();
@@ -625,6 +643,16 @@ int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
     }
   upload(p->init_mean, m0);
   upload(p->init_std, s0);
+  // the std a rollout starts from: MpcCemStd with bounds_like_levine clamps it at once (mpc.py:170, 291-294; the mean
+  // is the mid point there, so the distance to either bound is half the range)
+  std::vector<float> s0r = s0;
+  if (cem_std && cfg->bounds_like_levine)
+    for (int t = 0; t < p->h; ++t)
+      for (int j = 0; j < p->d; ++j) {
+        const float half = (p->high[j] - p->low[j]) / 2.0f;
+        s0r[t * p->d + j] = std::max(1e-8f, std::min(half * 0.5f, s0[t * p->d + j]));
+      }
+  upload(p->reset_std, s0r);
   p->mean.alloc(p->hd);
   p->stdv.alloc(p->hd);
   for (int b = 0; b < 2; ++b) {

@@ -25,6 +25,9 @@ struct StepState {
 struct SamplerConst {
   int h, d, K;          // horizon, action dim, rFFT bins (h/2+1)
   int white;            // noise_beta == 0: iid normal, z laid out [row][h][d]
+  int trunc;            // MpcCemStd: draws are signed tail probabilities [row][h][d] (truncnorm_ppf), action = mean + std * ppf
+  int levine;           // MpcCemStd bounds_like_levine: lower/upper = -2/+2 (else the action bounds in std units)
+  uint32_t magic_d, magic_K;   // ceil(2^32 / d), ceil(2^32 / K): x / d == __umulhi(x, magic_d) for x < 2^16
   const float* G;       // [h][2K] synthesis matrix (colored): y[t] = sum_j G[t][j] * z[j], z = [zr(K), zi(K)]
   const float* low;     // [d]
   const float* high;    // [d]
@@ -76,17 +79,40 @@ __device__ __forceinline__ float step_cost(const CostConst& cc, const Dyn& dyn, 
   return -dyn.obs(cc.idx_a) + 0.1f * a2;
 }
 
+// scipy.stats.truncnorm._ppf (what controllers/mpc.py:194-198 draws through) for fp32: the uniform draw arrives as
+// a SIGNED TAIL PROBABILITY w -- u = w for u < 1/2, w = -(1 - u) otherwise -- so that the small tail keeps its
+// relative precision (a plain fp32 u has 6e-8 absolute resolution near 1, i.e. 2e-4 sigma at +3.8 sigma); the
+// quantile is taken from whichever tail of the truncated distribution is lighter, like scipy's left/right cases.
+__device__ __forceinline__ float truncnorm_ppf(float w, float a, float b) {
+  const float pa = normcdff(a), pnb = normcdff(-b);          // P(X < a), P(X > b)
+  const float mass = (a < 0.f && b > 0.f) ? 1.f - pa - pnb : (b <= 0.f ? normcdff(b) - pa : normcdff(-a) - pnb);
+  const float ul = w >= 0.f ? w : 1.f + w, ur = w >= 0.f ? 1.f - w : -w;
+  const float pl = fmaf(ul, mass, pa), pr = fmaf(ur, mass, pnb);
+  const float x = pl <= pr ? normcdfinvf(pl) : -normcdfinvf(pr);
+  return fminf(fmaxf(x, a), b);
+}
+
 // ---------------------------------------------------------------------------------------------
 // unit normals for one trajectory row -> z[dim][j] (colored, row stride zs) or straight into the
 // tile (white).  Philox counter = (global row, block, step, iteration); key = seed.
 __device__ __forceinline__ void fill_normals(float* dst, int count, uint32_t grow, const RolloutArgs& a,
-                                             uint32_t step, int K2, int zs, bool white) {
+                                             uint32_t step, int K2, int zs, bool white, bool uniform,
+                                             uint32_t magic_K) {
   const int lane = lane_id();
   for (int b = lane; b * 4 < count; b += 32) {
     Philox4 r = philox4x32_10(grow, (uint32_t)b, step, (uint32_t)a.iteration, a.seed_lo, a.seed_hi);
     float n[4];
-    box_muller(r.x, r.y, n[0], n[1]);
-    box_muller(r.z, r.w, n[2], n[3]);
+    if (uniform) {                       // signed tail probabilities in (-1/2, 1/2) \ {0} (see truncnorm_ppf)
+      const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float tail = ((float)(rr[q] & 0x7FFFFFFFu) + 0.5f) * 2.3283064365386963e-10f;   // (0, 1/2)
+        n[q] = (rr[q] >> 31) ? -tail : tail;
+      }
+    } else {
+      box_muller(r.x, r.y, n[0], n[1]);
+      box_muller(r.z, r.w, n[2], n[3]);
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int c = b * 4 + q;
@@ -98,7 +124,7 @@ __device__ __forceinline__ void fill_normals(float* dst, int count, uint32_t gro
           const int dk = count >> 1;            // d*K
           const int part = c >= dk;
           const int r2 = c - part * dk;
-          const int dim = r2 / K;
+          const int dim = (int)__umulhi((uint32_t)r2, magic_K);
           const int k = r2 - dim * K;
           dst[dim * zs + part * K + k] = n[q];
         }
@@ -210,20 +236,27 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
           const float* sr = a.inj_zr + (size_t)row * dK;
           const float* si = a.inj_zi + (size_t)row * dK;
           for (int i = lane; i < dK; i += 32) {
-            const int dim = i / sc.K, k = i - dim * sc.K;
+            const int dim = (int)__umulhi((uint32_t)i, sc.magic_K), k = i - dim * sc.K;
             w_z[dim * zs + k] = sr[i];
             w_z[dim * zs + sc.K + k] = si[i];
           }
         }
       } else {
-        fill_normals(zdst, count, grow, a, ss.step, K2, zs, sc.white);
+        fill_normals(zdst, count, grow, a, ss.step, K2, zs, sc.white, sc.trunc != 0, sc.magic_K);
       }
       __syncwarp();
       // ---- 2. synthesis + affine + clip (icem.py:73-79), elite shift (icem.py:91-104), mean row ----
       const bool mean_row = a.inject_mean_row0 && grow == 0u && !shifted;
       const float* elite = shifted ? a.prev_elites + (size_t)(row - a.n_fresh_local) * a.stride : nullptr;
       for (int o = lane; o < hd; o += 32) {
-        const int t = o / d, dim = o - t * d;
+        const int t = (int)__umulhi((uint32_t)o, sc.magic_d), dim = o - t * d;
+        if (sc.trunc) {       // MpcCemStd: mean + std * truncnorm.ppf(u; lower, upper), no clip (mpc.py:194-198, 290-301)
+          const float sd = s_std[o], mu = s_mean[o];
+          const float lo_ = sc.levine ? -2.f : (s_low[dim] - mu) / (sd + 1e-8f);
+          const float hi_ = sc.levine ? 2.f : (s_high[dim] - mu) / (sd + 1e-8f);
+          tile[o] = fmaf(sd, truncnorm_ppf(tile[o], lo_, hi_), mu);
+          continue;
+        }
         float y;
         if (sc.white) {
           y = tile[o];

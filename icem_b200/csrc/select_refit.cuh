@@ -56,6 +56,9 @@ struct RefitArgs {
   const float* init_std;           // [h*d] reset value (icem.py:175)
   // per-iteration record of this plan step
   float* trace_mean; float* trace_std; float* trace_costs; int32_t* trace_idx;
+  // MpcCemStd switches (controllers/mpc.py:237-248, 290-301); all 0 / null for MpcICem
+  int cem_std, execute_mean, mean_to_zero, levine;
+  const float* low; const float* high;   // [d] action bounds (levine std clamp)
   float* out_action;               // [d]  (last iteration)
   float* out_best_cost;            // [1]  min(costs) of the last iteration (icem.py:177)
 };
@@ -165,7 +168,11 @@ __device__ void merge_refit(const RefitArgs& r, unsigned long long* s_keys /* [k
     }
     const float sd = sqrtf(var * inv_k);                       // ddof = 0 (icem.py:208)
     const float nm = r.one_minus_alpha * m + r.alpha * r.mean[e];   // icem.py:210-211
-    const float ns = r.one_minus_alpha * sd + r.alpha * r.std[e];
+    float ns = r.one_minus_alpha * sd + r.alpha * r.std[e];
+    if (r.levine) {            // mpc.py:291-294 (_update_bounds after every refit)
+      const int dim = e % r.d;
+      ns = fmaxf(1e-8f, fminf(fminf((nm - r.low[dim]) * 0.5f, (r.high[dim] - nm) * 0.5f), ns));
+    }
     r.trace_mean[e] = nm;
     r.trace_std[e] = ns;
     if (!r.last_iteration) {
@@ -175,14 +182,24 @@ __device__ void merge_refit(const RefitArgs& r, unsigned long long* s_keys /* [k
   }
   __syncthreads();
   if (r.last_iteration) {
-    // icem.py:163: executed action = first action of the best trajectory of the last population
-    for (int e = tid; e < r.d; e += blockDim.x) r.out_action[e] = s_src[0][e];
+    // icem.py:163 / mpc.py:237-240: executed action = first action of the best trajectory of the last population,
+    // or (MpcCemStd with execute_best_elite false) the first row of the refitted mean
+    for (int e = tid; e < r.d; e += blockDim.x) r.out_action[e] = r.execute_mean ? r.trace_mean[e] : s_src[0][e];
     if (tid == 0) r.out_best_cost[0] = r.new_elite_costs[0];
-    // icem.py:167-175: mean[:-1] = mean[1:], last row kept; std reset
+    // icem.py:167-175: mean[:-1] = mean[1:], last row kept; std reset.  mpc.py:243-252: last row zero with
+    // bounds_like_levine, mean = zeros without shift_means; the std reset is followed by _update_bounds
     for (int e = tid; e < hd; e += blockDim.x) {
       const int src = e + r.d < hd ? e + r.d : e;
-      r.mean[e] = r.trace_mean[src];
-      r.std[e] = r.init_std[e];
+      float nm = r.trace_mean[src];
+      if (r.cem_std && r.levine && e + r.d >= hd) nm = 0.f;
+      if (r.mean_to_zero) nm = 0.f;
+      float ns = r.init_std[e];
+      if (r.levine) {
+        const int dim = e % r.d;
+        ns = fmaxf(1e-8f, fminf(fminf((nm - r.low[dim]) * 0.5f, (r.high[dim] - nm) * 0.5f), ns));
+      }
+      r.mean[e] = nm;
+      r.std[e] = ns;
     }
   }
 }

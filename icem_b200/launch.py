@@ -7,7 +7,8 @@ The reference selects controller / forward model / environment by STRING through
 launcher adds entries to them before calling `main.main()` and edits nothing else:
 
   controller     "mpc-icem-b200"            -> icem_b200.controller.MpcICemB200
-                 ("mpc-icem" too with --override-mpc-icem, so existing settings files run unchanged)
+                 "mpc-cem-std-b200"         -> icem_b200.controller.MpcCemStdB200 (vanilla CEM baseline)
+                 ("mpc-icem" / "mpc-cem-std" too with --override-mpc-icem, so existing settings files run unchanged)
   forward_model  "CudaGroundTruthModel"     -> icem_b200.models.CudaGroundTruthModel
                  "CudaDenseTanhModel"       -> icem_b200.models.CudaDenseTanhModel
   env            "HalfCheetah" / "HumanoidStandup" resolve to the device-simulated stand-ins of icem_b200.envs
@@ -46,10 +47,13 @@ def register(override_mpc_icem=False, standin_envs=True):
     import models
     table = controllers.ControllerFactory.valid_base_controllers
     table["mpc-icem-b200"] = ("icem_b200.controller", "MpcICemB200")
+    table["mpc-cem-std-b200"] = ("icem_b200.controller", "MpcCemStdB200")
     if override_mpc_icem:
         table["mpc-icem"] = ("icem_b200.controller", "MpcICemB200")
+        table["mpc-cem-std"] = ("icem_b200.controller", "MpcCemStdB200")
     models.models_dict["CudaGroundTruthModel"] = ("icem_b200.models", "CudaGroundTruthModel")
     models.models_dict["CudaDenseTanhModel"] = ("icem_b200.models", "CudaDenseTanhModel")
+    models.models_dict["CudaMlpModel"] = ("icem_b200.models", "CudaMlpModel")
     if standin_envs:
         import environments  # noqa: F401  (package import must precede the submodule override)
         from . import envs

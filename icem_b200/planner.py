@@ -38,6 +38,10 @@ class PlannerSettings:
     rank: int = 0
     colorednoise_v2: bool = False
     keep_iteration_actions: bool = False
+    planner: str = "icem"                # "icem" (MpcICem) | "cem_std" (MpcCemStd: truncated normal, bounds update)
+    execute_best_elite: bool = True      # cem_std only (controllers/mpc.py:237-240)
+    shift_means: bool = True             # cem_std only (controllers/mpc.py:243-248)
+    bounds_like_levine: bool = False     # cem_std only (controllers/mpc.py:290-301)
     articulated_model: object = None     # robots.CompiledModel; None = the built-in tables for `dynamics`
     obs_offset: Optional[int] = None
 
@@ -64,7 +68,9 @@ class Planner:
             cost_along_trajectory=_lib.REDUCE[s.cost_along_trajectory], dynamics=_lib.DYN[s.dynamics],
             cost=_lib.COST[s.cost], cost_penalise_flipping=int(bool(s.penalise_flipping)), obs_dim=int(s.obs_dim),
             colorednoise_v2=int(bool(s.colorednoise_v2)), keep_iteration_actions=int(bool(s.keep_iteration_actions)),
-            world_size=int(s.world_size), rank=int(s.rank),
+            world_size=int(s.world_size), rank=int(s.rank), planner=_lib.PLANNER[s.planner],
+            execute_best_elite=int(bool(s.execute_best_elite)), shift_means=int(bool(s.shift_means)),
+            bounds_like_levine=int(bool(s.bounds_like_levine)),
             factor_decrease_num=float(s.factor_decrease_num), alpha=float(s.alpha), init_std=float(s.init_std),
             fraction_elites_reused=float(s.fraction_elites_reused), noise_beta=float(s.noise_beta),
             seed=int(s.seed) & (2 ** 64 - 1), action_low=fptr(self._low), action_high=fptr(self._high))
@@ -165,6 +171,11 @@ class Planner:
         return a.value, b.value
 
     def inject_noise(self, iteration, zr, zi=None):
+        """Unit normal draws (iCEM) or, for planner="cem_std", the uniform draws u of truncnorm.rvs (float64);
+        the latter are passed on as signed tail probabilities (include/icem_b200.h: icem_inject_noise)."""
+        if self.settings.planner == "cem_std":
+            u = np.asarray(zr, np.float64)
+            zr = np.where(u < 0.5, u, -(1.0 - u))
         zr = f32(zr)
         zi_ = f32(zi) if zi is not None else None
         check(self._lib.icem_inject_noise(self._h, iteration, zr.shape[0], fptr(zr),

@@ -83,3 +83,47 @@ def controller_config(case):
     c["action_low"] = np.asarray(case["low"], np.float32)     # gym Box dtype
     c["action_high"] = np.asarray(case["high"], np.float32)
     return c
+
+
+def _cem_sampler(**over):
+    p = dict(alpha=0.1, elites_size=10, opt_iterations=3, init_std=0.5, shift_means=True, execute_best_elite=True,
+             bounds_like_levine=False)
+    p.update(over)
+    return p
+
+
+# vanilla CEM (controllers/mpc.py::MpcCemStd): the paper's baseline, SURVEY 8(f)-1
+CEM_STD_CASES = {
+    "cemstd_cheetah": dict(
+        model=lambda: DenseTanhModel.appendix_c(seed=3), cost="halfcheetah", penalise_flipping=True,
+        low=-np.ones(6), high=np.ones(6),
+        ctrl=dict(num_simulated_trajectories=96, horizon=30, cost_along_trajectory="sum",
+                  action_sampler_params=_cem_sampler(), do_visualize_plan=False, verbose=False),
+        start_obs=0.1 * np.random.RandomState(1010).randn(17), seed=10, steps=3),
+    "cemstd_levine_mean": dict(
+        model=_humanoid_like_model, cost="humanoid_standup", penalise_flipping=False,
+        low=-0.4 * np.ones(17), high=0.4 * np.ones(17),
+        ctrl=dict(num_simulated_trajectories=64, horizon=12, cost_along_trajectory="sum",
+                  action_sampler_params=_cem_sampler(bounds_like_levine=True, execute_best_elite=False, alpha=0.25,
+                                                     elites_size=8, opt_iterations=4),
+                  do_visualize_plan=False, verbose=False),
+        start_obs=0.1 * np.random.RandomState(1011).randn(47), seed=11, steps=3),
+    "cemstd_noshift": dict(
+        model=lambda: DenseTanhModel.appendix_c(seed=9), cost="halfcheetah", penalise_flipping=True,
+        low=np.array([-1, -0.5, -1, -2, -1, -1.0]), high=np.array([1, 0.5, 2, 1, 1, 1.0]),
+        ctrl=dict(num_simulated_trajectories=40, horizon=20, cost_along_trajectory="best",
+                  action_sampler_params=_cem_sampler(shift_means=False, init_std=0.3),
+                  do_visualize_plan=False, verbose=False),
+        start_obs=0.1 * np.random.RandomState(1012).randn(17), seed=12, steps=2),
+}
+
+
+def cem_std_config(case):
+    c = dict(case["ctrl"])
+    s = dict(c.pop("action_sampler_params"))
+    c.pop("do_visualize_plan", None)
+    c.pop("verbose", None)
+    c.update(s)
+    c["action_low"] = np.asarray(case["low"], np.float32)
+    c["action_high"] = np.asarray(case["high"], np.float32)
+    return c

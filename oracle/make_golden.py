@@ -16,11 +16,13 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    for name, case in cases.CASES.items():
+    todo = [(n, c, "MpcICem") for n, c in cases.CASES.items()] + \
+           [(n, c, "MpcCemStd") for n, c in cases.CEM_STD_CASES.items()]
+    for name, case, controller in todo:
         model = case["model"]()
         steps, next_randn = ref_harness.run_reference_episode(
             model, case["cost"], case["ctrl"], case["low"], case["high"], case["start_obs"],
-            case["seed"], case["steps"], case["penalise_flipping"])
+            case["seed"], case["steps"], case["penalise_flipping"], controller=controller)
         blob = {"next_randn": np.float64(next_randn), "num_steps": np.int64(len(steps))}
         for s, st in enumerate(steps):
             blob[f"s{s}_action"] = st["action"]

@@ -11,7 +11,7 @@ from oracle import ref_loader
 
 
 def build_reference_controller(model, cost_name, cfg_kwargs, action_low, action_high,
-                               penalise_flipping=True):
+                               penalise_flipping=True, controller="MpcICem"):
     """model: an oracle/dynamics_np.py model.  cost_name: "halfcheetah" | "humanoid_standup".
     cfg_kwargs: the `controller_params` dict of the settings JSON.  Returns (controller, recorder)."""
     ref = ref_loader.load_reference()
@@ -67,7 +67,8 @@ def build_reference_controller(model, cost_name, cfg_kwargs, action_low, action_
             pass
 
     env = _Env(name="standin")
-    ctrl = ref.icem.MpcICem(env=env, forward_model=_Model(env=env), **cfg_kwargs)
+    cls = ref.icem.MpcICem if controller == "MpcICem" else getattr(ref.mpc, controller)
+    ctrl = cls(env=env, forward_model=_Model(env=env), **cfg_kwargs)
 
     rec = {"iterations": []}
     orig_update = ctrl.update_distributions
@@ -87,10 +88,10 @@ def build_reference_controller(model, cost_name, cfg_kwargs, action_low, action_
 
 
 def run_reference_episode(model, cost_name, cfg_kwargs, action_low, action_high, start_obs,
-                          seed, num_steps, penalise_flipping=True):
+                          seed, num_steps, penalise_flipping=True, controller="MpcICem"):
     """np.random.seed(seed); beginning_of_rollout; `num_steps` x (get_action; obs <- model.step)."""
     ctrl, rec = build_reference_controller(model, cost_name, cfg_kwargs, action_low, action_high,
-                                           penalise_flipping)
+                                           penalise_flipping, controller)
     np.random.seed(seed)
     obs = np.asarray(start_obs, dtype=np.float64).copy()
     ctrl.beginning_of_rollout(observation=obs, state=None, mode="train")

@@ -1,2 +1,2 @@
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | sed "s/^/T: /"

@@ -139,3 +139,52 @@ def test_colorednoise_draw_equivalence_and_constants():
 def test_min_trajectories_error():
     with pytest.raises(ValueError, match="At least two trajectories"):
         ICemConfig(horizon=3, num_simulated_trajectories=1, action_low=[-1], action_high=[1])
+
+
+# ---- vanilla CEM (MpcCemStd) ----------------------------------------------------------------------
+def _run_cem_std_case(case, record_actions=False):
+    from oracle.cem_std_np import CemStdConfig, CemStdOracle
+    model = case["model"]()
+    cfg = CemStdConfig(**cases.cem_std_config(case))
+    if case["cost"] == "halfcheetah":
+        cost = lambda o, a: costs_np.halfcheetah_cost(o, a, case["penalise_flipping"])
+    else:
+        cost = COSTS[case["cost"]]
+    orc = CemStdOracle(cfg, model.rollout, cost, record_actions=record_actions)
+    np.random.seed(case["seed"])
+    obs = np.asarray(case["start_obs"], np.float64).copy()
+    orc.beginning_of_rollout()
+    traces = []
+    for _ in range(case["steps"]):
+        tr = orc.get_action(obs)
+        traces.append(tr)
+        obs = model.step(obs[None], tr.action[None])[0]
+    return traces, float(np.random.randn())
+
+
+@pytest.mark.parametrize("name", sorted(cases.CEM_STD_CASES))
+def test_cem_std_oracle_matches_reference_golden(name, golden_dir):
+    """oracle/cem_std_np.py against fixtures recorded from the UNMODIFIED reference MpcCemStd."""
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    traces, next_randn = _run_cem_std_case(cases.CEM_STD_CASES[name])
+    assert next_randn == float(g["next_randn"])
+    for s, tr in enumerate(traces):
+        np.testing.assert_allclose(tr.action, g[f"s{s}_action"], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(tr.mean_after_shift, g[f"s{s}_mean_after_shift"], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(tr.std_after_reset, g[f"s{s}_std_after_reset"], rtol=0, atol=1e-10)
+        for i, it in enumerate(tr.iterations):
+            np.testing.assert_allclose(it.costs, g[f"s{s}_i{i}_costs"], rtol=0, atol=1e-8)
+            np.testing.assert_array_equal(it.elite_idx, g[f"s{s}_i{i}_elite_idx"])
+            np.testing.assert_allclose(it.mean, g[f"s{s}_i{i}_mean"], rtol=0, atol=1e-10)
+            np.testing.assert_allclose(it.std, g[f"s{s}_i{i}_std"], rtol=0, atol=1e-10)
+
+
+def test_truncnorm_rvs_is_ppf_of_uniform_draws():
+    """What "identical RNG state" means for MpcCemStd: truncnorm.rvs == ppf(np.random.uniform) draw for draw."""
+    from scipy.stats import truncnorm
+    lo, hi = np.array([-1.5, -0.2, 0.3]), np.array([0.5, 2.0, 4.0])
+    np.random.seed(4)
+    a = truncnorm.rvs(lo, hi, loc=0.1, scale=0.7, size=(5, 3))
+    np.random.seed(4)
+    u = np.random.uniform(size=(5, 3))
+    np.testing.assert_allclose(a, truncnorm.ppf(u, lo, hi) * 0.7 + 0.1, rtol=0, atol=1e-14)
