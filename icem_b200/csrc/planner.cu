@@ -18,6 +18,7 @@
 #include "dyn_articulated.cuh"
 #include "dyn_dense.cuh"
 #include "mlp_rollout.cuh"
+#include "sampler.cuh"
 #include "rollout.cuh"
 #include "select_refit.cuh"
 
@@ -90,6 +91,7 @@ struct icem_planner {
   int state_dim = 0, obs_dim = 0;
   int sm_count = 148;
   bool white = false;
+  bool force_warp_sampler = false;   // ICEM_B200_WARP_SAMPLER=1 at icem_create: A/B the two samplers (tests)
   std::vector<IterPlan> plan;
   cudaStream_t stream = nullptr;
 
@@ -277,13 +279,54 @@ static void launch_mlp(icem_planner* p, const RolloutArgs& a, int rows_max) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
+// stand-alone colored-noise sampler (sampler.cuh): even horizons up to 62, iCEM planner
+static bool series_sampler_eligible(icem_planner* p) {
+  return !p->white && p->cfg.planner == ICEM_PLANNER_ICEM && (p->h % 2) == 0 && p->K <= 32 &&
+         p->d <= kSamplerThreads && !p->force_warp_sampler;
+}
+
+template <int KPAD>
+static void launch_series_sampler_k(icem_planner* p, const RolloutArgs& a, int rows_max) {
+  const SamplerConst sc = sampler_const(p);
+  const int R = sampler_rows_per_batch(p->d, a.stride);
+  const size_t smem = sampler_smem_bytes(p->h, p->d, KPAD, a.stride, R);
+  auto kern = colored_sampler_kernel<KPAD>;
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    ICEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int occ = 0;
+  ICEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSamplerThreads, smem));
+  if (occ < 1) throw InvalidArg("sampler kernel does not fit on an SM (shared memory)");
+  const int batches = (rows_max + R - 1) / R;
+  const int grid = std::max(1, std::min(batches, p->sm_count * occ));
+  kern<<<grid, kSamplerThreads, smem, p->stream>>>(a, sc, R);
+  ICEM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+static void launch_series_sampler(icem_planner* p, const RolloutArgs& a, int rows_max) {
+  if (p->K <= 8) launch_series_sampler_k<8>(p, a, rows_max);
+  else if (p->K <= 16) launch_series_sampler_k<16>(p, a, rows_max);
+  else launch_series_sampler_k<32>(p, a, rows_max);
+}
+
 template <bool kSample, bool kRollout>
 static void launch_rollout_dyn(icem_planner* p, const RolloutArgs& a, int rows_max) {
+  if (kSample && !kRollout && series_sampler_eligible(p)) {
+    launch_series_sampler(p, a, rows_max);
+    return;
+  }
   switch (p->cfg.dynamics) {
     case ICEM_DYN_MLP: {
       if (kSample) {
-        NoDyn::Params np{p->d};
-        launch_rollout<NoDyn, true, false>(p, a, np, rows_max);
+        if (series_sampler_eligible(p)) {
+          launch_series_sampler(p, a, rows_max);
+        } else {
+          NoDyn::Params np{p->d};
+          launch_rollout<NoDyn, true, false>(p, a, np, rows_max);
+        }
       }
       if (kRollout) launch_mlp(p, a, rows_max);
       break;
@@ -609,6 +652,7 @@ int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
     p->cfg.execute_best_elite = 1; p->cfg.shift_means = 1; p->cfg.bounds_like_levine = 0;
   }
   p->white = cem_std || !(cfg->noise_beta > 0);
+  { const char* e = getenv("ICEM_B200_WARP_SAMPLER"); p->force_warp_sampler = e && e[0] == '1'; }
   p->low.assign(cfg->action_low, cfg->action_low + p->d);
   p->high.assign(cfg->action_high, cfg->action_high + p->d);
   p->cfg.action_low = p->low.data();

@@ -90,3 +90,55 @@ def test_plan_step_runs_and_improves_cost():
         assert np.abs(ref - costs).max() <= 8e-2
         st, _, _ = p.sim_step(st, a)
     p.close()
+
+
+def test_series_sampler_inside_the_plan_step():
+    """The MLP path samples with the stand-alone thread-per-series kernel (csrc/sampler.cuh).  Inside the graph-captured
+    plan step it must honour: injected draws (icem.py:73-79), shifted elites appended after the fresh rows at
+    iteration 0 of every later step (icem.py:91-104, 131-137), the mean written over row 0 on the last iteration
+    (icem.py:87-88), and Philox production draws with the reference sampler's statistics."""
+    from oracle.shims import colorednoise as cn
+    h, d, n = 12, 6, 2048
+    p, _ = _planner(256, n=n)
+    p.begin_rollout()
+    rs = np.random.RandomState(3)
+    K = h // 2 + 1
+    zr, zi = rs.standard_normal((n, d, K)), rs.standard_normal((n, d, K))
+    p.inject_noise(0, zr, zi)
+    for i in (1, 2):          # parity mode needs every iteration's draws
+        ni = p.population_size(i, first_step=True)[1]
+        p.inject_noise(i, rs.standard_normal((ni, d, K)), rs.standard_normal((ni, d, K)))
+    st = 0.1 * rs.randn(18)
+    a0 = p.plan(st)
+    y = cn.synthesize(zr.copy(), zi.copy(), 0.25, h).transpose(0, 2, 1)
+    ref = np.clip(y * 0.5 + 0.0, -1, 1)
+    got = p.actions(0, n)
+    assert np.abs(got - ref).max() <= 4e-6 + 1e-7
+    # last iteration: row 0 is the mean the iteration sampled from (the refit result of the one before)
+    n2 = p.population_size(2, first_step=True)[1]
+    np.testing.assert_array_equal(p.actions(2, n2)[0], p.iteration_record(1)["mean"].astype(np.float32))
+    elites, _, _ = p.elites()
+    # second step, production noise: 3 shifted elites follow the n fresh rows
+    st, _, _ = p.sim_step(st, a0)
+    mean_before = p.mean().astype(np.float64)          # already time-shifted (icem.py:167-171)
+    p.plan(st)
+    rows = p.population_size(0, first_step=False)[1]
+    assert rows == n + 3
+    acts = p.actions(0, rows)
+    np.testing.assert_array_equal(acts[n:, :-1], elites[:3, 1:])
+    assert np.all(np.abs(acts[n:, -1]) <= 1.0) and np.abs(acts[n:, -1] - mean_before[-1]).max() > 1e-3
+    # fresh rows: unit-variance colored noise around the shifted mean with the reset std 0.5, clipped
+    np.random.seed(0)
+    refn = cn.powerlaw_psd_gaussian(0.25, (n, d, h)).transpose(0, 2, 1)
+    ref_a = np.clip(refn * 0.5 + mean_before, -1, 1)
+    fresh = acts[:n].astype(np.float64)
+    assert np.abs(fresh.mean(0) - ref_a.mean(0)).max() < 0.06
+    assert np.abs(fresh.std(0) - ref_a.std(0)).max() < 0.05
+    z, zref = fresh - mean_before, ref_a - mean_before
+    ac = lambda x: np.mean(x[:, 1:] * x[:, :-1]) / np.mean(x * x)
+    assert abs(ac(z) - ac(zref)) < 0.04
+    assert abs((np.abs(fresh) == 1.0).mean() - (np.abs(ref_a) == 1.0).mean()) < 0.02
+    # no two series share draws: correlation between action dims / neighbouring rows ~ 0
+    assert abs(np.mean(z[:, :, 0] * z[:, :, 1]) / np.mean(z * z)) < 0.05
+    assert abs(np.mean(z[1:, :, 0] * z[:-1, :, 0]) / np.mean(z * z)) < 0.05
+    p.close()

@@ -30,10 +30,21 @@ def _planner(case, **over):
     return p, model
 
 
-@pytest.mark.parametrize("h,d,beta,v2", [(30, 6, 0.25, False), (30, 17, 2.0, False), (12, 6, 0.25, False),
-                                          (30, 6, 1.0, True), (7, 3, 0.5, False), (30, 6, 0.0, False)])
-def test_sampler_matches_irfft_path(h, d, beta, v2):
-    """T1: fused colored-noise synthesis + affine + clip vs the irfft restatement on identical draws."""
+@pytest.mark.parametrize("h,d,beta,v2,n", [(30, 6, 0.25, False, 300), (30, 17, 2.0, False, 300),
+                                            (12, 6, 0.25, False, 300), (30, 6, 1.0, True, 300),
+                                            (7, 3, 0.5, False, 300), (30, 6, 0.0, False, 300),
+                                            (30, 17, 2.0, False, 20011), (12, 6, 0.25, False, 70001),
+                                            (40, 5, 1.0, False, 3000), (2, 3, 0.5, False, 100),
+                                            (62, 2, 2.0, False, 1000), (64, 2, 2.0, False, 200)])
+@pytest.mark.parametrize("warp_sampler", [False, True])
+def test_sampler_matches_irfft_path(h, d, beta, v2, n, warp_sampler, monkeypatch):
+    """T1: colored-noise synthesis + affine + clip vs the irfft restatement on identical draws, for both device
+    samplers: the thread-per-series kernel (csrc/sampler.cuh; even h <= 62, several row batches per CTA at the
+    large n) and the warp-per-trajectory one of the fused kernel (csrc/rollout.cuh; also odd h, white noise)."""
+    if warp_sampler:
+        if n > 3000:
+            pytest.skip("one size is enough for the A/B leg")
+        monkeypatch.setenv("ICEM_B200_WARP_SAMPLER", "1")
     from icem_b200.planner import Planner, PlannerSettings
     rs = np.random.RandomState(1)
     low = -np.abs(rs.uniform(0.3, 1.0, d)).astype(np.float32)
@@ -41,7 +52,6 @@ def test_sampler_matches_irfft_path(h, d, beta, v2):
     p = Planner(PlannerSettings(horizon=h, num_simulated_trajectories=8, action_low=low, action_high=high,
                                 noise_beta=beta, obs_dim=17, colorednoise_v2=v2))
     p.set_dense_model(np.eye(17), np.zeros((17, d)))
-    n = 300
     mean = rs.uniform(-0.2, 0.2, (h, d))
     std = rs.uniform(0.1, 0.6, (h, d))
     if beta > 0:
