@@ -113,25 +113,16 @@ colored_sampler_kernel(RolloutArgs a, SamplerConst sc, int rows_per_batch) {
         }
       }
       // ---- folded synthesis + affine + clip -> tile ---------------------------------------------
-      // mean row (icem.py:87-88) and shifted elites (icem.py:91-104) touch <= 1 + n_keep rows of a population:
-      // they take the fix-up branch, every other thread runs the 5-instruction emit
-      const bool mean_row = a.inject_mean_row0 && grow == 0u && !shifted;
-      const bool special = mean_row || shifted;
-      const float* elite = shifted ? a.prev_elites + (size_t)(row - a.n_fresh_local) * stride + dim + d : nullptr;
       const float2* pm = s_ms + dim;
       float* po = tile + r * stride + dim;
-      const int last = (h - 1) * d;
       auto emit = [&](int o, float y) {          // o = t * d
         const float2 ms = pm[o];
-        float v = fminf(fmaxf(fmaf(y, ms.y, ms.x), lo), hi);
-        if (__builtin_expect(special, 0)) {
-          if (mean_row) v = ms.x;
-          else if (o < last) v = elite[o];
-        }
-        po[o] = v;
+        po[o] = fminf(fmaxf(fmaf(y, ms.y, ms.x), lo), hi);
       };
       int o0 = 0, o1 = h * d, o2 = half * d, o3 = half * d;     // t*d, (h-t)*d, (half-t)*d, (half+t)*d
       for (int t = 0; t <= Q; ++t, o0 += d, o1 -= d, o2 -= d, o3 += d) {
+        // keep the four running offsets in registers (ptxas otherwise re-derives each from t with IMADs)
+        asm volatile("" : "+r"(o0), "+r"(o1), "+r"(o2), "+r"(o3));
         const float4* c4 = reinterpret_cast<const float4*>(s_c + t * KPAD);
         const float4* s4 = reinterpret_cast<const float4*>(s_s + t * KPAD);
         float ce = 0.f, co = 0.f, se = 0.f, so = 0.f;
@@ -149,6 +140,17 @@ colored_sampler_kernel(RolloutArgs a, SamplerConst sc, int rows_per_batch) {
         if (o2 > o0) {
           emit(o2, cm - sm);
           if (t > 0) emit(o3, cm + sm);
+        }
+      }
+      // mean row (icem.py:87-88) and shifted elites (icem.py:91-104) are <= 1 + n_keep rows of a population:
+      // their threads overwrite what they just sampled (a shifted row keeps its fresh LAST action)
+      const bool mean_row = a.inject_mean_row0 && grow == 0u && !shifted;
+      if (mean_row | shifted) {
+        const float* elite = a.prev_elites + (size_t)(shifted ? row - a.n_fresh_local : 0) * stride + dim + d;
+        for (int t = 0; t < h; ++t) {
+          const int o = t * d;
+          if (mean_row) po[o] = pm[o].x;
+          else if (t < h - 1) po[o] = elite[o];
         }
       }
     }
