@@ -246,7 +246,7 @@ def run_ours(args):
                     "kernel": "mlp_rollout_kernel (tcgen05.mma, bf16 operands, fp32 accumulate in TMEM)",
                     "kernel_ms_avg": ms, "kernel_rows": n0,
                     "algorithmic_flops_per_trajectory": flops / n0,
-                    "note": "epilogue-bound: 2*H tanh + bf16 pack per trajectory-step on CUDA cores between MMAs"}
+                    "note": "latency-chain + MUFU bound: one 128-row tile per SM (resident weights fill shared memory), per step L1 MMA -> tanh epilogue (MUFU 16/clk/SM) -> L2 MMAs pipelined under it -> tanh epilogue -> L3; see DESIGN.md section 9 for the measured per-step timeline"}
     planner.close()
 
     # ---- end to end through the plugin API with host buffers: `e2e` ------------------------------------

@@ -6,16 +6,21 @@
 //     obs' = obs + W3 tanh(W2 tanh(W1 [obs, act] + b1) + b2) + b3            (2 hidden layers of width H)
 // followed by the per-step cost on the PRE-action observation (controllers/abstract_controller.py:74-91).
 //
-// One CTA = one tile of 128 trajectories; 512 threads: thread (q, lane, g) with warp = 4 g + q owns trajectory row
-// r = 32 q + lane (TMEM lane r; a warp may only touch the lane quarter warp % 4) and every 4th 32-column chunk
-// of the hidden layer in the epilogues; the fp32 observation is replicated in the 4 threads of a row.  The three weight
-// matrices stay RESIDENT in shared memory as bf16 in the tcgen05 K-major no-swizzle core-matrix layout
-// ([n/8][k/8][n%8][k%8], 128-byte core matrices) for the whole kernel; per control step:
-//     X[128 x 32] (bf16, smem)  --tcgen05.mma M128 N=H K=16 x2-->  D[128 x H] fp32 in TMEM
-//     epilogue: tcgen05.ld 32x32b.x32 -> +bias, tanh.approx -> bf16 -> smem (the next MMA's A operand)
-//     H1[128 x H] --16 MMAs--> D ; epilogue ; H2 --16 MMAs (N=32)--> D[128 x 32] ; obs += D + b3 (fp32 registers)
-// MMAs are issued by ONE thread and tracked with tcgen05.commit on an mbarrier; accumulators never leave TMEM
-// except through the epilogue loads.  Actions come from the sampler kernel's HBM/L2 tiles.
+// One CTA = one tile of 128 trajectories.  16 epilogue warps + 1 MMA-issuer warp (warp specialisation, no CTA-wide
+// barrier inside the rollout): epilogue thread (q, lane, g), warp = 4 g + q, owns trajectory row r = 32 q + lane
+// (TMEM lane r; a warp may only touch the lane quarter warp % 4) and the 16 columns g*16.. of every 64-column
+// STAGE of a hidden layer; the fp32 observation is replicated in the 4 threads of a row.  The three weight matrices
+// stay RESIDENT in shared memory as bf16 in the tcgen05 K-major no-swizzle core-matrix layout
+// ([n/8][k/8][n%8][k%8], 128-byte core matrices) for the whole kernel.  Per control step:
+//     X[128 x 32] (bf16, smem) --2 MMAs M128 N=H K=16--> D1[128 x H] fp32 in TMEM (columns 0..H)
+//     epilogue 1, stage by stage: tcgen05.ld 32x32b.x16 -> +bias, tanh.approx -> bf16 -> smem; as soon as a stage
+//       (64 columns = 4 K-steps of the next layer's A operand) is in shared memory its warps arrive on that stage's
+//       mbarrier and the issuer accumulates those K-steps into D2 (TMEM columns 256..256+H): the layer-2 MMAs run
+//       UNDER the layer-1 epilogue instead of after it
+//     epilogue 2 (from D2), same stage pipeline into the N=32 output MMAs -> D3 (TMEM columns 0..32)
+//     obs += D3 + b3 (fp32 registers)
+// MMAs are issued by ONE thread and tracked with tcgen05.commit on mbarriers; accumulators never leave TMEM except
+// through the epilogue loads.  Actions come from the sampler kernel's HBM/L2 tiles, prefetched one step ahead.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -25,14 +30,19 @@
 namespace icem {
 
 constexpr int kMlpTile = 128;     // trajectories per CTA tile (UMMA M)
-constexpr int kMlpColGroups = 4;  // threads per trajectory row: each takes every 4th 32-column chunk in the epilogues
-constexpr int kMlpThreads = kMlpTile * kMlpColGroups;   // 16 warps: 4 per scheduler hide the TMEM / MUFU latency
+constexpr int kMlpColGroups = 4;  // threads per trajectory row: each takes 16 columns of every 64-column stage
+constexpr int kMlpEpiThreads = kMlpTile * kMlpColGroups;   // 16 epilogue warps: 4 per scheduler hide TMEM / MUFU latency
+constexpr int kMlpThreads = kMlpEpiThreads + 32;           // + the MMA-issuer warp
+constexpr int kMlpStageCols = 64; // hidden columns per pipeline stage (= 4 K-steps of the next layer's MMA)
+constexpr int kMlpMaxStages = 4;  // hidden <= 256
+constexpr uint32_t kMlpTmemCols = 512;   // D1 / D3 at column 0, D2 at column 256
 constexpr int kMlpInPad = 32;     // padded input width (obs + act <= 32)
 constexpr int kMlpOutPad = 32;    // padded output width (obs <= 32)
 
 struct MlpParams {
   int obs_dim, act_dim, hidden;               // hidden in {64, 128, 256}
-  const __nv_bfloat16* w1;                    // packed [hidden x kMlpInPad]
+  int act_off;                                // input column of action 0: obs_dim rounded up to 8 (act_off + act_dim <= 32)
+  const __nv_bfloat16* w1;                    // packed [hidden x kMlpInPad], columns [obs | 0 | act | 0]
   const __nv_bfloat16* w2;                    // packed [hidden x hidden]
   const __nv_bfloat16* w3;                    // packed [kMlpOutPad x hidden]
   const float* bias;                          // [hidden + hidden + kMlpOutPad]
@@ -78,7 +88,46 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// 8 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// split form: issue now, tcgen05.wait::ld later (the registers are undefined until the wait)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar)) : "memory");
+}
 __device__ __forceinline__ float tanh_approx(float x) {
+#if defined(ICEM_MLP_EXP) && ICEM_MLP_EXP == 1        // timing experiment: no MUFU
+  return x * 0.5f;
+#endif
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
@@ -109,8 +158,17 @@ inline size_t mlp_smem_bytes(int hidden) {
   const size_t w = ((size_t)hidden * kMlpInPad + (size_t)hidden * hidden + (size_t)kMlpOutPad * hidden) * 2;
   const size_t a = (size_t)kMlpTile * hidden * 2;
   const size_t b = ((size_t)2 * hidden + kMlpOutPad) * 4;
-  return w + a + b + 64;
+  return w + a + b + 128;     // + mbarriers (1 + 4 + 3) and the TMEM slot
 }
+
+#ifdef ICEM_MLP_TRACE
+// debug build only (python -m icem_b200.build with defines=["ICEM_MLP_TRACE"]): cycle stamps of CTA 0's first steps
+__device__ long long g_mlp_trace[64 * 32];
+#define MLP_TRACE(step, slot) do { if (blockIdx.x == 0 && (step) < 64u && lane == 0 && q == 0 && (g == 0 || g == kMlpColGroups)) \
+    g_mlp_trace[(step) * 32 + (slot)] = clock64(); } while (0)
+#else
+#define MLP_TRACE(step, slot) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kMlpThreads, 1)
@@ -122,15 +180,18 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
   __nv_bfloat16* sW3 = sW2 + (size_t)H * H;
   __nv_bfloat16* sA = sW3 + (size_t)kMlpOutPad * H;                   // [128 x max(H, 32)] activations
   float* sBias = reinterpret_cast<float*>(sA + (size_t)kMlpTile * H);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sBias + 2 * H + kMlpOutPad);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* bar_x = reinterpret_cast<uint64_t*>(sBias + 2 * H + kMlpOutPad);   // X operand in smem      (16 arrivals)
+  uint64_t* bar_a = bar_x + 1;                // [4] activation stage s in smem: layer 1 / layer 2 alternate (16 arrivals)
+  uint64_t* bar_d = bar_a + kMlpMaxStages;    // [3] accumulators D1, D2, D3 complete (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d + 3);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int q = warp & 3, g = warp >> 2;             // TMEM lane quarter, column group
-  const int r = q * 32 + (tid & 31);                 // trajectory row inside the tile
-  const int h = sc.h, d = sc.d, od = mp.obs_dim;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, g = warp >> 2;             // TMEM lane quarter, column group (g == 4: the issuer warp)
+  const int r = q * 32 + lane;                       // trajectory row inside the tile
+  const int h = sc.h, d = sc.d, od = mp.obs_dim, act_off = mp.act_off;
+  const int S = H / kMlpStageCols;                   // pipeline stages per hidden layer (H in {64, 128, 256})
 
-  // ---- one-time: resident weights, barrier, TMEM ----
+  // ---- one-time: resident weights, barriers, TMEM ----
   {
     const uint4* src1 = reinterpret_cast<const uint4*>(mp.w1);
     uint4* dst1 = reinterpret_cast<uint4*>(sW1);
@@ -144,66 +205,117 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
     for (int i = tid; i < 2 * H + kMlpOutPad; i += blockDim.x) sBias[i] = mp.bias[i];
   }
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(bar_x, kMlpEpiThreads / 32);
+    for (int s = 0; s < kMlpMaxStages; ++s) mbar_init(&bar_a[s], kMlpEpiThreads / 32);
+    for (int i = 0; i < 3; ++i) mbar_init(&bar_d[i], 1);
     mbar_fence_init();
   }
-  const uint32_t tmem_cols = H <= 64 ? 64u : (H <= 128 ? 128u : 256u);
-  if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == 0) tmem_alloc(tmem_slot, kMlpTmemCols);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);      // this warp's 32 lanes
+  const uint32_t tmem_d2 = tmem_base + 256u;
 
   const uint32_t idesc_h = umma_idesc_bf16(kMlpTile, H);
   const uint32_t idesc_o = umma_idesc_bf16(kMlpTile, kMlpOutPad);
   const uint32_t sbo_in = (kMlpInPad / 8) * 128, sbo_h = (uint32_t)(H / 8) * 128;
-  uint32_t phase = 0;
 
   const StepState ss = *a.ss;
   const int n_rows = a.n_fresh_local + ((a.iteration == 0 && ss.has_prev_elites) ? a.n_shift_local : 0);
-  unsigned char* rowA = reinterpret_cast<unsigned char*>(sA) + (size_t)(r & 7) * 16;     // + (r/8)*SBO + chunk*128
+  uint32_t n = 0;      // control steps done by this CTA: bar_x / bar_d[*] complete once per step, bar_a[*] twice
 
-  for (int tile0 = blockIdx.x * kMlpTile; tile0 < n_rows; tile0 += gridDim.x * kMlpTile) {
-    const int row = tile0 + r;
-    const bool valid = row < n_rows;
-    float x[kMlpInPad];                      // [obs(od), act(d), 0...]: the fp32 state of this trajectory
+  if (g == kMlpColGroups) {
+    // ================= MMA issuer: one thread =================
+    if (lane == 0) {
+      const unsigned char* pA = reinterpret_cast<const unsigned char*>(sA);
+      const unsigned char* pW1 = reinterpret_cast<const unsigned char*>(sW1);
+      const unsigned char* pW2 = reinterpret_cast<const unsigned char*>(sW2);
+      const unsigned char* pW3 = reinterpret_cast<const unsigned char*>(sW3);
+      for (int tile0 = blockIdx.x * kMlpTile; tile0 < n_rows; tile0 += gridDim.x * kMlpTile) {
+        for (int t = 0; t + 1 < h; ++t, ++n) {
+          // layer 1: X -> D1
+          mbar_wait(bar_x, n & 1);
+          MLP_TRACE(n, 16);
+          tc_fence_after();
 #pragma unroll
-    for (int i = 0; i < kMlpInPad; ++i) x[i] = (valid && i < od) ? a.start_state[i] : 0.f;
-    const float* acts = a.actions + (size_t)(valid ? row : 0) * a.stride;
-    float total = (cc.reduce == 1) ? INFINITY : 0.f;
-
-    for (int t = 0; t < h; ++t) {
-      // ---- action of this step, per-step cost on the pre-action observation ----
-      float a2 = 0.f, oa = 0.f, ob = 0.f;
+          for (int ks = 0; ks < kMlpInPad / 16; ++ks)
+            tc_mma_bf16(tmem_base, umma_desc(pA + ks * 256, 128, sbo_in), umma_desc(pW1 + ks * 256, 128, sbo_in),
+                        idesc_h, ks > 0);
+          tc_commit(&bar_d[0]);
+          // layer 2: H1 stages -> D2, accumulated as the stages land in shared memory
+          for (int s = 0; s < S; ++s) {
+            mbar_wait(&bar_a[s], 0);
+            MLP_TRACE(n, 17 + s);
+            tc_fence_after();
 #pragma unroll
-      for (int i = 0; i < kMlpInPad; ++i) {
-        if (i >= od && i < od + d) {
-          x[i] = valid ? acts[t * d + (i - od)] : 0.f;
-          a2 = fmaf(x[i], x[i], a2);
+            for (int k4 = 0; k4 < kMlpStageCols / 16; ++k4) {
+              const int ks = s * (kMlpStageCols / 16) + k4;
+              tc_mma_bf16(tmem_d2, umma_desc(pA + ks * 256, 128, sbo_h), umma_desc(pW2 + ks * 256, 128, sbo_h),
+                          idesc_h, ks > 0);
+            }
+          }
+          tc_commit(&bar_d[1]);
+          // output layer: H2 stages -> D3 (over D1's first columns: D1 was consumed before any H2 stage existed)
+          for (int s = 0; s < S; ++s) {
+            mbar_wait(&bar_a[s], 1);
+            MLP_TRACE(n, 21 + s);
+            tc_fence_after();
+#pragma unroll
+            for (int k4 = 0; k4 < kMlpStageCols / 16; ++k4) {
+              const int ks = s * (kMlpStageCols / 16) + k4;
+              tc_mma_bf16(tmem_base, umma_desc(pA + ks * 256, 128, sbo_h), umma_desc(pW3 + ks * 256, 128, sbo_h),
+                          idesc_o, ks > 0);
+            }
+          }
+          tc_commit(&bar_d[2]);
+          MLP_TRACE(n, 25);
         }
-        oa = (i == cc.idx_a) ? x[i] : oa;
-        ob = (i == cc.idx_b) ? x[i] : ob;
       }
-      float c;
-      if (cc.kind == 0) {
-        c = 0.1f * a2 - ob;
-        if (cc.penalise_flipping) c += (oa > 1.5707963267948966f ? 10.f : 0.f) + (oa < -1.5707963267948966f ? 10.f : 0.f);
-      } else {
-        c = -oa + 0.1f * a2;
-      }
-      if (cc.reduce == 0) total += c;
-      else if (cc.reduce == 1) total = fminf(total, c);
-      else total = c;
-      if (t + 1 == h) break;                 // the final predicted state is never scored
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue warps =================
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;               // this warp's 32 TMEM lanes
+    unsigned char* rowA = reinterpret_cast<unsigned char*>(sA) + (size_t)(r & 7) * 16;   // + (r/8)*SBO + chunk*128
+    unsigned char* dstX = rowA + (size_t)(r >> 3) * sbo_in;
+    unsigned char* dstH = rowA + (size_t)(r >> 3) * sbo_h;
 
-      // ---- X row -> smem (bf16, K-major core matrices), layer 1: thread g writes 16-byte chunk g ----
-      {
-        unsigned char* dst = rowA + (size_t)(r >> 3) * sbo_in;
+    for (int tile0 = blockIdx.x * kMlpTile; tile0 < n_rows; tile0 += gridDim.x * kMlpTile) {
+      const int row = tile0 + r;
+      const bool valid = row < n_rows;
+      // fp32 state of this trajectory in input-column order [obs(od) | 0 | act(d) at act_off | 0].  Thread g keeps
+      // only what it uses current: its own 8-column chunk (the X operand chunk it packs); g == 0 keeps the whole
+      // observation (it evaluates the cost).  Action columns are (re)loaded by the threads whose chunk holds them.
+      float x[kMlpInPad];
+#pragma unroll
+      for (int i = 0; i < kMlpInPad; ++i) x[i] = (valid && i < od) ? a.start_state[i] : 0.f;
+      const float* acts = a.actions + (size_t)(valid ? row : 0) * a.stride;
+      float total = (cc.reduce == 1) ? INFINITY : 0.f;
+      const bool holds_act = g >= (act_off >> 3);        // warp-uniform: chunk g overlaps [act_off, act_off + d)
+      // action of step t -> x[act_off .. act_off + d): act_off is a multiple of 8, so each case is static indexing.
+      // Loads only: nothing consumes them before the next step's cost / pack, so their latency is never waited on.
+#define ICEM_FOR_ACT(OFF, BODY) \
+      _Pragma("unroll") for (int m = 0; m < kMlpInPad - OFF; ++m) if (m < d) { float& xa = x[OFF + m]; BODY; }
+#define ICEM_ACT_CASES(BODY)                          \
+      if (act_off == 24) { ICEM_FOR_ACT(24, BODY) }   \
+      else if (act_off == 16) { ICEM_FOR_ACT(16, BODY) } \
+      else { ICEM_FOR_ACT(8, BODY) }
+      auto load_action = [&](int t) {
+        if (!(holds_act || g == 0)) return;
+        const float* at = acts + t * d;
+        ICEM_ACT_CASES(xa = valid ? at[m] : 0.f)
+      };
+      load_action(0);
+
+      for (int t = 0; t < h; ++t) {
+
+        // ---- X row -> smem (bf16, K-major core matrices), layer 1: thread g writes 16-byte chunk g ----
+        const bool last = t + 1 == h;          // the final predicted state is never scored: no transition after it
 #pragma unroll
         for (int ch = 0; ch < kMlpInPad / 8; ++ch) {
-          if (ch == g) {
+          if (ch == g && !last) {
             __nv_bfloat162 p0 = __floats2bfloat162_rn(x[8 * ch], x[8 * ch + 1]);
             __nv_bfloat162 p1 = __floats2bfloat162_rn(x[8 * ch + 2], x[8 * ch + 3]);
             __nv_bfloat162 p2 = __floats2bfloat162_rn(x[8 * ch + 4], x[8 * ch + 5]);
@@ -211,77 +323,128 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
             uint4 v;
             v.x = *reinterpret_cast<uint32_t*>(&p0); v.y = *reinterpret_cast<uint32_t*>(&p1);
             v.z = *reinterpret_cast<uint32_t*>(&p2); v.w = *reinterpret_cast<uint32_t*>(&p3);
-            *reinterpret_cast<uint4*>(dst + ch * 128) = v;
+            *reinterpret_cast<uint4*>(dstX + ch * 128) = v;
           }
         }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < kMlpInPad / 16; ++ks)
-          tc_mma_bf16(tmem_base, umma_desc(reinterpret_cast<unsigned char*>(sA) + ks * 256, 128, sbo_in),
-                      umma_desc(reinterpret_cast<unsigned char*>(sW1) + ks * 256, 128, sbo_in), idesc_h, ks > 0);
-        tc_commit(bar);
-      }
-      // ---- hidden layers: epilogue (bias + tanh -> bf16 A operand), next MMA ----
-      for (int layer = 0; layer < 2; ++layer) {
-        mbar_wait(bar, phase);
-        phase ^= 1;
-        tc_fence_after();
-        const float* bs = sBias + layer * H;
-        unsigned char* dst = rowA + (size_t)(r >> 3) * sbo_h;
-        for (int c0 = g * 32; c0 < H; c0 += 32 * kMlpColGroups) {      // 32-column chunks dealt round-robin
-          float v[32];
-          tmem_ld32(taddr + (uint32_t)c0, v);
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int k = 8 * ch + 2 * q;
-              __nv_bfloat162 pr = __floats2bfloat162_rn(tanh_approx(v[k] + bs[c0 + k]),
-                                                        tanh_approx(v[k + 1] + bs[c0 + k + 1]));
-              pk[q] = *reinterpret_cast<uint32_t*>(&pr);
-            }
-            *reinterpret_cast<uint4*>(dst + (size_t)(c0 / 8 + ch) * 128) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
+        if (!last) {
+          fence_proxy_async_smem();
+          tc_fence_before();                   // the out-epilogue's TMEM loads precede the next layer-1 MMA
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_x);
+          MLP_TRACE(n, 0);
         }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+        // ---- per-step cost on the pre-action observation: one thread per row, AFTER the X operand
+        // is handed to the MMA issuer so that it is off the step's critical path ----
+        if (g == 0) {
+          float oa = 0.f, ob = 0.f, a2 = 0.f;
+          ICEM_ACT_CASES(a2 = fmaf(xa, xa, a2))
+#pragma unroll
+          for (int i = 0; i < kMlpInPad; ++i) {
+            oa = (i == cc.idx_a) ? x[i] : oa;
+            ob = (i == cc.idx_b) ? x[i] : ob;
+          }
+          float c;
+          if (cc.kind == 0) {
+            c = 0.1f * a2 - ob;
+            if (cc.penalise_flipping)
+              c += (oa > 1.5707963267948966f ? 10.f : 0.f) + (oa < -1.5707963267948966f ? 10.f : 0.f);
+          } else {
+            c = -oa + 0.1f * a2;
+          }
+          if (cc.reduce == 0) total += c;
+          else if (cc.reduce == 1) total = fminf(total, c);
+          else total = c;
+        }
+        if (last) break;
+
+        // ---- hidden layers: epilogue stage by stage (bias + tanh -> bf16 A operand of the next MMA) ----
+#pragma unroll 1
+        for (int layer = 0; layer < 2; ++layer) {
+          mbar_wait(&bar_d[layer], n & 1);
+          MLP_TRACE(n, 1 + 6 * layer);
           tc_fence_after();
-          const unsigned char* wB = reinterpret_cast<const unsigned char*>(layer == 0 ? sW2 : sW3);
-          const uint32_t id = layer == 0 ? idesc_h : idesc_o;
-          for (int ks = 0; ks < H / 16; ++ks)
-            tc_mma_bf16(tmem_base, umma_desc(reinterpret_cast<unsigned char*>(sA) + ks * 256, 128, sbo_h),
-                        umma_desc(wB + ks * 256, 128, sbo_h), id, ks > 0);
-          tc_commit(bar);
-        }
-      }
-      // ---- output layer epilogue: obs += W3 h2 + b3 (fp32 state in registers) ----
-      mbar_wait(bar, phase);
-      phase ^= 1;
-      tc_fence_after();
-      {
-        float v[32];
-        tmem_ld32(taddr, v);
-        const float* b3 = sBias + 2 * H;
+          const float* bs = sBias + layer * H;
+          const uint32_t dcol = lane_addr + (layer == 0 ? tmem_base : tmem_d2);
+          // TMEM loads run one stage ahead of the arithmetic: stage s+1's tcgen05.ld is in flight while stage s
+          // goes through the MUFU / pack / store sequence (tcgen05.wait::ld waits for everything issued so far)
+          uint32_t raw[2][16];
+          tmem_ld16_issue(dcol + (uint32_t)(g * 16), raw[0]);
 #pragma unroll
-        for (int i = 0; i < kMlpOutPad; ++i)
-          if (i < od) x[i] += v[i] + b3[i];
+          for (int s = 0; s < kMlpMaxStages; ++s) {
+            if (s < S) {
+              const int c0 = s * kMlpStageCols + g * 16;
+              tmem_ld_wait();
+              if (s + 1 < S) tmem_ld16_issue(dcol + (uint32_t)(c0 + kMlpStageCols), raw[(s + 1) & 1]);
+              const uint32_t* rv = raw[s & 1];
+              const float4* b4 = reinterpret_cast<const float4*>(bs + c0);
+              uint32_t pk[8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 b = b4[j];
+                __nv_bfloat162 lo2 = __floats2bfloat162_rn(tanh_approx(__uint_as_float(rv[4 * j]) + b.x),
+                                                           tanh_approx(__uint_as_float(rv[4 * j + 1]) + b.y));
+                __nv_bfloat162 hi2 = __floats2bfloat162_rn(tanh_approx(__uint_as_float(rv[4 * j + 2]) + b.z),
+                                                           tanh_approx(__uint_as_float(rv[4 * j + 3]) + b.w));
+                pk[2 * j] = *reinterpret_cast<uint32_t*>(&lo2);
+                pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi2);
+              }
+              unsigned char* dst = dstH + (size_t)(c0 / 8) * 128;
+              *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(dst + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              fence_proxy_async_smem();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&bar_a[s]);
+              MLP_TRACE(n, 2 + 6 * layer + s);
+            }
+          }
+        }
+        // the next step's action.  Issued HERE, after this step's last proxy fence: fence.proxy.async is a
+        // MEMBAR that waits for every outstanding global load of the thread (measured: ~1000 cycles per step
+        // when the loads were issued before the epilogues); now they land while the output MMAs drain.
+        load_action(t + 1);
+
+        // ---- output layer epilogue: obs += W3 h2 + b3 (fp32 state in registers).  W3 rows / b3 entries past
+        // obs_dim are zero, so the padding and action columns receive + 0. ----
+        mbar_wait(&bar_d[2], n & 1);
+        MLP_TRACE(n, 13);
+        tc_fence_after();
+        if (g == 0) {
+          float v[32];
+          tmem_ld32(lane_addr + tmem_base, v);
+          const float4* b3 = reinterpret_cast<const float4*>(sBias + 2 * H);
+#pragma unroll
+          for (int j = 0; j < kMlpOutPad / 4; ++j) {
+            const float4 b = b3[j];
+            x[4 * j] += v[4 * j] + b.x;         x[4 * j + 1] += v[4 * j + 1] + b.y;
+            x[4 * j + 2] += v[4 * j + 2] + b.z; x[4 * j + 3] += v[4 * j + 3] + b.w;
+          }
+        } else {
+          float v[8];
+          tmem_ld8(lane_addr + tmem_base + (uint32_t)(8 * g), v);
+          const float4* b3 = reinterpret_cast<const float4*>(sBias + 2 * H + 8 * g);
+          const float4 b0 = b3[0], b1 = b3[1];
+#pragma unroll
+          for (int ch = 1; ch < kMlpInPad / 8; ++ch) {
+            if (ch == g) {
+              x[8 * ch] += v[0] + b0.x;     x[8 * ch + 1] += v[1] + b0.y;
+              x[8 * ch + 2] += v[2] + b0.z; x[8 * ch + 3] += v[3] + b0.w;
+              x[8 * ch + 4] += v[4] + b1.x; x[8 * ch + 5] += v[5] + b1.y;
+              x[8 * ch + 6] += v[6] + b1.z; x[8 * ch + 7] += v[7] + b1.w;
+            }
+          }
+        }
+        MLP_TRACE(n, 14);
+        ++n;
       }
-      tc_fence_before();      // the next step's MMA overwrites these TMEM columns after the CTA barrier above it
+      if (valid && g == 0) a.costs[row] = total;
     }
-    if (valid && g == 0) a.costs[row] = total;
-    __syncthreads();
+#undef ICEM_ACT_CASES
+#undef ICEM_FOR_ACT
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == 0) tmem_dealloc(tmem_base, kMlpTmemCols);
 }
 
 // one transition of the same model for a single state (env.step on the device model / closed-loop bench):
@@ -292,7 +455,9 @@ __global__ void mlp_advance_kernel(MlpParams mp, const float* state, const float
   __shared__ float h1[256], h2[256];
   const int H = mp.hidden, od = mp.obs_dim, d = mp.act_dim, tid = threadIdx.x;
   auto bf = [](float v) { return __bfloat162float(__float2bfloat16_rn(v)); };
-  if (tid < kMlpInPad) xin[tid] = tid < od ? state[tid] : (action && tid < od + d ? action[tid - od] : 0.f);
+  const int ao = mp.act_off;
+  if (tid < kMlpInPad)
+    xin[tid] = tid < od ? state[tid] : (action && tid >= ao && tid < ao + d ? action[tid - ao] : 0.f);
   __syncthreads();
   if (action) {
     for (int n = tid; n < H; n += blockDim.x) {

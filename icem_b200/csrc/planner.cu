@@ -913,7 +913,20 @@ int icem_set_mlp_model(icem_planner_t* p, int32_t n_layers, const int32_t* dims,
     dst.alloc(h.size());
     ICEM_CUDA(cudaMemcpy(dst.p, h.data(), h.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
   };
-  pack(weights[0], H, in, H, kMlpInPad, p->mlp_w1);
+  // layer-1 input columns: [obs | 0 | act at act_off | 0], act_off = obs width rounded up to 8 (the kernel
+  // indexes its register state statically per 8-column chunk)
+  const int act_off = (out + 7) & ~7;
+  if (act_off + p->d > kMlpInPad)
+    throw Unsupported("obs_dim rounded up to 8, plus act_dim, must be <= 32 for the tensor-core rollout");
+  {
+    std::vector<float> w1((size_t)H * kMlpInPad, 0.f);
+    for (int n = 0; n < H; ++n) {
+      for (int k = 0; k < out; ++k) w1[(size_t)n * kMlpInPad + k] = weights[0][(size_t)n * in + k];
+      for (int m = 0; m < p->d; ++m) w1[(size_t)n * kMlpInPad + act_off + m] = weights[0][(size_t)n * in + out + m];
+    }
+    pack(w1.data(), H, kMlpInPad, H, kMlpInPad, p->mlp_w1);
+  }
+  p->mlp.act_off = act_off;
   pack(weights[1], H, H, H, H, p->mlp_w2);
   pack(weights[2], out, H, kMlpOutPad, H, p->mlp_w3);
   std::vector<float> b((size_t)2 * H + kMlpOutPad, 0.f);
@@ -1377,5 +1390,11 @@ int icem_bench_op(icem_planner_t* p, int32_t op, int32_t n, int32_t reps, int32_
   ICEM_CUDA(cudaStreamSynchronize(p->stream));
   ICEM_API_END
 }
+
+#ifdef ICEM_MLP_TRACE
+int icem_debug_mlp_trace(long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, icem::g_mlp_trace, sizeof(long long) * (size_t)n);
+}
+#endif
 
 }  // extern "C"
