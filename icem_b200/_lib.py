@@ -7,11 +7,11 @@ import numpy as np
 LIB_PATH = os.environ.get("ICEM_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
                                                            "libicem_b200.so")
 
-ICEM_ABI_VERSION = 2
+ICEM_ABI_VERSION = 3
 DYN = {"dense_tanh": 0, "halfcheetah": 1, "humanoid_standup": 2, "mlp": 3}
 COST = {"halfcheetah": 0, "humanoid_standup": 1}
 REDUCE = {"sum": 0, "best": 1, "final": 2}
-PLANNER = {"icem": 0, "cem_std": 1}
+PLANNER = {"icem": 0, "cem_std": 1, "random": 2}
 UNIQUE_ID_BYTES = 128
 
 
@@ -24,7 +24,7 @@ class IcemConfig(C.Structure):
         ("cost", C.c_int32), ("cost_penalise_flipping", C.c_int32), ("obs_dim", C.c_int32),
         ("colorednoise_v2", C.c_int32), ("keep_iteration_actions", C.c_int32), ("world_size", C.c_int32),
         ("rank", C.c_int32), ("planner", C.c_int32), ("execute_best_elite", C.c_int32), ("shift_means", C.c_int32),
-        ("bounds_like_levine", C.c_int32),
+        ("bounds_like_levine", C.c_int32), ("action_change_frequency", C.c_int32),
         ("factor_decrease_num", C.c_double), ("alpha", C.c_double), ("init_std", C.c_double),
         ("fraction_elites_reused", C.c_double), ("noise_beta", C.c_double),
         ("seed", C.c_uint64),

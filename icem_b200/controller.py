@@ -247,3 +247,26 @@ class MpcCemStdB200(MpcICemB200):
 
     def _evals_per_timestep(self):      # controllers/mpc.py:172
         return self.num_sim_traj * self.opt_iter * self.horizon
+
+
+class MpcRandomB200(MpcICemB200):
+    """Drop-in for the reference's random-shooting `MpcRandom` (icem/controllers/mpc.py:86-138): one population of
+    uniformly drawn, piecewise-constant action sequences per step (a drawn action is held for
+    `action_change_frequency` further `sample()` calls, and the calls run on across rows and across plan steps),
+    execute the first action of the cheapest trajectory.  Same constructor keywords.  As shipped the
+    reference class cannot be instantiated (it inherits the abstract `StatefulController.end_of_rollout` and never
+    defines it); this class provides the no-op the other controllers have."""
+    _banner = "MPC-Random"
+
+    def _parse_action_sampler_params(self, *, action_change_frequency):
+        self.action_change_frequency = action_change_frequency
+        assert self.action_change_frequency < self.horizon      # mpc.py:92
+        self.alpha, self.elites_size, self.opt_iter, self.init_std = 0.0, 2, 1, 0.5
+
+    def _sampler_settings(self):
+        return dict(planner="random", factor_decrease_num=1.0, use_mean_actions=False, keep_previous_elites=False,
+                    shift_elites_over_time=False, fraction_elites_reused=0.0, noise_beta=0.0,
+                    action_change_frequency=self.action_change_frequency)
+
+    def _evals_per_timestep(self):
+        return self.num_sim_traj * self.horizon

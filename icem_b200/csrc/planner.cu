@@ -131,6 +131,7 @@ struct icem_planner {
   // run state
   bool was_reset = false;
   uint32_t step = 0;
+  uint32_t plans_total = 0;           // never reset (MpcRandom's call counter runs across rollouts)
   bool has_prev = false;
   bool inject_pending = false;
   cudaGraphExec_t graph_exec = nullptr;
@@ -208,6 +209,8 @@ static SamplerConst sampler_const(icem_planner* p) {
   sc.h = p->h; sc.d = p->d; sc.K = p->K; sc.white = p->white;
   sc.trunc = p->cfg.planner == ICEM_PLANNER_CEM_STD;
   sc.levine = p->cfg.bounds_like_levine;
+  sc.rnd_freq = p->cfg.planner == ICEM_PLANNER_RANDOM ? p->cfg.action_change_frequency : -1;
+  sc.n_global = p->cfg.num_simulated_trajectories;
   sc.magic_d = (uint32_t)((0x100000000ull + p->d - 1) / p->d);
   sc.magic_K = (uint32_t)((0x100000000ull + p->K - 1) / p->K);
   sc.G = p->G.p; sc.low = p->d_low.p; sc.high = p->d_high.p;
@@ -552,6 +555,7 @@ static void write_step_in(icem_planner* p, const double* state) {
   ss.step = p->step;
   ss.has_prev_elites = p->has_prev ? 1 : 0;
   ss.inject = p->inject_pending ? 1 : 0;
+  ss.plans_total = p->plans_total;
   memcpy(p->h_in, &ss, sizeof ss);
   if (state) {
     float* f = reinterpret_cast<float*>(p->h_in + sizeof(StepState));
@@ -580,6 +584,7 @@ static void ensure_graph(icem_planner* p) {
 
 static void finish_step(icem_planner* p) {
   p->step += 1;
+  p->plans_total += 1;
   p->has_prev = true;
   if (p->inject_pending) {
     p->inject_pending = false;
@@ -642,16 +647,27 @@ int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
   p->sm_count = prop.multiProcessorCount;
   p->h = cfg->horizon; p->d = cfg->act_dim; p->hd = p->h * p->d; p->K = p->h / 2 + 1;
   p->iters = cfg->opt_iterations;
-  if (cfg->planner != ICEM_PLANNER_ICEM && cfg->planner != ICEM_PLANNER_CEM_STD) throw Unsupported("unknown planner id");
+  if (cfg->planner != ICEM_PLANNER_ICEM && cfg->planner != ICEM_PLANNER_CEM_STD &&
+      cfg->planner != ICEM_PLANNER_RANDOM)
+    throw Unsupported("unknown planner id");
   const bool cem_std = cfg->planner == ICEM_PLANNER_CEM_STD;
-  if (cem_std) {
+  const bool rnd = cfg->planner == ICEM_PLANNER_RANDOM;
+  if (rnd) {
+    // MpcRandom (controllers/mpc.py:86-138): ONE population per plan step, nothing is refit or reused
+    if (cfg->action_change_frequency < 0 || cfg->action_change_frequency >= cfg->horizon)
+      throw InvalidArg("action_change_frequency must be in [0, horizon)");       // mpc.py:92
+    p->cfg.opt_iterations = 1; p->iters = 1;
+    p->cfg.factor_decrease_num = 1.0;
+    p->cfg.use_mean_actions = p->cfg.keep_previous_elites = p->cfg.shift_elites_over_time = 0;
+    p->cfg.execute_best_elite = 1; p->cfg.shift_means = 1; p->cfg.bounds_like_levine = 0;
+  } else if (cem_std) {
     // MpcCemStd has no population decay, elite reuse or mean injection (controllers/mpc.py:212-233)
     p->cfg.factor_decrease_num = 1.0;
     p->cfg.use_mean_actions = p->cfg.keep_previous_elites = p->cfg.shift_elites_over_time = 0;
   } else {
     p->cfg.execute_best_elite = 1; p->cfg.shift_means = 1; p->cfg.bounds_like_levine = 0;
   }
-  p->white = cem_std || !(cfg->noise_beta > 0);
+  p->white = cem_std || rnd || !(cfg->noise_beta > 0);
   { const char* e = getenv("ICEM_B200_WARP_SAMPLER"); p->force_warp_sampler = e && e[0] == '1'; }
   p->low.assign(cfg->action_low, cfg->action_low + p->d);
   p->high.assign(cfg->action_high, cfg->action_high + p->d);

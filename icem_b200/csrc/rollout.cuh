@@ -19,7 +19,7 @@ struct StepState {
   uint32_t step;            // plan-step counter since beginning_of_rollout (Philox counter word)
   int32_t has_prev_elites;  // elite_samples non-empty -> shifted elites join iteration 0
   int32_t inject;           // parity mode: read unit normals from HBM instead of Philox
-  int32_t pad;
+  uint32_t plans_total;     // plan steps since icem_create (MpcRandom's sample() counter never resets)
 };
 
 struct SamplerConst {
@@ -27,6 +27,8 @@ struct SamplerConst {
   int white;            // noise_beta == 0: iid normal, z laid out [row][h][d]
   int trunc;            // MpcCemStd: draws are signed tail probabilities [row][h][d] (truncnorm_ppf), action = mean + std * ppf
   int levine;           // MpcCemStd bounds_like_levine: lower/upper = -2/+2 (else the action bounds in std units)
+  int rnd_freq;         // MpcRandom: >= 0 = action_change_frequency (uniform piecewise-constant actions), -1 = off
+  int n_global;         // MpcRandom: population size (sample() calls per plan step = n_global * h)
   uint32_t magic_d, magic_K;   // ceil(2^32 / d), ceil(2^32 / K): x / d == __umulhi(x, magic_d) for x < 2^16
   const float* G;       // [h][2K] synthesis matrix (colored): y[t] = sum_j G[t][j] * z[j], z = [zr(K), zi(K)]
   const float* low;     // [d]
@@ -241,7 +243,7 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
             w_z[dim * zs + sc.K + k] = si[i];
           }
         }
-      } else {
+      } else if (sc.rnd_freq < 0) {
         fill_normals(zdst, count, grow, a, ss.step, K2, zs, sc.white, sc.trunc != 0, sc.magic_K);
       }
       __syncwarp();
@@ -250,6 +252,26 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
       const float* elite = shifted ? a.prev_elites + (size_t)(row - a.n_fresh_local) * a.stride : nullptr;
       for (int o = lane; o < hd; o += 32) {
         const int t = (int)__umulhi((uint32_t)o, sc.magic_d), dim = o - t * d;
+        if (sc.rnd_freq >= 0) {
+          // MpcRandom (mpc.py:95-107): sample() is called row by row, step by step; the action drawn at
+          // construction serves the first `freq` calls, every later draw serves freq + 1 calls.  Call index ->
+          // segment -> Philox counter, so the result does not depend on how rows are spread over ranks.
+          float u;
+          if (ss.inject) {
+            u = tile[o];
+          } else {
+            const unsigned long long call = ((unsigned long long)ss.plans_total * (unsigned long long)sc.n_global
+                                             + (unsigned long long)grow) * (unsigned long long)h + (unsigned long long)t;
+            const unsigned long long f = (unsigned long long)sc.rnd_freq;
+            const unsigned long long seg = call < f ? 0ull : 1ull + (call - f) / (f + 1ull);
+            const Philox4 r = philox4x32_10((uint32_t)seg, (uint32_t)(seg >> 32), (uint32_t)(dim >> 2), 0x524E4431u,
+                                            a.seed_lo, a.seed_hi);
+            const uint32_t w = (dim & 3) == 0 ? r.x : (dim & 3) == 1 ? r.y : (dim & 3) == 2 ? r.z : r.w;
+            u = ((float)w + 0.5f) * 2.3283064365386963e-10f;
+          }
+          tile[o] = fminf(fmaf(s_high[dim] - s_low[dim], u, s_low[dim]), s_high[dim]);   // Box.sample (gym)
+          continue;
+        }
         if (sc.trunc) {       // MpcCemStd: mean + std * truncnorm.ppf(u; lower, upper), no clip (mpc.py:194-198, 290-301)
           const float sd = s_std[o], mu = s_mean[o];
           const float lo_ = sc.levine ? -2.f : (s_low[dim] - mu) / (sd + 1e-8f);

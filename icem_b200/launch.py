@@ -8,6 +8,7 @@ launcher adds entries to them before calling `main.main()` and edits nothing els
 
   controller     "mpc-icem-b200"            -> icem_b200.controller.MpcICemB200
                  "mpc-cem-std-b200"         -> icem_b200.controller.MpcCemStdB200 (vanilla CEM baseline)
+                 "mpc-random-b200"          -> icem_b200.controller.MpcRandomB200 (random shooting baseline)
                  ("mpc-icem" / "mpc-cem-std" too with --override-mpc-icem, so existing settings files run unchanged)
   forward_model  "CudaGroundTruthModel"     -> icem_b200.models.CudaGroundTruthModel
                  "CudaDenseTanhModel"       -> icem_b200.models.CudaDenseTanhModel
@@ -48,7 +49,9 @@ def register(override_mpc_icem=False, standin_envs=True):
     table = controllers.ControllerFactory.valid_base_controllers
     table["mpc-icem-b200"] = ("icem_b200.controller", "MpcICemB200")
     table["mpc-cem-std-b200"] = ("icem_b200.controller", "MpcCemStdB200")
+    table["mpc-random-b200"] = ("icem_b200.controller", "MpcRandomB200")
     if override_mpc_icem:
+        table["mpc-random"] = ("icem_b200.controller", "MpcRandomB200")
         table["mpc-icem"] = ("icem_b200.controller", "MpcICemB200")
         table["mpc-cem-std"] = ("icem_b200.controller", "MpcCemStdB200")
     models.models_dict["CudaGroundTruthModel"] = ("icem_b200.models", "CudaGroundTruthModel")

@@ -38,7 +38,8 @@ class PlannerSettings:
     rank: int = 0
     colorednoise_v2: bool = False
     keep_iteration_actions: bool = False
-    planner: str = "icem"                # "icem" (MpcICem) | "cem_std" (MpcCemStd: truncated normal, bounds update)
+    planner: str = "icem"                # "icem" (MpcICem) | "cem_std" (MpcCemStd) | "random" (MpcRandom)
+    action_change_frequency: int = 0     # random only (controllers/mpc.py:91)
     execute_best_elite: bool = True      # cem_std only (controllers/mpc.py:237-240)
     shift_means: bool = True             # cem_std only (controllers/mpc.py:243-248)
     bounds_like_levine: bool = False     # cem_std only (controllers/mpc.py:290-301)
@@ -71,6 +72,7 @@ class Planner:
             world_size=int(s.world_size), rank=int(s.rank), planner=_lib.PLANNER[s.planner],
             execute_best_elite=int(bool(s.execute_best_elite)), shift_means=int(bool(s.shift_means)),
             bounds_like_levine=int(bool(s.bounds_like_levine)),
+            action_change_frequency=int(s.action_change_frequency),
             factor_decrease_num=float(s.factor_decrease_num), alpha=float(s.alpha), init_std=float(s.init_std),
             fraction_elites_reused=float(s.fraction_elites_reused), noise_beta=float(s.noise_beta),
             seed=int(s.seed) & (2 ** 64 - 1), action_low=fptr(self._low), action_high=fptr(self._high))

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define ICEM_ABI_VERSION 2
+#define ICEM_ABI_VERSION 3
 
 /* status codes */
 enum { ICEM_OK = 0, ICEM_ERR_INVALID = 1, ICEM_ERR_CUDA = 2, ICEM_ERR_STATE = 3, ICEM_ERR_UNSUPPORTED = 4,
@@ -46,8 +46,10 @@ enum {
 /* action sampler / planner family */
 enum {
   ICEM_PLANNER_ICEM = 0,     /* MpcICem  (controllers/icem.py): colored / white Gaussian noise + clip            */
-  ICEM_PLANNER_CEM_STD = 1   /* MpcCemStd (controllers/mpc.py:142-327): truncated normal sampling, no decay,
+  ICEM_PLANNER_CEM_STD = 1,  /* MpcCemStd (controllers/mpc.py:142-327): truncated normal sampling, no decay,
                                  no elite reuse; bounds update, execute_best_elite / shift_means switches        */
+  ICEM_PLANNER_RANDOM = 2    /* MpcRandom (controllers/mpc.py:86-138): random shooting, one population of
+                                 piecewise-constant uniform actions, execute the best trajectory's first action  */
 };
 
 /* cost_along_trajectory (controllers/abstract_controller.py:82-91) */
@@ -79,6 +81,8 @@ typedef struct icem_config {
   int32_t execute_best_elite;     /* CEM_STD (mpc.py:237-240): 1 = first action of the best trajectory, 0 = mean[0] */
   int32_t shift_means;            /* CEM_STD (mpc.py:243-248): 1 = time-shift the mean, 0 = reset it to zeros        */
   int32_t bounds_like_levine;     /* CEM_STD (mpc.py:290-301): clamp std to half the distance to the bounds, +-2 sigma */
+  int32_t action_change_frequency;/* RANDOM (mpc.py:91,95-101): a drawn action is held for this many further sample()
+                                     calls; calls run over the whole population row by row, and on across plan steps */
   double factor_decrease_num;     /* gamma */
   double alpha;
   double init_std;
@@ -169,7 +173,9 @@ int icem_last_plan_ms(icem_planner_t* p, float* total_ms, float* rollout_kernels
  * order (oracle/shims/colorednoise.py): zr[rows][d][K] then zi[rows][d][K] (K = h/2+1), rows = this rank's
  * fresh trajectories followed by its shifted-elite rows; for noise_beta == 0: z[rows][h][d] in zr, zi NULL;
  * for ICEM_PLANNER_CEM_STD: the uniform draws u[rows][h][d] of truncnorm.rvs as SIGNED TAIL PROBABILITIES in zr
- * (w = u for u < 1/2, w = -(1 - u) otherwise: keeps the precision of the small tail in float32), zi NULL.
+ * (w = u for u < 1/2, w = -(1 - u) otherwise: keeps the precision of the small tail in float32), zi NULL;
+ * for ICEM_PLANNER_RANDOM: the uniform draw behind every action entry, u[rows][h][d] in zr (entries of one held
+ * action repeat), zi NULL: action = low + (high - low) * u like gym's Box.sample.
  * Cleared after the plan step that consumed them. */
 int icem_inject_noise(icem_planner_t* p, int32_t iteration, int32_t rows, const float* zr, const float* zi);
 

@@ -127,3 +127,31 @@ def cem_std_config(case):
     c["action_low"] = np.asarray(case["low"], np.float32)
     c["action_high"] = np.asarray(case["high"], np.float32)
     return c
+
+
+# ---- MpcRandom (controllers/mpc.py:86-138) -----------------------------------------------------------------
+RANDOM_CASES = {
+    "random_cheetah": dict(
+        model=lambda: DenseTanhModel.appendix_c(seed=4), cost="halfcheetah", penalise_flipping=True,
+        low=-np.ones(6), high=np.ones(6),
+        ctrl=dict(num_simulated_trajectories=50, horizon=30, cost_along_trajectory="sum",
+                  action_sampler_params=dict(action_change_frequency=4), do_visualize_plan=False, verbose=False),
+        start_obs=0.1 * np.random.RandomState(1020).randn(17), seed=20, steps=3),
+    "random_bounds_final": dict(
+        model=lambda: DenseTanhModel.appendix_c(seed=6), cost="halfcheetah", penalise_flipping=False,
+        low=np.array([-1, -0.5, -1, -2, -1, -1.0]), high=np.array([1, 0.5, 2, 1, 1, 1.0]),
+        ctrl=dict(num_simulated_trajectories=33, horizon=7, cost_along_trajectory="final",
+                  action_sampler_params=dict(action_change_frequency=0), do_visualize_plan=False, verbose=False),
+        start_obs=0.1 * np.random.RandomState(1021).randn(17), seed=21, steps=4),
+}
+
+
+def random_config(case):
+    c = dict(case["ctrl"])
+    s = dict(c.pop("action_sampler_params"))
+    c.pop("do_visualize_plan", None)
+    c.pop("verbose", None)
+    c.update(s)
+    c["action_low"] = np.asarray(case["low"], np.float32)
+    c["action_high"] = np.asarray(case["high"], np.float32)
+    return c

@@ -17,7 +17,8 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 def main():
     os.makedirs(OUT, exist_ok=True)
     todo = [(n, c, "MpcICem") for n, c in cases.CASES.items()] + \
-           [(n, c, "MpcCemStd") for n, c in cases.CEM_STD_CASES.items()]
+           [(n, c, "MpcCemStd") for n, c in cases.CEM_STD_CASES.items()] + \
+           [(n, c, "MpcRandom") for n, c in cases.RANDOM_CASES.items()]
     for name, case, controller in todo:
         model = case["model"]()
         steps, next_randn = ref_harness.run_reference_episode(
@@ -26,14 +27,18 @@ def main():
         blob = {"next_randn": np.float64(next_randn), "num_steps": np.int64(len(steps))}
         for s, st in enumerate(steps):
             blob[f"s{s}_action"] = st["action"]
-            blob[f"s{s}_mean_after_shift"] = st["mean_after_shift"]
-            blob[f"s{s}_std_after_reset"] = st["std_after_reset"]
+            if st["mean_after_shift"] is not None:
+                blob[f"s{s}_mean_after_shift"] = st["mean_after_shift"]
+                blob[f"s{s}_std_after_reset"] = st["std_after_reset"]
             blob[f"s{s}_num_iters"] = np.int64(len(st["iterations"]))
             for i, it in enumerate(st["iterations"]):
                 blob[f"s{s}_i{i}_costs"] = it["costs"]
                 blob[f"s{s}_i{i}_elite_idx"] = it["elite_idx"].astype(np.int64)
-                blob[f"s{s}_i{i}_mean"] = it["mean"]
-                blob[f"s{s}_i{i}_std"] = it["std"]
+                if "mean" in it:
+                    blob[f"s{s}_i{i}_mean"] = it["mean"]
+                    blob[f"s{s}_i{i}_std"] = it["std"]
+                else:       # MpcRandom: the sampled population itself is the thing to pin
+                    blob[f"s{s}_i{i}_actions"] = it["actions"].astype(np.float32)
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **blob)
         print(name, "steps", len(steps), "pops", [len(it["costs"]) for it in steps[-1]["iterations"]],
               "action0", np.round(steps[0]["action"][:3], 6))

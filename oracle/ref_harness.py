@@ -68,6 +68,29 @@ def build_reference_controller(model, cost_name, cfg_kwargs, action_low, action_
 
     env = _Env(name="standin")
     cls = ref.icem.MpcICem if controller == "MpcICem" else getattr(ref.mpc, controller)
+    if controller == "MpcRandom":
+        # As shipped, MpcRandom inherits the abstract StatefulController.end_of_rollout and cannot be instantiated;
+        # add that one no-op (what MpcICem / MpcCemStd define) and nothing else.  Its sampler parameters are read by
+        # attribute (mpc.py:91), as smart_settings objects allow.
+        import types
+
+        class _Runnable(cls):
+            def end_of_rollout(self, total_time, total_return, mode):
+                pass
+        cfg_kwargs = dict(cfg_kwargs)
+        cfg_kwargs["action_sampler_params"] = types.SimpleNamespace(**cfg_kwargs["action_sampler_params"])
+        ctrl = _Runnable(env=env, forward_model=_Model(env=env), **cfg_kwargs)
+        rec = {"iterations": []}
+        orig_cost = ctrl.trajectory_cost_fn
+
+        def recording_cost(cost_fn, rollout_buffer):
+            costs = np.array(orig_cost(cost_fn, rollout_buffer))
+            rec["iterations"].append(dict(population=len(costs), costs=costs.copy(),
+                                          elite_idx=np.array([int(np.argmin(costs))]),
+                                          actions=rollout_buffer.as_array("actions").copy()))
+            return costs
+        ctrl.trajectory_cost_fn = recording_cost
+        return ctrl, rec
     ctrl = cls(env=env, forward_model=_Model(env=env), **cfg_kwargs)
 
     rec = {"iterations": []}
@@ -90,9 +113,12 @@ def build_reference_controller(model, cost_name, cfg_kwargs, action_low, action_
 def run_reference_episode(model, cost_name, cfg_kwargs, action_low, action_high, start_obs,
                           seed, num_steps, penalise_flipping=True, controller="MpcICem"):
     """np.random.seed(seed); beginning_of_rollout; `num_steps` x (get_action; obs <- model.step)."""
+    if controller == "MpcRandom":
+        np.random.seed(seed)          # the constructor already draws (random.py:8, mpc.py:90)
     ctrl, rec = build_reference_controller(model, cost_name, cfg_kwargs, action_low, action_high,
                                            penalise_flipping, controller)
-    np.random.seed(seed)
+    if controller != "MpcRandom":
+        np.random.seed(seed)
     obs = np.asarray(start_obs, dtype=np.float64).copy()
     ctrl.beginning_of_rollout(observation=obs, state=None, mode="train")
     steps = []
@@ -100,7 +126,8 @@ def run_reference_episode(model, cost_name, cfg_kwargs, action_low, action_high,
         rec["iterations"] = []
         action = np.array(ctrl.get_action(obs, None), dtype=np.float64)
         steps.append(dict(action=action, iterations=rec["iterations"],
-                          mean_after_shift=ctrl.mean.copy(), std_after_reset=ctrl.std.copy(),
+                          mean_after_shift=ctrl.mean.copy() if hasattr(ctrl, "mean") else None,
+                          std_after_reset=ctrl.std.copy() if hasattr(ctrl, "std") else None,
                           start_obs=obs.copy()))
         obs = model.step(obs[None], action[None])[0]
     return steps, float(np.random.randn())

@@ -188,3 +188,41 @@ def test_truncnorm_rvs_is_ppf_of_uniform_draws():
     np.random.seed(4)
     u = np.random.uniform(size=(5, 3))
     np.testing.assert_allclose(a, truncnorm.ppf(u, lo, hi) * 0.7 + 0.1, rtol=0, atol=1e-14)
+
+
+# ---- random shooting (MpcRandom) ------------------------------------------------------------------
+def _run_random_case(case, record_actions=False):
+    from oracle.random_np import RandomConfig, RandomOracle
+    model = case["model"]()
+    cost = lambda o, a: costs_np.halfcheetah_cost(o, a, case["penalise_flipping"])
+    np.random.seed(case["seed"])                    # the constructor draws (random.py:8, mpc.py:90)
+    orc = RandomOracle(RandomConfig(**cases.random_config(case)), model.rollout, cost, record_actions=record_actions)
+    obs = np.asarray(case["start_obs"], np.float64).copy()
+    orc.beginning_of_rollout()
+    traces = []
+    for _ in range(case["steps"]):
+        tr = orc.get_action(obs)
+        traces.append(tr)
+        obs = model.step(obs[None], tr.action[None])[0]
+    return traces, float(np.random.randn())
+
+
+@pytest.mark.parametrize("name", sorted(cases.RANDOM_CASES))
+def test_random_oracle_matches_reference_golden(name, golden_dir):
+    """oracle/random_np.py against fixtures recorded from the reference MpcRandom (+ the one no-op method it lacks):
+    the sampled populations (held actions running across rows and plan steps), costs, best index, executed action
+    and the total number of RNG draws."""
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    traces, next_randn = _run_random_case(cases.RANDOM_CASES[name], record_actions=True)
+    assert next_randn == float(g["next_randn"])
+    for s, tr in enumerate(traces):
+        np.testing.assert_array_equal(tr.action.astype(np.float32), g[f"s{s}_action"].astype(np.float32))
+        it = tr.iterations[0]
+        np.testing.assert_array_equal(it.actions.astype(np.float32), g[f"s{s}_i0_actions"])
+        np.testing.assert_allclose(it.costs, g[f"s{s}_i0_costs"], rtol=0, atol=1e-10)
+        np.testing.assert_array_equal(it.elite_idx, g[f"s{s}_i0_elite_idx"])
+        # the recorded uniforms reproduce the actions: what the device is fed in parity mode
+        u, _ = it.noise[0]
+        c = cases.random_config(cases.RANDOM_CASES[name])
+        lo, hi = c["action_low"].astype(np.float64), c["action_high"].astype(np.float64)
+        np.testing.assert_array_equal((lo + (hi - lo) * u).astype(np.float32), g[f"s{s}_i0_actions"])
