@@ -88,6 +88,7 @@ SIGNATURES = {
     "icem_observe": (C.c_int, [_H, _D, C.c_int32, _D, C.c_int32]),
     "icem_op_sample": (C.c_int, [_H, C.c_int32, _F, _F, _F, _F, _F]),
     "icem_op_rollout_cost": (C.c_int, [_H, C.c_int32, _D, C.c_int32, _F, _F]),
+    "icem_op_rollout_observations": (C.c_int, [_H, C.c_int32, _D, C.c_int32, _F, C.c_int32, _D]),
     "icem_op_topk": (C.c_int, [_H, C.c_int32, _F, C.c_int32, _I, _F]),
     "icem_comm_get_unique_id": (C.c_int, [C.c_char_p]),
     "icem_comm_init": (C.c_int, [_H, C.c_char_p]),

@@ -43,8 +43,12 @@ class MpcICemB200(*_Bases):
         self._check_validity_parameters()
         self.logger = _get_logger(self.__class__.__name__)
         self.was_reset = False
-        if getattr(self, "use_env_reward_as_cost", False):
-            raise NotImplementedError("use_env_reward_as_cost is not implemented by the CUDA controller")
+        if getattr(self, "use_env_reward_as_cost", False) and not getattr(self.env, "reward_is_negative_cost", False):
+            # abstract_controller.py:75-76 scores -rewards of the simulated steps.  The device kernels evaluate
+            # env.cost_fn; that is the same number exactly when the env's reward is defined as -cost_fn (true for
+            # the stand-in envs of icem_b200.envs, which declare it), not for gym's own reward terms.
+            raise NotImplementedError("use_env_reward_as_cost needs an env whose reward is -cost_fn "
+                                      "(env.reward_is_negative_cost); gym's reward terms have no device kernel")
 
         fm = self.forward_model
         if not getattr(fm, "is_cuda_model", False) or not hasattr(fm, "cuda_spec"):
@@ -149,9 +153,13 @@ class MpcICemB200(*_Bases):
             raise AttributeError("beginning_of_rollout() needs to be called before")
         if self.verbose:
             print(f"-------------------- {self.mean[0][0:6]}")
+            if mode != "expert":       # icem.py:114-115
+                self.check_model_consistency()
         self.forward_model_state = self.forward_model.got_actual_observation_and_env_state(
             observation=obs, env_state=state, model_state=self.forward_model_state)
         start = self.forward_model.start_state(obs, self.forward_model_state)
+        self._last_start = np.array(start, dtype=np.float64)
+        self._obs_dim = int(np.asarray(obs).shape[-1])
         first = self._steps_since_reset == 0
         try:
             executed_action = self._planner.plan(start)
@@ -168,6 +176,9 @@ class MpcICemB200(*_Bases):
             self.expected_cost = float(rec["elite_costs"][0])
             if self.logger is not None:
                 self.logger.log(self.expected_cost, key="Expected_trajectory_cost")   # icem.py:177
+        if self.do_visualize_plan:      # icem.py:179-183: the best trajectory of the last iteration = elite 0
+            best = self.elite_samples[0]
+            self.visualize_plan(obs=best["observations"], state=self.forward_model_state, acts=best["actions"])
         # for stateful models, actually simulate step (icem.py:185-188); the result is overwritten by the next
         # call whenever the env state is supplied, so it is only evaluated when it will be used
         if self.forward_model_state is not None and state is None:
@@ -201,20 +212,35 @@ class MpcICemB200(*_Bases):
 
     @property
     def elite_samples(self):
-        """RolloutBuffer of the k elites of the last CEM iteration, best first (icem.py:201); the device keeps
-        only what the planner needs, so the rollouts carry `actions` (+ per-trajectory `costs`)."""
+        """RolloutBuffer of the k elites of the last CEM iteration, best first (icem.py:201).  The planner keeps
+        only the elites' action sequences on the device; the remaining fields the reference's rollouts carry
+        (models/abstract_models.py:28-29: observations, next_observations, rewards) are materialised lazily, on
+        first access after a plan step, by re-running just these k sequences on the device model
+        (icem_op_rollout_observations) -- SURVEY 8f-2."""
         if getattr(self, "_steps_since_reset", 0) == 0:
             return (_ref["buffer"]() if _ref else api.EliteBuffer())
         if self._elite_cache is None:
             acts, costs, _ = self._planner.elites()
-            if _ref:
-                rollouts = [_ref["rollout"].from_dict(actions=a.astype(np.float64)) for a in acts]
-                self._elite_cache = _ref["buffer"](rollouts=rollouts)
-            else:
-                self._elite_cache = api.EliteBuffer(
-                    [api.EliteRollout(actions=a.astype(np.float64)) for a in acts])
+            obs = self._planner.rollout_observations(self._last_start, acts, self._obs_dim)
+            rollouts = []
+            for a, o in zip(acts.astype(np.float64), obs):
+                step_costs = np.asarray(self.cost_fn(o[:-1], a, o[1:]), dtype=np.float64)
+                fields = dict(observations=o[:-1], next_observations=o[1:], actions=a, rewards=-step_costs)
+                rollouts.append(_ref["rollout"].from_dict(**fields) if _ref else api.EliteRollout(**fields))
+            self._elite_cache = _ref["buffer"](rollouts=rollouts) if _ref else api.EliteBuffer(rollouts)
             self._elite_costs = costs.astype(np.float64)
         return self._elite_cache
+
+    def check_model_consistency(self):
+        """controllers/mpc.py:39-47: warn when the model state and the real env state have drifted apart."""
+        env = self.env
+        if self.forward_model_state is None or not hasattr(env, "compute_state_difference"):
+            return
+        diff = env.compute_state_difference(self.forward_model_state, env.get_GT_state())
+        if diff > 1e-5:
+            print(f"Warning: internal GT model and actual env are not in sync: Difference: {diff}")
+            print("env state:", env.get_GT_state())
+            print("model_state:", self.forward_model_state)
 
     def close(self):
         self._planner.close()

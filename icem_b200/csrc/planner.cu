@@ -464,7 +464,8 @@ __global__ void advance_kernel(typename Dyn::Params dp, float* state, const floa
   float* w_dyn = s_dyn + ((Dyn::cta_floats(dp) + 3) & ~3);
   float* s_act = w_dyn + ((Dyn::warp_floats(dp) + 3) & ~3);
   Dyn::cta_init(dp, s_dyn);
-  for (int i = threadIdx.x; i < dp.act_dim; i += blockDim.x) s_act[i] = action[i];
+  if (action)
+    for (int i = threadIdx.x; i < dp.act_dim; i += blockDim.x) s_act[i] = action[i];
   __syncthreads();
   Dyn dyn;
   dyn.bind(dp, s_dyn, w_dyn);
@@ -1258,6 +1259,38 @@ int icem_op_rollout_cost(icem_planner_t* p, int32_t n, const double* state, int3
   launch_rollout_dyn<false, true>(p, a, n);
   ICEM_CUDA(cudaStreamSynchronize(p->stream));
   ICEM_CUDA(cudaMemcpy(costs_out, d_cost.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  ICEM_API_END
+}
+
+int icem_op_rollout_observations(icem_planner_t* p, int32_t n, const double* state, int32_t state_dim,
+                                 const float* actions, int32_t obs_dim, double* obs_out) {
+  ICEM_API_BEGIN
+  if (!p || !state || !actions || !obs_out) throw InvalidArg("null argument");
+  if (n < 1 || n > 4096) throw InvalidArg("n must be in [1, 4096] (this operator is for elites, not populations)");
+  require_model(p);
+  if (state_dim != p->state_dim) throw InvalidArg("state_dim does not match the forward model");
+  if (obs_dim < 1 || obs_dim > 512) throw InvalidArg("obs_dim out of range");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  const int sd = p->state_dim, h = p->h, d = p->d;
+  DevBuf<float> d_state, d_act, d_obs;
+  d_state.alloc((size_t)2 * sd);                       // start state, running state
+  d_act.alloc((size_t)n * h * d);
+  d_obs.alloc((size_t)n * (h + 1) * obs_dim);
+  std::vector<float> hs(sd);
+  for (int i = 0; i < sd; ++i) hs[i] = (float)state[i];
+  ICEM_CUDA(cudaMemcpyAsync(d_state.p, hs.data(), sd * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+  ICEM_CUDA(cudaMemcpyAsync(d_act.p, actions, (size_t)n * h * d * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+  float* run = d_state.p + sd;
+  for (int r = 0; r < n; ++r) {
+    float* obs_r = d_obs.p + (size_t)r * (h + 1) * obs_dim;
+    advance_dyn(p, d_state.p, nullptr, run, obs_r, obs_dim);                     // entry 0: the start observation
+    for (int t = 0; t < h; ++t)
+      advance_dyn(p, run, d_act.p + ((size_t)r * h + t) * d, run, obs_r + (size_t)(t + 1) * obs_dim, obs_dim);
+  }
+  std::vector<float> ho((size_t)n * (h + 1) * obs_dim);
+  ICEM_CUDA(cudaMemcpyAsync(ho.data(), d_obs.p, ho.size() * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+  ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  for (size_t i = 0; i < ho.size(); ++i) obs_out[i] = ho[i];
   ICEM_API_END
 }
 

@@ -169,6 +169,7 @@ def humanoid_standup_qpos0():
 class _DeviceSimEnv(_EnvBase):
     """Common part: one device planner handle used only for `icem_sim_step` (single transitions)."""
     kind = None
+    reward_is_negative_cost = True     # step() returns -cost_fn(obs, action): use_env_reward_as_cost == cost path
 
     def __init__(self, *, name, device=0, **kwargs):
         super().__init__(name=name, **kwargs)

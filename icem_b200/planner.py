@@ -234,6 +234,17 @@ class Planner:
                                       dptr(obs) if obs_dim else None, obs_dim, C.byref(rew)))
         return nxt, (obs[:obs_dim] if obs_dim else None), rew.value
 
+    def rollout_observations(self, state, actions, obs_dim):
+        """[n, h+1, obs_dim] observations along given action sequences [n, h, d] (icem_op_rollout_observations)."""
+        st = f64(state).ravel()
+        acts = f32(actions)
+        if acts.ndim != 3 or acts.shape[1:] != (self.h, self.d):
+            raise ValueError("actions must be [n, h, d]")
+        out = np.empty((acts.shape[0], self.h + 1, obs_dim), dtype=np.float64)
+        check(self._lib.icem_op_rollout_observations(self._h, acts.shape[0], dptr(st), st.shape[0], fptr(acts),
+                                                     obs_dim, dptr(out)))
+        return out
+
     def observe(self, state, obs_dim):
         st = f64(state).ravel()
         obs = np.empty(obs_dim, dtype=np.float64)

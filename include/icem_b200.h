@@ -206,6 +206,13 @@ int icem_op_sample(icem_planner_t* p, int32_t n, const float* zr, const float* z
 /* controllers/mpc.py:56-67 + controllers/abstract_controller.py:74-91: costs[n] for given action sequences */
 int icem_op_rollout_cost(icem_planner_t* p, int32_t n, const double* state, int32_t state_dim,
                          const float* actions, float* costs_out);
+/* The observations a FEW given action sequences visit (what the reference keeps for every rollout in its
+ * RolloutBuffer, misc/rolloutbuffer.py:10-54, models/abstract_models.py:28-53): obs_out[n][h+1][obs_dim], entry t =
+ * observation before action t, entry h = the final predicted observation.  Used lazily for `elite_samples`
+ * (controllers/icem.py:201), `visualize_plan` (controllers/abstract_controller.py:93-128); the planner itself never
+ * materialises observations.  One small launch per step: meant for k elites, not for populations. */
+int icem_op_rollout_observations(icem_planner_t* p, int32_t n, const double* state, int32_t state_dim,
+                                 const float* actions, int32_t obs_dim, double* obs_out);
 /* controllers/icem.py:199: k smallest by ascending (cost, index); NaN sorts last */
 int icem_op_topk(icem_planner_t* p, int32_t n, const float* costs, int32_t k, int32_t* idx_out, float* costs_out);
 

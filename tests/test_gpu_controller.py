@@ -89,3 +89,79 @@ def test_verbose_prints_reference_format(capsys):
     assert "iter 0:128 --- best cost:" in out and "iter 2:81 --- best cost:" in out     # controllers/icem.py:156-158
     ctrl.close()
     env.close()
+
+
+@pytest.mark.parametrize("env_name", ["HalfCheetah", "HumanoidStandup"])
+def test_elite_samples_carry_the_rollout_fields_of_the_reference(env_name):
+    """`elite_samples` are full rollouts (observations, next_observations, actions, rewards) like the
+    reference's (models/abstract_models.py:28-53), materialised lazily from the device model: replaying an elite's
+    actions in the env from the same state visits the same observations, and the summed step costs are the elite's
+    planner cost."""
+    ctrl, env = _make(env_name)
+    ob = env.reset()
+    ctrl.beginning_of_rollout(observation=ob, state=env.get_GT_state(), mode="train")
+    for _ in range(2):
+        state = env.get_GT_state()
+        ac = ctrl.get_action(ob, state=state)
+        el = ctrl.elite_samples
+        assert el is ctrl.elite_samples                       # cached until the next plan step
+        obs_dim = env.observation_space.shape[0]
+        assert el.as_array("observations").shape == (10, 30, obs_dim)
+        assert el.as_array("next_observations").shape == (10, 30, obs_dim)
+        np.testing.assert_allclose(el[0]["observations"][0], ob, atol=1e-5)
+        np.testing.assert_array_equal(el[3]["observations"][1:], el[3]["next_observations"][:-1])
+        _, costs, _ = ctrl._planner.elites()
+        for j in (0, 9):
+            np.testing.assert_allclose(-np.sum(el[j]["rewards"]), costs[j], atol=2e-3, rtol=1e-4)
+        # replay elite 0 in a second env instance from the same state
+        twin = type(env)(name=env.name)
+        twin.reset()
+        twin.set_GT_state(state)
+        for t in range(5):
+            o, *_ = twin.step(el[0]["actions"][t])
+            np.testing.assert_allclose(o, el[0]["next_observations"][t], atol=2e-4, rtol=1e-4)
+        twin.close()
+        ob, *_ = env.step(ac)
+    ctrl.close()
+    env.close()
+
+
+def test_do_visualize_plan_gets_the_best_planned_trajectory(monkeypatch):
+    """icem.py:179-183: with do_visualize_plan set, visualize_plan receives the best trajectory's observations and
+    actions and the model state."""
+    ctrl, env = _make("HalfCheetah", do_visualize_plan="all")
+    seen = {}
+    monkeypatch.setattr(type(ctrl), "visualize_plan", lambda self, *, obs, state, acts: seen.update(
+        obs=np.array(obs), state=np.array(state), acts=np.array(acts)), raising=False)
+    ob = env.reset()
+    ctrl.beginning_of_rollout(observation=ob, state=env.get_GT_state(), mode="train")
+    st = env.get_GT_state()
+    ac = ctrl.get_action(ob, state=st)
+    assert seen["obs"].shape == (30, 17) and seen["acts"].shape == (30, 6)
+    np.testing.assert_allclose(seen["acts"][0], ac, atol=1e-6)
+    np.testing.assert_allclose(seen["obs"][0], ob, atol=1e-5)
+    np.testing.assert_array_equal(seen["state"], st)
+    ctrl.close()
+    env.close()
+
+
+def test_use_env_reward_as_cost_is_the_cost_path_on_envs_that_declare_it():
+    """abstract_controller.py:75-76: costs = -rewards.  The stand-in envs return reward = -cost_fn, so the flag
+    selects the same numbers; an env that does not declare that is refused (no silent substitution)."""
+    a, env_a = _make("HalfCheetah", use_env_reward_as_cost=True)
+    b, env_b = _make("HalfCheetah")
+    ob = env_a.reset()
+    env_b.set_GT_state(env_a.get_GT_state())
+    for c, e in ((a, env_a), (b, env_b)):
+        c.beginning_of_rollout(observation=ob, state=e.get_GT_state(), mode="train")
+    np.testing.assert_array_equal(a.get_action(ob, state=env_a.get_GT_state()),
+                                  b.get_action(ob, state=env_b.get_GT_state()))
+    env_a.reward_is_negative_cost = False
+    with pytest.raises(NotImplementedError, match="reward_is_negative_cost"):
+        from icem_b200.controller import MpcICemB200
+        from icem_b200.models import CudaGroundTruthModel
+        MpcICemB200(env=env_a, forward_model=CudaGroundTruthModel(env=env_a), horizon=30,
+                    num_simulated_trajectories=16, cost_along_trajectory="sum", use_env_reward_as_cost=True,
+                    action_sampler_params=SAMPLER)
+    for c, e in ((a, env_a), (b, env_b)):
+        c.close(); e.close()
