@@ -70,6 +70,8 @@ SIGNATURES = {
     "icem_set_articulated_model": (C.c_int, [_H, C.POINTER(IcemArticulatedModel)]),
     "icem_begin_rollout": (C.c_int, [_H]),
     "icem_plan": (C.c_int, [_H, _D, C.c_int32, _D]),
+    "icem_plan_async": (C.c_int, [_H, _D, C.c_int32]),
+    "icem_plan_finish": (C.c_int, [_H, _D]),
     "icem_plan_device": (C.c_int, [_H]),
     "icem_advance_state_device": (C.c_int, [_H]),
     "icem_sync": (C.c_int, [_H]),

@@ -149,6 +149,12 @@ class MpcICemB200(*_Bases):
         pass
 
     def get_action(self, obs, state, mode="train"):
+        self.begin_get_action(obs, state, mode)
+        return self.finish_get_action()
+
+    # get_action in two halves: many controllers (independent episodes) launch their plan steps first and collect
+    # them afterwards, so the device works on all of them at once (icem_b200/batched.py)
+    def begin_get_action(self, obs, state, mode="train"):
         if not self.was_reset:
             raise AttributeError("beginning_of_rollout() needs to be called before")
         if self.verbose:
@@ -160,13 +166,17 @@ class MpcICemB200(*_Bases):
         start = self.forward_model.start_state(obs, self.forward_model_state)
         self._last_start = np.array(start, dtype=np.float64)
         self._obs_dim = int(np.asarray(obs).shape[-1])
-        first = self._steps_since_reset == 0
+        self._pending = (obs, state, self._steps_since_reset == 0)
         try:
-            executed_action = self._planner.plan(start)
+            self._planner.plan_async(start)
         except IcemError as e:
             if "beginning_of_rollout" in str(e):
                 raise AttributeError(str(e))
             raise
+
+    def finish_get_action(self):
+        obs, state, first = self._pending
+        executed_action = self._planner.plan_finish()
         self._steps_since_reset += 1
         self._elite_cache = None
         if self.verbose:

@@ -134,6 +134,7 @@ struct icem_planner {
   uint32_t plans_total = 0;           // never reset (MpcRandom's call counter runs across rollouts)
   bool has_prev = false;
   bool inject_pending = false;
+  bool plan_in_flight = false;        // between icem_plan_async and icem_plan_finish
   cudaGraphExec_t graph_exec = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   std::vector<cudaEvent_t> ev_roll;   // pairs around rollout kernels (bench / timing mode)
@@ -971,12 +972,12 @@ int icem_begin_rollout(icem_planner_t* p) {
   ICEM_API_END
 }
 
-int icem_plan(icem_planner_t* p, const double* state, int32_t state_dim, double* action_out) {
-  ICEM_API_BEGIN
-  if (!p || !state || !action_out) throw InvalidArg("null argument");
+// launch half of a plan step: stage the inputs, enqueue the CEM iterations, no host synchronisation
+static void plan_launch(icem_planner* p, const double* state, int32_t state_dim) {
   if (!p->was_reset) throw StateError("beginning_of_rollout() needs to be called before");   // icem.py:109-110
   require_model(p);
   if (state_dim != p->state_dim) throw InvalidArg("state_dim does not match the forward model");
+  if (p->plan_in_flight) throw StateError("a plan step is already in flight (icem_plan_finish not called)");
   ICEM_CUDA(cudaSetDevice(p->cfg.device));
   write_step_in(p, state);
   ICEM_CUDA(cudaEventRecord(p->ev_a, p->stream));
@@ -990,11 +991,39 @@ int icem_plan(icem_planner_t* p, const double* state, int32_t state_dim, double*
     ICEM_CUDA(cudaGraphLaunch(p->graph_exec, p->stream));
   }
   ICEM_CUDA(cudaEventRecord(p->ev_b, p->stream));
+  p->plan_in_flight = true;
+}
+
+static void plan_finish(icem_planner* p, double* action_out) {
+  if (!p->plan_in_flight) throw StateError("no plan step in flight (icem_plan_async not called)");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
   ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  p->plan_in_flight = false;
   ICEM_CUDA(cudaEventElapsedTime(&p->last_total_ms, p->ev_a, p->ev_b));
   p->last_rollout_ms = 0.f;
   for (int i = 0; i < p->d; ++i) action_out[i] = (double)p->h_out[i];
   finish_step(p);
+}
+
+int icem_plan(icem_planner_t* p, const double* state, int32_t state_dim, double* action_out) {
+  ICEM_API_BEGIN
+  if (!p || !state || !action_out) throw InvalidArg("null argument");
+  plan_launch(p, state, state_dim);
+  plan_finish(p, action_out);
+  ICEM_API_END
+}
+
+int icem_plan_async(icem_planner_t* p, const double* state, int32_t state_dim) {
+  ICEM_API_BEGIN
+  if (!p || !state) throw InvalidArg("null argument");
+  plan_launch(p, state, state_dim);
+  ICEM_API_END
+}
+
+int icem_plan_finish(icem_planner_t* p, double* action_out) {
+  ICEM_API_BEGIN
+  if (!p || !action_out) throw InvalidArg("null argument");
+  plan_finish(p, action_out);
   ICEM_API_END
 }
 

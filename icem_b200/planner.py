@@ -158,6 +158,16 @@ class Planner:
         check(self._lib.icem_plan(self._h, dptr(st), st.shape[0], dptr(out)))
         return out
 
+    def plan_async(self, state):
+        """Launch a plan step without waiting for it (icem_plan_async); pair with plan_finish()."""
+        st = f64(state).ravel()
+        check(self._lib.icem_plan_async(self._h, dptr(st), st.shape[0]))
+
+    def plan_finish(self) -> np.ndarray:
+        out = np.empty(self.d, dtype=np.float64)
+        check(self._lib.icem_plan_finish(self._h, dptr(out)))
+        return out
+
     def plan_device(self):
         check(self._lib.icem_plan_device(self._h))
 

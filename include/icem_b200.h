@@ -159,6 +159,15 @@ int icem_begin_rollout(icem_planner_t* p);
  * Returns ICEM_ERR_STATE ("beginning_of_rollout() needs to be called before") if not reset. */
 int icem_plan(icem_planner_t* p, const double* state, int32_t state_dim, double* action_out);
 
+/* The two halves of icem_plan, for MANY planner handles driven by one host thread (one independent MPC problem
+ * per handle, each on its own CUDA stream): launch every handle's plan step, then collect them -- the device runs
+ * the problems side by side.  This is the GPU form of the reference's episode-level parallelism
+ * (misc/rollout_utils.py:129-152 spawns one process per evaluation rollout); at the reference's default budget of
+ * 97 trajectories per step one problem occupies a few percent of a B200.  Exactly one plan step may be in flight
+ * per handle (ICEM_ERR_STATE otherwise). */
+int icem_plan_async(icem_planner_t* p, const double* state, int32_t state_dim);
+int icem_plan_finish(icem_planner_t* p, double* action_out);
+
 /* Same plan step with the start state already resident on the device (no host<->device copy): the state is
  * the one left by the previous icem_plan / icem_advance_state_device.  Asynchronous; pair with icem_sync. */
 int icem_plan_device(icem_planner_t* p);
