@@ -7,7 +7,7 @@ import numpy as np
 LIB_PATH = os.environ.get("ICEM_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
                                                            "libicem_b200.so")
 
-ICEM_ABI_VERSION = 3
+ICEM_ABI_VERSION = 4
 DYN = {"dense_tanh": 0, "halfcheetah": 1, "humanoid_standup": 2, "mlp": 3}
 COST = {"halfcheetah": 0, "humanoid_standup": 1}
 REDUCE = {"sum": 0, "best": 1, "final": 2}
@@ -25,6 +25,7 @@ class IcemConfig(C.Structure):
         ("colorednoise_v2", C.c_int32), ("keep_iteration_actions", C.c_int32), ("world_size", C.c_int32),
         ("rank", C.c_int32), ("planner", C.c_int32), ("execute_best_elite", C.c_int32), ("shift_means", C.c_int32),
         ("bounds_like_levine", C.c_int32), ("action_change_frequency", C.c_int32),
+        ("num_problems", C.c_int32),
         ("factor_decrease_num", C.c_double), ("alpha", C.c_double), ("init_std", C.c_double),
         ("fraction_elites_reused", C.c_double), ("noise_beta", C.c_double),
         ("seed", C.c_uint64),
@@ -70,6 +71,9 @@ SIGNATURES = {
     "icem_set_articulated_model": (C.c_int, [_H, C.POINTER(IcemArticulatedModel)]),
     "icem_begin_rollout": (C.c_int, [_H]),
     "icem_plan": (C.c_int, [_H, _D, C.c_int32, _D]),
+    "icem_plan_batch": (C.c_int, [_H, _D, C.c_int32, C.c_int32, _D]),
+    "icem_num_problems": (C.c_int, [_H]),
+    "icem_set_active_problem": (C.c_int, [_H, C.c_int32]),
     "icem_plan_async": (C.c_int, [_H, _D, C.c_int32]),
     "icem_plan_finish": (C.c_int, [_H, _D]),
     "icem_plan_device": (C.c_int, [_H]),

@@ -75,6 +75,48 @@ class EpisodeBatch:
             e.close()
 
 
+class FusedEpisodeBatch(EpisodeBatch):
+    """The same B episodes through ONE planner handle created with `num_problems = B` (icem_plan_batch): every
+    kernel of the plan step covers all episodes (grid.y = episode) and the whole step of all episodes is one CUDA
+    graph launch, so the number of concurrent episodes is not limited by the 32 hardware stream queues.  All
+    episodes share settings and model; episode i draws with seed + i, exactly like a single-problem handle with
+    that seed (tests/test_gpu_batched.py)."""
+
+    def __init__(self, envs, controller):
+        self.envs, self.controller = list(envs), controller
+        self.controllers = [controller]
+        self.obs = [None] * len(self.envs)
+        if controller._planner.settings.num_problems != len(self.envs):
+            raise ValueError("controller must be created with num_problems == len(envs)")
+
+    def reset(self, mode="train"):
+        for i, env in enumerate(self.envs):
+            self.obs[i] = env.reset_with_mode(mode) if hasattr(env, "reset_with_mode") else env.reset()
+        c = self.controller
+        c.beginning_of_rollout(observation=self.obs[0], state=self.envs[0].get_GT_state(), mode=mode)
+        return list(self.obs)
+
+    def plan(self, mode="train"):
+        fm = self.controller.forward_model
+        states = np.stack([fm.start_state(ob, env.get_GT_state()) for env, ob in zip(self.envs, self.obs)])
+        return self.controller._planner.plan_batch(states)
+
+
+def make_fused_episode_batch(env_name, num_episodes, controller_params, seed=0, device=0, controller_cls=None):
+    from . import envs as envs_mod
+    from .controller import MpcICemB200
+    from .models import CudaGroundTruthModel
+    cls = controller_cls or MpcICemB200
+    es = []
+    for i in range(num_episodes):
+        env = envs_mod.make_env(env_name, device=device)
+        env.seed(seed + i)
+        es.append(env)
+    ctrl = cls(env=es[0], forward_model=CudaGroundTruthModel(env=es[0]), seed=seed + 1000, device=device,
+               world_size=1, rank=0, num_problems=num_episodes, **controller_params)
+    return FusedEpisodeBatch(es, ctrl)
+
+
 def make_episode_batch(env_name, num_episodes, controller_params, seed=0, device=0, controller_cls=None):
     """B stand-in envs + CUDA ground-truth models + controllers with the reference's `controller_params` dict."""
     from . import envs as envs_mod

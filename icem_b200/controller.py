@@ -29,7 +29,7 @@ def _get_logger(name):
 
 class MpcICemB200(*_Bases):
     def __init__(self, *, action_sampler_params, horizon, num_simulated_trajectories, factor_decrease_num=1,
-                 verbose=False, seed=None, device=None, world_size=None, rank=None, **kwargs):
+                 verbose=False, seed=None, device=None, world_size=None, rank=None, num_problems=1, **kwargs):
         super().__init__(**kwargs)     # ModelBasedController: forward_model, env, cost_along_trajectory, ...
         # controllers/mpc.py:22-36
         self.horizon = horizon
@@ -70,7 +70,7 @@ class MpcICemB200(*_Bases):
             dynamics=spec["dynamics"], cost=cost, obs_dim=spec["obs_dim"], penalise_flipping=penalise,
             cost_along_trajectory=self.cost_along_trajectory, alpha=self.alpha, elites_size=self.elites_size,
             opt_iterations=self.opt_iter, init_std=self.init_std, seed=seed, device=device, world_size=world_size,
-            rank=rank, **self._sampler_settings()))
+            rank=rank, num_problems=num_problems, **self._sampler_settings()))
         if spec.get("dense") is not None:
             self._planner.set_dense_model(*spec["dense"])
         if spec.get("mlp") is not None:

@@ -69,6 +69,8 @@ struct NoDyn {
   __device__ void export_state(float*) const {}
 };
 
+constexpr int kStateSlot = 256;     // floats reserved per problem for the start state in `step_in`
+
 struct IterPlan {
   int n_global;       // N_i
   int chunk;          // ceil(N_i / world)
@@ -89,6 +91,9 @@ struct icem_planner {
   std::vector<float> low, high;
   int h = 0, d = 0, hd = 0, K = 0, k = 0, n_keep = 0, stride = 0, iters = 0;
   int state_dim = 0, obs_dim = 0;
+  int B = 1;                          // independent MPC problems batched in this handle (cfg.num_problems)
+  int active = 0;                     // problem the observable-state getters read
+  size_t actions_per = 0, costs_per = 0;   // per-problem elements of `actions` / `costs`
   int sm_count = 148;
   bool white = false;
   bool force_warp_sampler = false;   // ICEM_B200_WARP_SAMPLER=1 at icem_create: A/B the two samplers (tests)
@@ -261,8 +266,10 @@ static void launch_rollout(icem_planner* p, const RolloutArgs& a, const typename
   ICEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
   if (occ < 1) throw InvalidArg("rollout kernel does not fit on an SM (shared memory)");
   const int ctas_needed = (rows_max + warps - 1) / warps;
-  const int grid = std::max(1, std::min(ctas_needed, p->sm_count * occ));   // persistent: <= one resident wave
-  kern<<<grid, warps * 32, smem, p->stream>>>(a, sc, cc, dp);
+  // persistent: <= one resident wave, shared between the problems of a batched handle (grid.y = problem)
+  const int nprob = a.prob_actions ? p->B : 1;      // operator launches carry no problem strides
+  const int grid = std::max(1, std::min(ctas_needed, std::max(1, p->sm_count * occ / nprob)));
+  kern<<<dim3(grid, nprob), warps * 32, smem, p->stream>>>(a, sc, cc, dp);
   ICEM_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
 }
@@ -373,6 +380,8 @@ static RolloutArgs rollout_args(icem_planner* p, int i) {
   a.ss = step_state_dev(p);
   a.seed_lo = (uint32_t)p->cfg.seed;
   a.seed_hi = (uint32_t)(p->cfg.seed >> 32);
+  a.prob_actions = p->actions_per; a.prob_costs = p->costs_per;
+  a.prob_dist = p->hd; a.prob_elites = p->k * p->stride; a.prob_state = kStateSlot;
   return a;
 }
 
@@ -415,6 +424,8 @@ static RefitArgs refit_args(icem_planner* p, int i) {
   r.low = p->d_low.p; r.high = p->d_high.p;
   r.out_action = p->out.p;
   r.out_best_cost = p->out.p + p->d;
+  r.prob_actions = p->actions_per; r.prob_dist = p->hd; r.prob_elites = p->k * p->stride; r.prob_k = p->k;
+  r.prob_trace_hd = p->iters * p->hd; r.prob_trace_k = p->iters * p->k; r.prob_out = p->d + 1;
   return r;
 }
 
@@ -437,10 +448,11 @@ static void enqueue_iterations(icem_planner* p, bool time_rollouts) {
     s.k = p->k; s.stride = p->stride;
     s.costs = a.costs; s.actions = a.actions; s.ss = a.ss;
     s.cand = p->cand.p; s.ticket = p->ticket.p;
+    s.prob_actions = p->actions_per; s.prob_costs = p->costs_per; s.prob_cand = p->sm_count * p->k;
     RefitArgs r = refit_args(p, i);
     const size_t smem = (size_t)p->k * sizeof(unsigned long long);
     if (p->cfg.world_size == 1) {
-      select_kernel<<<select_grid(p, ip.rows_cap), kSelectThreads, smem, p->stream>>>(s, r, 1);
+      select_kernel<<<dim3(select_grid(p, ip.rows_cap), p->B), kSelectThreads, smem, p->stream>>>(s, r, 1);
       ICEM_CUDA(cudaGetLastError());
       g_launches.fetch_add(1, std::memory_order_relaxed);
     } else {
@@ -543,13 +555,19 @@ static void build_plan(icem_planner* p) {
     rows_max = std::max(rows_max, ip.rows_cap);
     p->plan.push_back(ip);
   }
-  p->costs.alloc(std::max<size_t>(cost_off, 1));
-  p->actions.alloc((size_t)std::max<size_t>(c.keep_iteration_actions ? act_off : (size_t)rows_max, 1) * p->stride);
+  p->costs_per = std::max<size_t>(cost_off, 1);
+  p->actions_per = (size_t)std::max<size_t>(c.keep_iteration_actions ? act_off : (size_t)rows_max, 1) * p->stride;
+  p->costs.alloc(p->costs_per * p->B);
+  p->actions.alloc(p->actions_per * p->B);
 }
 
 static void reset_distribution(icem_planner* p) {
-  ICEM_CUDA(cudaMemcpyAsync(p->mean.p, p->init_mean.p, p->hd * sizeof(float), cudaMemcpyDeviceToDevice, p->stream));
-  ICEM_CUDA(cudaMemcpyAsync(p->stdv.p, p->reset_std.p, p->hd * sizeof(float), cudaMemcpyDeviceToDevice, p->stream));
+  for (int b = 0; b < p->B; ++b) {
+    ICEM_CUDA(cudaMemcpyAsync(p->mean.p + (size_t)b * p->hd, p->init_mean.p, p->hd * sizeof(float),
+                              cudaMemcpyDeviceToDevice, p->stream));
+    ICEM_CUDA(cudaMemcpyAsync(p->stdv.p + (size_t)b * p->hd, p->reset_std.p, p->hd * sizeof(float),
+                              cudaMemcpyDeviceToDevice, p->stream));
+  }
 }
 
 static void write_step_in(icem_planner* p, const double* state) {
@@ -559,9 +577,10 @@ static void write_step_in(icem_planner* p, const double* state) {
   ss.inject = p->inject_pending ? 1 : 0;
   ss.plans_total = p->plans_total;
   memcpy(p->h_in, &ss, sizeof ss);
-  if (state) {
+  if (state) {      // [B][state_dim] doubles -> one kStateSlot-float slot per problem
     float* f = reinterpret_cast<float*>(p->h_in + sizeof(StepState));
-    for (int i = 0; i < p->state_dim; ++i) f[i] = (float)state[i];
+    for (int b = 0; b < p->B; ++b)
+      for (int i = 0; i < p->state_dim; ++i) f[(size_t)b * kStateSlot + i] = (float)state[(size_t)b * p->state_dim + i];
   }
 }
 
@@ -572,7 +591,8 @@ static void ensure_graph(icem_planner* p) {
   try {
     ICEM_CUDA(cudaMemcpyAsync(p->step_in.p, p->h_in, p->in_bytes, cudaMemcpyHostToDevice, p->stream));
     enqueue_iterations(p, false);
-    ICEM_CUDA(cudaMemcpyAsync(p->h_out, p->out.p, (p->d + 1) * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    ICEM_CUDA(cudaMemcpyAsync(p->h_out, p->out.p, (size_t)p->B * (p->d + 1) * sizeof(float), cudaMemcpyDeviceToHost,
+                              p->stream));
   } catch (...) {
     cudaStreamEndCapture(p->stream, &g);
     if (g) cudaGraphDestroy(g);
@@ -654,6 +674,12 @@ int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
     throw Unsupported("unknown planner id");
   const bool cem_std = cfg->planner == ICEM_PLANNER_CEM_STD;
   const bool rnd = cfg->planner == ICEM_PLANNER_RANDOM;
+  p->B = cfg->num_problems > 0 ? cfg->num_problems : 1;
+  if (p->B > 4096) throw InvalidArg("num_problems must be <= 4096");
+  if (p->B > 1) {
+    if (cfg->world_size > 1) throw Unsupported("num_problems > 1 needs world_size == 1 (problems are not sharded)");
+    if (cfg->dynamics == ICEM_DYN_MLP) throw Unsupported("num_problems > 1 is not available for the MLP rollout");
+  }
   if (rnd) {
     // MpcRandom (controllers/mpc.py:86-138): ONE population per plan step, nothing is refit or reused
     if (cfg->action_change_frequency < 0 || cfg->action_change_frequency >= cfg->horizon)
@@ -715,20 +741,21 @@ int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
         s0r[t * p->d + j] = std::max(1e-8f, std::min(half * 0.5f, s0[t * p->d + j]));
       }
   upload(p->reset_std, s0r);
-  p->mean.alloc(p->hd);
-  p->stdv.alloc(p->hd);
+  const size_t B = (size_t)p->B;      // every per-problem buffer is [B][...]
+  p->mean.alloc(B * p->hd);
+  p->stdv.alloc(B * p->hd);
   for (int b = 0; b < 2; ++b) {
-    p->elite_actions[b].alloc((size_t)p->k * p->stride);
-    p->elite_costs[b].alloc(p->k);
-    p->elite_idx[b].alloc(p->k);
+    p->elite_actions[b].alloc(B * p->k * p->stride);
+    p->elite_costs[b].alloc(B * p->k);
+    p->elite_idx[b].alloc(B * p->k);
   }
-  p->trace_mean.alloc((size_t)p->iters * p->hd);
-  p->trace_std.alloc((size_t)p->iters * p->hd);
-  p->trace_costs.alloc((size_t)p->iters * p->k);
-  p->trace_idx.alloc((size_t)p->iters * p->k);
-  p->out.alloc(p->d + 1);
-  p->cand.alloc((size_t)p->sm_count * p->k);
-  p->ticket.alloc(1);
+  p->trace_mean.alloc(B * p->iters * p->hd);
+  p->trace_std.alloc(B * p->iters * p->hd);
+  p->trace_costs.alloc(B * p->iters * p->k);
+  p->trace_idx.alloc(B * p->iters * p->k);
+  p->out.alloc(B * (p->d + 1));
+  p->cand.alloc(B * p->sm_count * p->k);
+  p->ticket.alloc(B);
   build_plan(p.get());
 
   if (cfg->dynamics == ICEM_DYN_HALFCHEETAH || cfg->dynamics == ICEM_DYN_HUMANOID_STANDUP) {
@@ -744,11 +771,11 @@ int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
     p->recv_rec.alloc(p->rec_bytes * cfg->world_size);
   }
   // staging sized for the largest state we support
-  p->in_bytes = sizeof(StepState) + 256 * sizeof(float);
+  p->in_bytes = sizeof(StepState) + B * kStateSlot * sizeof(float);
   p->step_in.alloc(p->in_bytes);
   ICEM_CUDA(cudaMallocHost(&p->h_in, p->in_bytes));
   memset(p->h_in, 0, p->in_bytes);
-  ICEM_CUDA(cudaMallocHost(&p->h_out, (p->d + 1) * sizeof(float)));
+  ICEM_CUDA(cudaMallocHost(&p->h_out, B * (p->d + 1) * sizeof(float)));
   ICEM_CUDA(cudaStreamSynchronize(p->stream));
   *out = p.release();
   ICEM_API_END
@@ -985,7 +1012,8 @@ static void plan_launch(icem_planner* p, const double* state, int32_t state_dim)
     // parity mode: direct launches (injected buffers are per-call)
     ICEM_CUDA(cudaMemcpyAsync(p->step_in.p, p->h_in, p->in_bytes, cudaMemcpyHostToDevice, p->stream));
     enqueue_iterations(p, false);
-    ICEM_CUDA(cudaMemcpyAsync(p->h_out, p->out.p, (p->d + 1) * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    ICEM_CUDA(cudaMemcpyAsync(p->h_out, p->out.p, (size_t)p->B * (p->d + 1) * sizeof(float), cudaMemcpyDeviceToHost,
+                              p->stream));
   } else {
     ensure_graph(p);
     ICEM_CUDA(cudaGraphLaunch(p->graph_exec, p->stream));
@@ -1001,13 +1029,35 @@ static void plan_finish(icem_planner* p, double* action_out) {
   p->plan_in_flight = false;
   ICEM_CUDA(cudaEventElapsedTime(&p->last_total_ms, p->ev_a, p->ev_b));
   p->last_rollout_ms = 0.f;
-  for (int i = 0; i < p->d; ++i) action_out[i] = (double)p->h_out[i];
+  for (int b = 0; b < p->B; ++b)
+    for (int i = 0; i < p->d; ++i) action_out[(size_t)b * p->d + i] = (double)p->h_out[(size_t)b * (p->d + 1) + i];
   finish_step(p);
+}
+
+int icem_plan_batch(icem_planner_t* p, const double* states, int32_t state_dim, int32_t num_states,
+                    double* actions_out) {
+  ICEM_API_BEGIN
+  if (!p || !states || !actions_out) throw InvalidArg("null argument");
+  if (num_states != p->B) throw InvalidArg("num_states must equal the handle's num_problems");
+  plan_launch(p, states, state_dim);
+  plan_finish(p, actions_out);
+  ICEM_API_END
+}
+
+int icem_num_problems(icem_planner_t* p) { return p ? p->B : -1; }
+
+int icem_set_active_problem(icem_planner_t* p, int32_t problem) {
+  ICEM_API_BEGIN
+  if (!p) throw InvalidArg("null planner");
+  if (problem < 0 || problem >= p->B) throw InvalidArg("problem index out of range");
+  p->active = problem;
+  ICEM_API_END
 }
 
 int icem_plan(icem_planner_t* p, const double* state, int32_t state_dim, double* action_out) {
   ICEM_API_BEGIN
   if (!p || !state || !action_out) throw InvalidArg("null argument");
+  if (p->B != 1) throw StateError("this handle batches several problems: use icem_plan_batch");
   plan_launch(p, state, state_dim);
   plan_finish(p, action_out);
   ICEM_API_END
@@ -1016,6 +1066,7 @@ int icem_plan(icem_planner_t* p, const double* state, int32_t state_dim, double*
 int icem_plan_async(icem_planner_t* p, const double* state, int32_t state_dim) {
   ICEM_API_BEGIN
   if (!p || !state) throw InvalidArg("null argument");
+  if (p->B != 1) throw StateError("this handle batches several problems: use icem_plan_batch");
   plan_launch(p, state, state_dim);
   ICEM_API_END
 }
@@ -1029,6 +1080,7 @@ int icem_plan_finish(icem_planner_t* p, double* action_out) {
 
 int icem_plan_device(icem_planner_t* p) {
   ICEM_API_BEGIN
+  if (p && p->B != 1) throw Unsupported("not available on a handle that batches several problems");
   if (!p) throw InvalidArg("null planner");
   if (!p->was_reset) throw StateError("beginning_of_rollout() needs to be called before");
   require_model(p);
@@ -1043,6 +1095,7 @@ int icem_plan_device(icem_planner_t* p) {
 
 int icem_advance_state_device(icem_planner_t* p) {
   ICEM_API_BEGIN
+  if (p && p->B != 1) throw Unsupported("not available on a handle that batches several problems");
   if (!p) throw InvalidArg("null planner");
   require_model(p);
   ICEM_CUDA(cudaSetDevice(p->cfg.device));
@@ -1068,6 +1121,7 @@ int icem_last_plan_ms(icem_planner_t* p, float* total_ms, float* rollout_ms) {
 
 int icem_inject_noise(icem_planner_t* p, int32_t iteration, int32_t rows, const float* zr, const float* zi) {
   ICEM_API_BEGIN
+  if (p && p->B != 1) throw Unsupported("not available on a handle that batches several problems");
   if (!p || !zr) throw InvalidArg("null argument");
   if (iteration < 0 || iteration >= p->iters) throw InvalidArg("iteration out of range");
   if (!p->white && !zi) throw InvalidArg("zi required for colored noise");
@@ -1098,7 +1152,7 @@ int icem_get_mean(icem_planner_t* p, float* out) {
   if (!p || !out) throw InvalidArg("null argument");
   ICEM_CUDA(cudaSetDevice(p->cfg.device));
   ICEM_CUDA(cudaStreamSynchronize(p->stream));
-  ICEM_CUDA(cudaMemcpy(out, p->mean.p, p->hd * sizeof(float), cudaMemcpyDeviceToHost));
+  ICEM_CUDA(cudaMemcpy(out, p->mean.p + (size_t)p->active * p->hd, p->hd * sizeof(float), cudaMemcpyDeviceToHost));
   ICEM_API_END
 }
 
@@ -1107,7 +1161,7 @@ int icem_get_std(icem_planner_t* p, float* out) {
   if (!p || !out) throw InvalidArg("null argument");
   ICEM_CUDA(cudaSetDevice(p->cfg.device));
   ICEM_CUDA(cudaStreamSynchronize(p->stream));
-  ICEM_CUDA(cudaMemcpy(out, p->stdv.p, p->hd * sizeof(float), cudaMemcpyDeviceToHost));
+  ICEM_CUDA(cudaMemcpy(out, p->stdv.p + (size_t)p->active * p->hd, p->hd * sizeof(float), cudaMemcpyDeviceToHost));
   ICEM_API_END
 }
 
@@ -1122,10 +1176,12 @@ int icem_get_elites(icem_planner_t* p, float* actions_out, float* costs_out, int
   ICEM_CUDA(cudaStreamSynchronize(p->stream));
   const int b = (p->iters - 1) & 1;
   if (actions_out)
-    ICEM_CUDA(cudaMemcpy2D(actions_out, p->hd * sizeof(float), p->elite_actions[b].p, p->stride * sizeof(float),
+    ICEM_CUDA(cudaMemcpy2D(actions_out, p->hd * sizeof(float),
+                           p->elite_actions[b].p + (size_t)p->active * p->k * p->stride, p->stride * sizeof(float),
                            p->hd * sizeof(float), p->k, cudaMemcpyDeviceToHost));
-  if (costs_out) ICEM_CUDA(cudaMemcpy(costs_out, p->elite_costs[b].p, p->k * sizeof(float), cudaMemcpyDeviceToHost));
-  if (idx_out) ICEM_CUDA(cudaMemcpy(idx_out, p->elite_idx[b].p, p->k * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  const size_t ak = (size_t)p->active * p->k;
+  if (costs_out) ICEM_CUDA(cudaMemcpy(costs_out, p->elite_costs[b].p + ak, p->k * sizeof(float), cudaMemcpyDeviceToHost));
+  if (idx_out) ICEM_CUDA(cudaMemcpy(idx_out, p->elite_idx[b].p + ak, p->k * sizeof(int32_t), cudaMemcpyDeviceToHost));
   ICEM_API_END
 }
 
@@ -1148,12 +1204,13 @@ int icem_get_iteration(icem_planner_t* p, int32_t i, float* mean_out, float* std
   if (i < 0 || i >= p->iters) throw InvalidArg("iteration out of range");
   ICEM_CUDA(cudaSetDevice(p->cfg.device));
   ICEM_CUDA(cudaStreamSynchronize(p->stream));
-  if (mean_out) ICEM_CUDA(cudaMemcpy(mean_out, p->trace_mean.p + (size_t)i * p->hd, p->hd * 4, cudaMemcpyDeviceToHost));
-  if (std_out) ICEM_CUDA(cudaMemcpy(std_out, p->trace_std.p + (size_t)i * p->hd, p->hd * 4, cudaMemcpyDeviceToHost));
+  const size_t th = ((size_t)p->active * p->iters + i) * p->hd, tk = ((size_t)p->active * p->iters + i) * p->k;
+  if (mean_out) ICEM_CUDA(cudaMemcpy(mean_out, p->trace_mean.p + th, p->hd * 4, cudaMemcpyDeviceToHost));
+  if (std_out) ICEM_CUDA(cudaMemcpy(std_out, p->trace_std.p + th, p->hd * 4, cudaMemcpyDeviceToHost));
   if (elite_costs_out)
-    ICEM_CUDA(cudaMemcpy(elite_costs_out, p->trace_costs.p + (size_t)i * p->k, p->k * 4, cudaMemcpyDeviceToHost));
+    ICEM_CUDA(cudaMemcpy(elite_costs_out, p->trace_costs.p + tk, p->k * 4, cudaMemcpyDeviceToHost));
   if (elite_idx_out)
-    ICEM_CUDA(cudaMemcpy(elite_idx_out, p->trace_idx.p + (size_t)i * p->k, p->k * 4, cudaMemcpyDeviceToHost));
+    ICEM_CUDA(cudaMemcpy(elite_idx_out, p->trace_idx.p + tk, p->k * 4, cudaMemcpyDeviceToHost));
   ICEM_API_END
 }
 
@@ -1164,7 +1221,8 @@ int icem_get_costs(icem_planner_t* p, int32_t i, float* out, int32_t n) {
   if (n < 0 || n > p->plan[i].rows_cap) throw InvalidArg("row count out of range");
   ICEM_CUDA(cudaSetDevice(p->cfg.device));
   ICEM_CUDA(cudaStreamSynchronize(p->stream));
-  ICEM_CUDA(cudaMemcpy(out, p->costs.p + p->plan[i].cost_off, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  ICEM_CUDA(cudaMemcpy(out, p->costs.p + (size_t)p->active * p->costs_per + p->plan[i].cost_off, (size_t)n * 4,
+                       cudaMemcpyDeviceToHost));
   ICEM_API_END
 }
 
@@ -1178,7 +1236,8 @@ int icem_get_actions(icem_planner_t* p, int32_t i, float* out, int32_t n) {
   ICEM_CUDA(cudaSetDevice(p->cfg.device));
   ICEM_CUDA(cudaStreamSynchronize(p->stream));
   if (n)
-    ICEM_CUDA(cudaMemcpy2D(out, p->hd * sizeof(float), p->actions.p + p->plan[i].act_off * p->stride,
+    ICEM_CUDA(cudaMemcpy2D(out, p->hd * sizeof(float),
+                           p->actions.p + (size_t)p->active * p->actions_per + p->plan[i].act_off * p->stride,
                            p->stride * sizeof(float), p->hd * sizeof(float), n, cudaMemcpyDeviceToHost));
   ICEM_API_END
 }
@@ -1379,6 +1438,7 @@ int icem_comm_init(icem_planner_t* p, const char id[ICEM_UNIQUE_ID_BYTES]) {
 int icem_bench_device(icem_planner_t* p, int32_t steps, int32_t warmup, int32_t flush_l2, float* total_ms,
                       float* rollout_ms, int32_t* rollout_launches) {
   ICEM_API_BEGIN
+  if (p && p->B != 1) throw Unsupported("not available on a handle that batches several problems");
   if (!p) throw InvalidArg("null planner");
   if (!p->was_reset) throw StateError("beginning_of_rollout() needs to be called before");
   require_model(p);

@@ -60,6 +60,10 @@ struct RolloutArgs {
   const float* inj_zi;
   const StepState* ss;
   uint32_t seed_lo, seed_hi;
+  // several independent MPC problems in one launch (blockIdx.y = problem): element strides between consecutive
+  // problems' buffers; problem i draws with seed + i.  All zero / unused for a single problem.
+  unsigned long long prob_actions, prob_costs;
+  int prob_dist, prob_elites, prob_state;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -92,6 +96,22 @@ __device__ __forceinline__ float truncnorm_ppf(float w, float a, float b) {
   const float pl = fmaf(ul, mass, pa), pr = fmaf(ur, mass, pnb);
   const float x = pl <= pr ? normcdfinvf(pl) : -normcdfinvf(pr);
   return fminf(fmaxf(x, a), b);
+}
+
+// MpcRandom (mpc.py:95-107): sample() is called row by row, step by step; the action drawn at construction serves
+// the first `freq` calls, every later draw serves freq + 1 calls.  Call index -> segment -> Philox counter, so the
+// result does not depend on how rows are spread over ranks.  Kept out of line: a rare mode must not perturb the
+// register allocation / code layout of the fused kernel's hot rollout loop (measured: 1.3 % when inlined).
+__device__ __noinline__ float random_shooting_uniform(uint32_t plans_total, int n_global, uint32_t grow, int h, int t,
+                                                      int dim, int freq, uint32_t seed_lo, uint32_t seed_hi) {
+  const unsigned long long call = ((unsigned long long)plans_total * (unsigned long long)n_global
+                                   + (unsigned long long)grow) * (unsigned long long)h + (unsigned long long)t;
+  const unsigned long long f = (unsigned long long)freq;
+  const unsigned long long seg = call < f ? 0ull : 1ull + (call - f) / (f + 1ull);
+  const Philox4 r = philox4x32_10((uint32_t)seg, (uint32_t)(seg >> 32), (uint32_t)(dim >> 2), 0x524E4431u,
+                                  seed_lo, seed_hi);
+  const uint32_t w = (dim & 3) == 0 ? r.x : (dim & 3) == 1 ? r.y : (dim & 3) == 2 ? r.z : r.w;
+  return ((float)w + 0.5f) * 2.3283064365386963e-10f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -139,6 +159,18 @@ template <class Dyn, bool kSample, bool kRollout>
 __global__ void __launch_bounds__(Dyn::kWarpsPerCta * 32, Dyn::kMinCtasPerSm)
 rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Params dp) {
   extern __shared__ __align__(128) float smem[];
+  if (blockIdx.y) {          // several problems in one launch: this CTA works on problem blockIdx.y
+    const unsigned long long pr = blockIdx.y;
+    a.actions += pr * a.prob_actions;
+    a.costs += pr * a.prob_costs;
+    a.mean += pr * (unsigned)a.prob_dist;
+    a.std += pr * (unsigned)a.prob_dist;
+    a.prev_elites += pr * (unsigned)a.prob_elites;
+    a.start_state += pr * (unsigned)a.prob_state;
+    const unsigned long long seed = (((unsigned long long)a.seed_hi << 32) | a.seed_lo) + pr;
+    a.seed_lo = (uint32_t)seed;
+    a.seed_hi = (uint32_t)(seed >> 32);
+  }
   const int warps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -211,13 +243,15 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
   for (int base = cta_lo; base < cta_hi; base += warps, ++it) {
     const int row = base + warp;
     const bool active = row < cta_hi;
-    if (!active && !Dyn::kCtaLockstep) break;
-    float* tile = w_tile;
+    // Warps whose row is past the end skip the round.  The lockstep barrier below is a NAMED barrier counted over
+    // the warps that do have a row this round (warp-uniform, the same for every participant), so no thread ever
+    // waits at a barrier that others do not reach (compute-sanitizer synccheck clean).
+    const int n_active = min(warps, cta_hi - base);
     if (!active) {
-      if (kRollout)
-        for (int t = 0; t < h; ++t) __syncthreads();
+      if (!Dyn::kCtaLockstep) break;
       continue;
     }
+    float* tile = w_tile;
     if (kSample) {
       const bool shifted = row >= a.n_fresh_local;
       // global trajectory index: fresh rows are contiguous per rank, shifted rows follow N_i
@@ -252,23 +286,10 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
       const float* elite = shifted ? a.prev_elites + (size_t)(row - a.n_fresh_local) * a.stride : nullptr;
       for (int o = lane; o < hd; o += 32) {
         const int t = (int)__umulhi((uint32_t)o, sc.magic_d), dim = o - t * d;
-        if (sc.rnd_freq >= 0) {
-          // MpcRandom (mpc.py:95-107): sample() is called row by row, step by step; the action drawn at
-          // construction serves the first `freq` calls, every later draw serves freq + 1 calls.  Call index ->
-          // segment -> Philox counter, so the result does not depend on how rows are spread over ranks.
-          float u;
-          if (ss.inject) {
-            u = tile[o];
-          } else {
-            const unsigned long long call = ((unsigned long long)ss.plans_total * (unsigned long long)sc.n_global
-                                             + (unsigned long long)grow) * (unsigned long long)h + (unsigned long long)t;
-            const unsigned long long f = (unsigned long long)sc.rnd_freq;
-            const unsigned long long seg = call < f ? 0ull : 1ull + (call - f) / (f + 1ull);
-            const Philox4 r = philox4x32_10((uint32_t)seg, (uint32_t)(seg >> 32), (uint32_t)(dim >> 2), 0x524E4431u,
-                                            a.seed_lo, a.seed_hi);
-            const uint32_t w = (dim & 3) == 0 ? r.x : (dim & 3) == 1 ? r.y : (dim & 3) == 2 ? r.z : r.w;
-            u = ((float)w + 0.5f) * 2.3283064365386963e-10f;
-          }
+        if (sc.rnd_freq >= 0) {      // MpcRandom: piecewise-constant uniform actions
+          const float u = ss.inject ? tile[o]
+                                    : random_shooting_uniform(ss.plans_total, sc.n_global, grow, h, t, dim, sc.rnd_freq,
+                                                              a.seed_lo, a.seed_hi);
           tile[o] = fminf(fmaf(s_high[dim] - s_low[dim], u, s_low[dim]), s_high[dim]);   // Box.sample (gym)
           continue;
         }
@@ -322,7 +343,7 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
       dyn.reset(a.start_state);
       float total = (cc.reduce == 1) ? INFINITY : 0.f;
       for (int t = 0; t < h; ++t) {
-        if (Dyn::kCtaLockstep) __syncthreads();
+        if (Dyn::kCtaLockstep) asm volatile("bar.sync 1, %0;" :: "r"(n_active * 32) : "memory");
         const float* act = tile + t * d;
         const float c = step_cost(cc, dyn, act, d);
         if (cc.reduce == 0) total += c;

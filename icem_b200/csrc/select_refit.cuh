@@ -34,6 +34,9 @@ struct SelectArgs {
   // multi-rank: where this rank's record goes ([k] keys then [k][stride] actions); null on one GPU
   unsigned long long* send_keys;
   float* send_actions;
+  // several problems in one launch (blockIdx.y = problem): element strides between problems (0 for one problem)
+  unsigned long long prob_actions, prob_costs;
+  int prob_cand;
 };
 
 struct RefitArgs {
@@ -61,6 +64,9 @@ struct RefitArgs {
   const float* low; const float* high;   // [d] action bounds (levine std clamp)
   float* out_action;               // [d]  (last iteration)
   float* out_best_cost;            // [1]  min(costs) of the last iteration (icem.py:177)
+  // several problems in one launch: element strides between problems (0 for one problem)
+  unsigned long long prob_actions;
+  int prob_dist, prob_elites, prob_k, prob_trace_hd, prob_trace_k, prob_out;
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -207,6 +213,27 @@ __device__ void merge_refit(const RefitArgs& r, unsigned long long* s_keys /* [k
 __global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectArgs a, RefitArgs r, int fuse_refit) {
   extern __shared__ unsigned long long s_keys[];   // [k]
   __shared__ bool s_last;
+  if (blockIdx.y) {          // this CTA works on problem blockIdx.y
+    const unsigned long long pr = blockIdx.y;
+    a.costs += pr * a.prob_costs;
+    a.actions += pr * a.prob_actions;
+    a.cand += pr * (unsigned)a.prob_cand;
+    a.ticket += pr;
+    r.local_actions += pr * r.prob_actions;
+    r.prev_elite_actions += pr * (unsigned)r.prob_elites;
+    r.new_elite_actions += pr * (unsigned)r.prob_elites;
+    r.prev_elite_costs += pr * (unsigned)r.prob_k;
+    r.new_elite_costs += pr * (unsigned)r.prob_k;
+    r.new_elite_idx += pr * (unsigned)r.prob_k;
+    r.mean += pr * (unsigned)r.prob_dist;
+    r.std += pr * (unsigned)r.prob_dist;
+    r.trace_mean += pr * (unsigned)r.prob_trace_hd;
+    r.trace_std += pr * (unsigned)r.prob_trace_hd;
+    r.trace_costs += pr * (unsigned)r.prob_trace_k;
+    r.trace_idx += pr * (unsigned)r.prob_trace_k;
+    r.out_action += pr * (unsigned)r.prob_out;
+    r.out_best_cost += pr * (unsigned)r.prob_out;
+  }
   const StepState ss = *a.ss;
   const int n_rows = a.n_fresh_local + ((a.iteration == 0 && ss.has_prev_elites) ? a.n_shift_local : 0);
   const int chunk = (n_rows + gridDim.x - 1) / gridDim.x;

@@ -40,6 +40,7 @@ class PlannerSettings:
     keep_iteration_actions: bool = False
     planner: str = "icem"                # "icem" (MpcICem) | "cem_std" (MpcCemStd) | "random" (MpcRandom)
     action_change_frequency: int = 0     # random only (controllers/mpc.py:91)
+    num_problems: int = 1                # independent MPC problems batched in one handle (plan_batch)
     execute_best_elite: bool = True      # cem_std only (controllers/mpc.py:237-240)
     shift_means: bool = True             # cem_std only (controllers/mpc.py:243-248)
     bounds_like_levine: bool = False     # cem_std only (controllers/mpc.py:290-301)
@@ -72,7 +73,7 @@ class Planner:
             world_size=int(s.world_size), rank=int(s.rank), planner=_lib.PLANNER[s.planner],
             execute_best_elite=int(bool(s.execute_best_elite)), shift_means=int(bool(s.shift_means)),
             bounds_like_levine=int(bool(s.bounds_like_levine)),
-            action_change_frequency=int(s.action_change_frequency),
+            action_change_frequency=int(s.action_change_frequency), num_problems=int(s.num_problems),
             factor_decrease_num=float(s.factor_decrease_num), alpha=float(s.alpha), init_std=float(s.init_std),
             fraction_elites_reused=float(s.fraction_elites_reused), noise_beta=float(s.noise_beta),
             seed=int(s.seed) & (2 ** 64 - 1), action_low=fptr(self._low), action_high=fptr(self._high))
@@ -157,6 +158,19 @@ class Planner:
         out = np.empty(self.d, dtype=np.float64)
         check(self._lib.icem_plan(self._h, dptr(st), st.shape[0], dptr(out)))
         return out
+
+    def plan_batch(self, states) -> np.ndarray:
+        """One plan step of every problem of a `num_problems = B` handle: states [B, state_dim] -> actions [B, d]."""
+        st = f64(states)
+        if st.ndim != 2:
+            raise ValueError("states must be [num_problems, state_dim]")
+        out = np.empty((st.shape[0], self.d), dtype=np.float64)
+        check(self._lib.icem_plan_batch(self._h, dptr(st), st.shape[1], st.shape[0], dptr(out)))
+        return out
+
+    def set_active_problem(self, i):
+        """Which problem mean() / std() / elites() / iteration_record() / costs() / actions() read."""
+        check(self._lib.icem_set_active_problem(self._h, int(i)))
 
     def plan_async(self, state):
         """Launch a plan step without waiting for it (icem_plan_async); pair with plan_finish()."""

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define ICEM_ABI_VERSION 3
+#define ICEM_ABI_VERSION 4
 
 /* status codes */
 enum { ICEM_OK = 0, ICEM_ERR_INVALID = 1, ICEM_ERR_CUDA = 2, ICEM_ERR_STATE = 3, ICEM_ERR_UNSUPPORTED = 4,
@@ -83,6 +83,10 @@ typedef struct icem_config {
   int32_t bounds_like_levine;     /* CEM_STD (mpc.py:290-301): clamp std to half the distance to the bounds, +-2 sigma */
   int32_t action_change_frequency;/* RANDOM (mpc.py:91,95-101): a drawn action is held for this many further sample()
                                      calls; calls run over the whole population row by row, and on across plan steps */
+  int32_t num_problems;           /* independent MPC problems batched in ONE handle (0 or 1 = a single problem): same
+                                     settings and model, own start state / mean / std / elites each, Philox seed + i;
+                                     every kernel of a plan step covers all problems (grid.y = problem).  See
+                                     icem_plan_batch. */
   double factor_decrease_num;     /* gamma */
   double alpha;
   double init_std;
@@ -167,6 +171,15 @@ int icem_plan(icem_planner_t* p, const double* state, int32_t state_dim, double*
  * per handle (ICEM_ERR_STATE otherwise). */
 int icem_plan_async(icem_planner_t* p, const double* state, int32_t state_dim);
 int icem_plan_finish(icem_planner_t* p, double* action_out);
+
+/* One plan step of EVERY problem of a handle created with num_problems = B: states[B][state_dim] in,
+ * actions_out[B][act_dim] out, one CUDA graph launch for all of them.  Problem i plans exactly like a single-problem
+ * handle created with seed + i.  The getters (icem_get_mean / _std / _elites / _iteration / _costs / _actions) read
+ * the problem selected with icem_set_active_problem (default 0). */
+int icem_plan_batch(icem_planner_t* p, const double* states, int32_t state_dim, int32_t num_states,
+                    double* actions_out);
+int icem_num_problems(icem_planner_t* p);
+int icem_set_active_problem(icem_planner_t* p, int32_t problem);
 
 /* Same plan step with the start state already resident on the device (no host<->device copy): the state is
  * the one left by the previous icem_plan / icem_advance_state_device.  Asynchronous; pair with icem_sync. */

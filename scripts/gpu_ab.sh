@@ -1,6 +1,4 @@
-# A/B: library variants on the two GT workloads
-for v in c2_l0 c2_l1 c3_l0 c3_l1; do
-  for wl in humanoid_standup_gt_n16384 halfcheetah_gt_n4096; do
-    ICEM_B200_LIB=$PWD/icem_b200/lib/libicem_$v.so python bench.py --workload $wl --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$v', '$wl', round(d['value']), 'traj/s', round(d['ms_per_step'],2),'ms', 'kernel_ms', round(d['roofline']['kernel_ms_avg'],3))"
-  done
-done
+python -m pytest tests/test_gpu_articulated.py tests/test_gpu_batched.py -m gpu -x -q 2>&1 | tail -2
+for i in 1 2; do python bench.py --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('bench', d['value'], d['ms_per_step'], d['roofline']['kernel_ms_avg'])"; done
+timeout 200 compute-sanitizer --tool synccheck --print-limit 5 python scripts/sanitize.py cheetah humanoid > gpurun_out/sanitize_synccheck.log 2>&1; grep -E "ok$|ERROR SUMMARY" gpurun_out/sanitize_synccheck.log

@@ -52,3 +52,57 @@ def test_async_halves_state_machine():
     np.testing.assert_array_equal(a, q.plan(st))
     p.close()
     q.close()
+
+
+@pytest.mark.parametrize("name,scale", [("halfcheetah_gt_n4096", 1 / 32), ("dense_tanh_cheetah_n4096", 1 / 64),
+                                        ("humanoid_standup_gt_n16384", 1 / 256)])
+def test_multi_problem_handle_equals_single_problem_handles(name, scale):
+    """icem_plan_batch: problem i of a num_problems = B handle plans bit-identically to a single-problem handle
+    created with seed + i, over several closed-loop steps (shifted / kept elites, per-problem distributions)."""
+    import dataclasses
+    from icem_b200 import workloads
+    from icem_b200.planner import IcemError, Planner
+    B = 5
+    w = workloads.get_workload(name)
+
+    def make(**over):
+        s = dataclasses.replace(workloads.planner_settings(name, scale_population=scale, seed=7), **over)
+        p = Planner(s)
+        if w.get("dense"):
+            p.set_dense_model(*workloads.dense_model_weights(*w["dense"]))
+        p.begin_rollout()
+        return p
+    batch = make(num_problems=B)
+    singles = [make(seed=7 + i) for i in range(B)]
+    states = np.stack([workloads.start_state(name, seed=i) for i in range(B)])
+    with pytest.raises(IcemError, match="icem_plan_batch"):
+        batch.plan(states[0])
+    for step in range(3):
+        acts = batch.plan_batch(states)
+        assert acts.shape == (B, w["act_dim"])
+        for i, p in enumerate(singles):
+            a = p.plan(states[i])
+            np.testing.assert_array_equal(acts[i], a)
+            batch.set_active_problem(i)
+            np.testing.assert_array_equal(batch.mean(), p.mean())
+            np.testing.assert_array_equal(batch.elites()[0], p.elites()[0])
+            np.testing.assert_array_equal(batch.iteration_record(1)["elite_idx"], p.iteration_record(1)["elite_idx"])
+            states[i] = p.sim_step(states[i], a)[0]
+        assert not np.array_equal(acts[0], acts[1])
+    batch.close()
+    for p in singles:
+        p.close()
+
+
+def test_fused_episode_batch_runs_like_the_streamed_one():
+    from icem_b200.batched import make_episode_batch, make_fused_episode_batch
+    B, T = 4, 3
+    fused = make_fused_episode_batch("HalfCheetah", B, PARAMS, seed=3)
+    eps = fused.run(T)
+    streamed = make_episode_batch("HalfCheetah", B, PARAMS, seed=3)
+    ref = streamed.run(T)
+    for i in range(B):           # same env seeds, planner seeds 1003 + i in both
+        np.testing.assert_array_equal(eps[i]["actions"], ref[i]["actions"])
+        np.testing.assert_array_equal(eps[i]["rewards"], ref[i]["rewards"])
+    fused.close()
+    streamed.close()
