@@ -103,7 +103,11 @@ __device__ __forceinline__ float truncnorm_ppf(float w, float a, float b) {
 // result does not depend on how rows are spread over ranks.  Kept out of line: a rare mode must not perturb the
 // register allocation / code layout of the fused kernel's hot rollout loop (measured: 1.3 % when inlined).
 __device__ __noinline__ float random_shooting_uniform(uint32_t plans_total, int n_global, uint32_t grow, int h, int t,
-                                                      int dim, int freq, uint32_t seed_lo, uint32_t seed_hi) {
+                                                      int dim, int freq, uint32_t seed_lo, uint32_t seed_hi,
+                                                      uint32_t problem) {
+  const unsigned long long seed = (((unsigned long long)seed_hi << 32) | seed_lo) + problem;
+  seed_lo = (uint32_t)seed;
+  seed_hi = (uint32_t)(seed >> 32);
   const unsigned long long call = ((unsigned long long)plans_total * (unsigned long long)n_global
                                    + (unsigned long long)grow) * (unsigned long long)h + (unsigned long long)t;
   const unsigned long long f = (unsigned long long)freq;
@@ -118,11 +122,12 @@ __device__ __noinline__ float random_shooting_uniform(uint32_t plans_total, int 
 // unit normals for one trajectory row -> z[dim][j] (colored, row stride zs) or straight into the
 // tile (white).  Philox counter = (global row, block, step, iteration); key = seed.
 __device__ __forceinline__ void fill_normals(float* dst, int count, uint32_t grow, const RolloutArgs& a,
-                                             uint32_t step, int K2, int zs, bool white, bool uniform,
+                                             uint32_t problem, uint32_t step, int K2, int zs, bool white, bool uniform,
                                              uint32_t magic_K) {
   const int lane = lane_id();
   for (int b = lane; b * 4 < count; b += 32) {
-    Philox4 r = philox4x32_10(grow, (uint32_t)b, step, (uint32_t)a.iteration, a.seed_lo, a.seed_hi);
+    const unsigned long long seed = (((unsigned long long)a.seed_hi << 32) | a.seed_lo) + problem;   // problem i: seed + i
+    Philox4 r = philox4x32_10(grow, (uint32_t)b, step, (uint32_t)a.iteration, (uint32_t)seed, (uint32_t)(seed >> 32));
     float n[4];
     if (uniform) {                       // signed tail probabilities in (-1/2, 1/2) \ {0} (see truncnorm_ppf)
       const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
@@ -159,18 +164,16 @@ template <class Dyn, bool kSample, bool kRollout>
 __global__ void __launch_bounds__(Dyn::kWarpsPerCta * 32, Dyn::kMinCtasPerSm)
 rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Params dp) {
   extern __shared__ __align__(128) float smem[];
-  if (blockIdx.y) {          // several problems in one launch: this CTA works on problem blockIdx.y
-    const unsigned long long pr = blockIdx.y;
-    a.actions += pr * a.prob_actions;
-    a.costs += pr * a.prob_costs;
-    a.mean += pr * (unsigned)a.prob_dist;
-    a.std += pr * (unsigned)a.prob_dist;
-    a.prev_elites += pr * (unsigned)a.prob_elites;
-    a.start_state += pr * (unsigned)a.prob_state;
-    const unsigned long long seed = (((unsigned long long)a.seed_hi << 32) | a.seed_lo) + pr;
-    a.seed_lo = (uint32_t)seed;
-    a.seed_hi = (uint32_t)(seed >> 32);
-  }
+  // Several problems in one launch: this CTA works on problem blockIdx.y.  The kernel parameters stay untouched
+  // in the constant bank and every per-problem pointer is formed where it is used (all outside the rollout loop):
+  // rebasing `a` itself would pin the rebased pointers in registers across the hot loop (measured: -1.5 %).
+  const unsigned long long pr = blockIdx.y;
+#define ICEM_P_ACTIONS (a.actions + pr * a.prob_actions)
+#define ICEM_P_COSTS (a.costs + pr * a.prob_costs)
+#define ICEM_P_MEAN (a.mean + pr * (unsigned)a.prob_dist)
+#define ICEM_P_STD (a.std + pr * (unsigned)a.prob_dist)
+#define ICEM_P_ELITES (a.prev_elites + pr * (unsigned)a.prob_elites)
+#define ICEM_P_STATE (a.start_state + pr * (unsigned)a.prob_state)
   const int warps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -204,8 +207,8 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
   if (kSample && !sc.white)
     for (int i = threadIdx.x; i < h * K2; i += blockDim.x) s_G[(i / K2) * gs + (i % K2)] = sc.G[i];
   for (int i = threadIdx.x; i < hd; i += blockDim.x) {
-    s_mean[i] = a.mean[i];
-    s_std[i] = a.std[i];
+    s_mean[i] = ICEM_P_MEAN[i];
+    s_std[i] = ICEM_P_STD[i];
   }
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
     s_low[i] = sc.low[i];
@@ -219,8 +222,7 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
   }
   __syncthreads();
 
-  const StepState ss = *a.ss;
-  const int n_rows = a.n_fresh_local + ((a.iteration == 0 && ss.has_prev_elites) ? a.n_shift_local : 0);
+  const int n_rows = a.n_fresh_local + ((a.iteration == 0 && a.ss->has_prev_elites) ? a.n_shift_local : 0);
   // rows are dealt to CTAs in equal contiguous blocks (every SM gets the same number of trajectories +-1), and
   // round-robin to the warps inside a CTA
   const int cta_lo = (int)((long long)n_rows * blockIdx.x / gridDim.x);
@@ -232,7 +234,7 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
   if (!kSample) {   // prologue of the TMA load pipeline
     if (cta_lo + warp < cta_hi && lane == 0) {
       mbar_expect_tx(&w_bar[0], tile_bytes);
-      tma_load_1d(w_tile, a.actions + (size_t)(cta_lo + warp) * a.stride, tile_bytes, &w_bar[0]);
+      tma_load_1d(w_tile, ICEM_P_ACTIONS + (size_t)(cta_lo + warp) * a.stride, tile_bytes, &w_bar[0]);
     }
   }
 
@@ -253,6 +255,9 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
     }
     float* tile = w_tile;
     if (kSample) {
+      // re-read per row (an L1 hit) rather than held in registers across the rollout loop
+      const uint32_t ss_step = a.ss->step;
+      const bool ss_inject = a.ss->inject != 0;
       const bool shifted = row >= a.n_fresh_local;
       // global trajectory index: fresh rows are contiguous per rank, shifted rows follow N_i
       const uint32_t grow = shifted ? (uint32_t)(a.n_fresh_global + (row - a.n_fresh_local))
@@ -263,7 +268,7 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
       // ---- 1. unit normals ----
       float* zdst = sc.white ? tile : w_z;
       const int count = sc.white ? hd : d * K2;
-      if (ss.inject) {
+      if (ss_inject) {
         if (sc.white) {
           const float* src = a.inj_zr + (size_t)row * hd;
           for (int i = lane; i < hd; i += 32) tile[i] = src[i];
@@ -278,18 +283,18 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
           }
         }
       } else if (sc.rnd_freq < 0) {
-        fill_normals(zdst, count, grow, a, ss.step, K2, zs, sc.white, sc.trunc != 0, sc.magic_K);
+        fill_normals(zdst, count, grow, a, (uint32_t)pr, ss_step, K2, zs, sc.white, sc.trunc != 0, sc.magic_K);
       }
       __syncwarp();
       // ---- 2. synthesis + affine + clip (icem.py:73-79), elite shift (icem.py:91-104), mean row ----
       const bool mean_row = a.inject_mean_row0 && grow == 0u && !shifted;
-      const float* elite = shifted ? a.prev_elites + (size_t)(row - a.n_fresh_local) * a.stride : nullptr;
+      const float* elite = shifted ? ICEM_P_ELITES + (size_t)(row - a.n_fresh_local) * a.stride : nullptr;
       for (int o = lane; o < hd; o += 32) {
         const int t = (int)__umulhi((uint32_t)o, sc.magic_d), dim = o - t * d;
         if (sc.rnd_freq >= 0) {      // MpcRandom: piecewise-constant uniform actions
-          const float u = ss.inject ? tile[o]
-                                    : random_shooting_uniform(ss.plans_total, sc.n_global, grow, h, t, dim, sc.rnd_freq,
-                                                              a.seed_lo, a.seed_hi);
+          const float u = ss_inject ? tile[o]
+                                    : random_shooting_uniform(a.ss->plans_total, sc.n_global, grow, h, t, dim, sc.rnd_freq,
+                                                              a.seed_lo, a.seed_hi, (uint32_t)pr);
           tile[o] = fminf(fmaf(s_high[dim] - s_low[dim], u, s_low[dim]), s_high[dim]);   // Box.sample (gym)
           continue;
         }
@@ -322,7 +327,7 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_1d(a.actions + (size_t)row * a.stride, tile, tile_bytes);
+        tma_store_1d(ICEM_P_ACTIONS + (size_t)row * a.stride, tile, tile_bytes);
         tma_store_commit();
       }
     } else {
@@ -332,7 +337,7 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
       const int nxt = row + warps;
       if (nxt < cta_hi && lane == 0) {
         mbar_expect_tx(&w_bar[buf ^ 1], tile_bytes);
-        tma_load_1d(w_tile + (buf ^ 1) * tile_floats, a.actions + (size_t)nxt * a.stride, tile_bytes,
+        tma_load_1d(w_tile + (buf ^ 1) * tile_floats, ICEM_P_ACTIONS + (size_t)nxt * a.stride, tile_bytes,
                     &w_bar[buf ^ 1]);
       }
       mbar_wait(&w_bar[buf], (uint32_t)((it >> 1) & 1));
@@ -340,7 +345,7 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
 
     if (kRollout) {
       // ---- 4. open-loop rollout from the shared start state, cost on the pre-action observation ----
-      dyn.reset(a.start_state);
+      dyn.reset(ICEM_P_STATE);
       float total = (cc.reduce == 1) ? INFINITY : 0.f;
       for (int t = 0; t < h; ++t) {
         if (Dyn::kCtaLockstep) asm volatile("bar.sync 1, %0;" :: "r"(n_active * 32) : "memory");
@@ -351,11 +356,17 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
         else total = c;
         if (t + 1 < h) dyn.step(act);      // the final predicted state is never scored (F9)
       }
-      if (lane == 0) a.costs[row] = total;
+      if (lane == 0) ICEM_P_COSTS[row] = total;
     }
     __syncwarp();
   }
   if (kSample && lane == 0) tma_store_wait_all();
+#undef ICEM_P_ACTIONS
+#undef ICEM_P_COSTS
+#undef ICEM_P_MEAN
+#undef ICEM_P_STD
+#undef ICEM_P_ELITES
+#undef ICEM_P_STATE
 }
 
 // shared-memory footprint of rollout_kernel for `warps` warps per CTA
