@@ -55,7 +55,7 @@ class MpcICemB200(*_Bases):
             raise TypeError(f"MpcICemB200 needs a CUDA-capable forward model (got {type(fm).__name__}); "
                             "use forward_model 'CudaGroundTruthModel' / 'CudaDenseTanhModel'. There is no CPU fallback.")
         spec = fm.cuda_spec()
-        cost, penalise = self._cost_spec()
+        cost, penalise, *cost_extra = self._cost_spec()
         if device is None or world_size is None or rank is None:
             from .distributed import default_placement
             dev_, ws_, rk_ = default_placement()
@@ -70,7 +70,9 @@ class MpcICemB200(*_Bases):
             dynamics=spec["dynamics"], cost=cost, obs_dim=spec["obs_dim"], penalise_flipping=penalise,
             cost_along_trajectory=self.cost_along_trajectory, alpha=self.alpha, elites_size=self.elites_size,
             opt_iterations=self.opt_iter, init_std=self.init_std, seed=seed, device=device, world_size=world_size,
-            rank=rank, num_problems=num_problems, **self._sampler_settings()))
+            rank=rank, num_problems=num_problems, cost_params=cost_extra[0] if cost_extra else None,
+            articulated_model=spec.get("articulated_model"),
+            obs_offset=0 if spec["dynamics"] == "articulated" else None, **self._sampler_settings()))
         if spec.get("dense") is not None:
             self._planner.set_dense_model(*spec["dense"])
         if spec.get("mlp") is not None:
@@ -231,7 +233,10 @@ class MpcICemB200(*_Bases):
             return (_ref["buffer"]() if _ref else api.EliteBuffer())
         if self._elite_cache is None:
             acts, costs, _ = self._planner.elites()
-            obs = self._planner.rollout_observations(self._last_start, acts, self._obs_dim)
+            pad = int(getattr(self.env, "obs_pad", 0))     # observation entries the device model does not carry
+            obs = self._planner.rollout_observations(self._last_start, acts, self._obs_dim - pad)
+            if pad:
+                obs = np.concatenate([obs, np.zeros(obs.shape[:-1] + (pad,))], axis=-1)
             rollouts = []
             for a, o in zip(acts.astype(np.float64), obs):
                 step_costs = np.asarray(self.cost_fn(o[:-1], a, o[1:]), dtype=np.float64)

@@ -90,6 +90,7 @@ struct Articulated {
 #endif
   static constexpr int kMinCtasPerSm = NVMAX <= 24 ? ICEM_ART_MIN_CTAS : 2;   // register cap: 85 / 128 per thread
   static constexpr bool kCtaLockstep = ICEM_ART_LOCKSTEP != 0;
+  static constexpr bool kHasHealth = true;      // state_healthy(): usable with ICEM_COST_LOCOMOTION
   static constexpr int kLd = NVMAX + 1;           // row stride of the transposition buffer (odd for NVMAX even)
   struct Params {
     const ArtModel* model;   // device global memory
@@ -137,6 +138,19 @@ struct Articulated {
     __syncwarp();
   }
   __device__ float obs(int i) const { return w[oState + i + M->obs_offset]; }
+  // warp-uniform: every state entry finite, and |obs[i]| < bound for the observation entries i >= first (bound <= 0:
+  // no bound).  The only user is Hopper (mujoco.py:199-203), whose observation carries the velocities clipped to
+  // +-10 (gym hopper_v3._get_obs), so a velocity entry counts as min(|v|, 10).
+  __device__ bool state_healthy(int first, float bound) const {
+    const int nq = M->nq, n = nq + M->nv, lane = lane_id();
+    bool ok = true;
+    for (int i = lane; i < n; i += 32) {
+      const float v = w[oState + i];
+      ok = ok && (v - v == 0.f);
+      if (bound > 0.f && i >= first + M->obs_offset) ok = ok && (i < nq ? fabsf(v) : fminf(fabsf(v), 10.f)) < bound;
+    }
+    return __all_sync(0xffffffffu, ok);
+  }
   __device__ void export_state(float* out) const {
     const int n = M->nq + M->nv;
     for (int i = lane_id(); i < n; i += 32) out[i] = w[oState + i];

@@ -10,6 +10,7 @@ struct DenseTanh {
   static constexpr int kWarpsPerCta = 8;
   static constexpr int kMinCtasPerSm = 2;
   static constexpr bool kCtaLockstep = false;
+  static constexpr bool kHasHealth = false;
   struct Params {
     int obs_dim, act_dim;
     const float* w_obs;   // [obs_dim][obs_dim] row-major (device)
@@ -49,6 +50,7 @@ struct DenseTanh {
     __syncwarp();
   }
   __device__ float obs(int i) const { return cur[i]; }
+  __device__ bool state_healthy(int, float) const { return true; }
   __device__ void step(const float* act) {
     for (int j = lane_id(); j < n; j += 32) {
       float acc = b[j];

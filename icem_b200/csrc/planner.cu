@@ -58,6 +58,7 @@ struct NoDyn {
   static constexpr int kWarpsPerCta = 8;
   static constexpr int kMinCtasPerSm = 2;
   static constexpr bool kCtaLockstep = false;
+  static constexpr bool kHasHealth = false;
   struct Params { int act_dim; };
   __host__ __device__ static int cta_floats(const Params&) { return 0; }
   __host__ __device__ static int warp_floats(const Params&) { return 0; }
@@ -65,6 +66,7 @@ struct NoDyn {
   __device__ void bind(const Params&, const float*, float*) {}
   __device__ void reset(const float*) {}
   __device__ float obs(int) const { return 0.f; }
+  __device__ bool state_healthy(int, float) const { return true; }
   __device__ void step(const float*) {}
   __device__ void export_state(float*) const {}
 };
@@ -232,6 +234,17 @@ static CostConst cost_const(icem_planner* p) {
     // environments/mujoco.py:77-84: (root angle, x velocity) = obs[2], obs[9] (18-dim) or obs[1], obs[8] (17-dim)
     cc.idx_a = p->obs_dim == 18 ? 2 : 1;
     cc.idx_b = p->obs_dim == 18 ? 9 : 8;
+  } else if (p->cfg.cost == ICEM_COST_LOCOMOTION) {
+    // environments/mujoco.py:153-176 (Ant), 196-231 (Hopper)
+    cc.idx_a = p->cfg.cost_z_index;
+    cc.idx_b = 2;                        // Hopper bounds states[..., 2:] (mujoco.py:199)
+    cc.inv_dt = (float)(1.0 / p->cfg.cost_dt);
+    cc.w_ctrl = (float)p->cfg.cost_ctrl_weight;
+    cc.w_unhealthy = (float)p->cfg.cost_unhealthy_weight;
+    cc.z_lo = (float)p->cfg.cost_z_lo;
+    cc.z_hi = (float)p->cfg.cost_z_hi;
+    cc.state_bound = (float)p->cfg.cost_state_bound;
+    cc.z_strict = p->cfg.cost_z_strict;
   } else {
     cc.idx_a = 2;   // environments/mujoco.py:267 root z
     cc.idx_b = 0;
@@ -250,13 +263,13 @@ static typename Articulated<NVMAX>::Params art_params(icem_planner* p) {
   return q;
 }
 
-template <class Dyn, bool kSample, bool kRollout>
-static void launch_rollout(icem_planner* p, const RolloutArgs& a, const typename Dyn::Params& dp, int rows_max) {
+template <class Dyn, bool kSample, bool kRollout, bool kNextObs = false>
+static void launch_rollout_impl(icem_planner* p, const RolloutArgs& a, const typename Dyn::Params& dp, int rows_max) {
   const SamplerConst sc = sampler_const(p);
   const CostConst cc = cost_const(p);
   const int warps = Dyn::kWarpsPerCta;
   const size_t smem = rollout_smem_bytes<Dyn, kSample>(sc, dp, a.stride, warps);
-  auto kern = rollout_kernel<Dyn, kSample, kRollout>;
+  auto kern = rollout_kernel<Dyn, kSample, kRollout, kNextObs>;
   static thread_local size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     ICEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -272,6 +285,18 @@ static void launch_rollout(icem_planner* p, const RolloutArgs& a, const typename
   kern<<<dim3(grid, nprob), warps * 32, smem, p->stream>>>(a, sc, cc, dp);
   ICEM_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+template <class Dyn, bool kSample, bool kRollout>
+static void launch_rollout(icem_planner* p, const RolloutArgs& a, const typename Dyn::Params& dp, int rows_max) {
+  if (p->cfg.cost == ICEM_COST_LOCOMOTION) {
+    // next_obs costs exist for the articulated ground-truth models only, and only where a cost is evaluated
+    if constexpr (kRollout && Dyn::kHasHealth) launch_rollout_impl<Dyn, kSample, true, true>(p, a, dp, rows_max);
+    else if constexpr (!kRollout) launch_rollout_impl<Dyn, kSample, false, false>(p, a, dp, rows_max);
+    else throw Unsupported("the locomotion cost needs an articulated ground-truth model");
+  } else {
+    launch_rollout_impl<Dyn, kSample, kRollout, false>(p, a, dp, rows_max);
+  }
 }
 
 static void launch_mlp(icem_planner* p, const RolloutArgs& a, int rows_max) {
@@ -347,6 +372,7 @@ static void launch_rollout_dyn(icem_planner* p, const RolloutArgs& a, int rows_m
       break;
     case ICEM_DYN_HALFCHEETAH:
     case ICEM_DYN_HUMANOID_STANDUP:
+    case ICEM_DYN_ARTICULATED:
       if (Articulated<12>::fits(p->art.nb, p->art.nv, p->art.nc))
         launch_rollout<Articulated<12>, kSample, kRollout>(p, a, art_params<12>(p), rows_max);
       else if (Articulated<24>::fits(p->art.nb, p->art.nv, p->art.nc))
@@ -516,6 +542,7 @@ static void advance_dyn(icem_planner* p, float* state, const float* action, floa
       break;
     case ICEM_DYN_HALFCHEETAH:
     case ICEM_DYN_HUMANOID_STANDUP:
+    case ICEM_DYN_ARTICULATED:
       if (Articulated<12>::fits(p->art.nb, p->art.nv, p->art.nc))
         launch_advance<Articulated<12>>(p, art_params<12>(p), state, action, next_state, obs_out, obs_dim);
       else if (Articulated<24>::fits(p->art.nb, p->art.nv, p->art.nc))
@@ -655,7 +682,6 @@ int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
   if (cfg->factor_decrease_num <= 0) throw InvalidArg("factor_decrease_num must be positive");
   if (cfg->cost_along_trajectory < 0 || cfg->cost_along_trajectory > 2)
     throw Unsupported("Implement method to compute cost along trajectory");   // abstract_controller.py:88-91
-  if (cfg->cost != ICEM_COST_HALFCHEETAH && cfg->cost != ICEM_COST_HUMANOID_STANDUP) throw Unsupported("unknown cost id");
   int ndev = 0;
   ICEM_CUDA(cudaGetDeviceCount(&ndev));
   if (cfg->device < 0 || cfg->device >= ndev) throw InvalidArg("CUDA device ordinal out of range");
@@ -676,6 +702,12 @@ int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
   const bool rnd = cfg->planner == ICEM_PLANNER_RANDOM;
   p->B = cfg->num_problems > 0 ? cfg->num_problems : 1;
   if (p->B > 4096) throw InvalidArg("num_problems must be <= 4096");
+  if (cfg->cost == ICEM_COST_LOCOMOTION) {
+    if (!(cfg->cost_dt > 0)) throw InvalidArg("cost_dt must be positive for ICEM_COST_LOCOMOTION");
+    if (cfg->dynamics == ICEM_DYN_MLP) throw Unsupported("the locomotion cost is not available for the MLP rollout");
+  } else if (cfg->cost != ICEM_COST_HALFCHEETAH && cfg->cost != ICEM_COST_HUMANOID_STANDUP) {
+    throw Unsupported("unknown cost id");
+  }
   if (p->B > 1) {
     if (cfg->world_size > 1) throw Unsupported("num_problems > 1 needs world_size == 1 (problems are not sharded)");
     if (cfg->dynamics == ICEM_DYN_MLP) throw Unsupported("num_problems > 1 is not available for the MLP rollout");
@@ -758,7 +790,8 @@ int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
   p->ticket.alloc(B);
   build_plan(p.get());
 
-  if (cfg->dynamics == ICEM_DYN_HALFCHEETAH || cfg->dynamics == ICEM_DYN_HUMANOID_STANDUP) {
+  if (cfg->dynamics == ICEM_DYN_HALFCHEETAH || cfg->dynamics == ICEM_DYN_HUMANOID_STANDUP ||
+      cfg->dynamics == ICEM_DYN_ARTICULATED) {
     p->state_dim = 0;   // known once icem_set_articulated_model provides the tables
   } else if (cfg->dynamics == ICEM_DYN_DENSE_TANH || cfg->dynamics == ICEM_DYN_MLP) {
     p->state_dim = 0;   // known once the model is set
@@ -816,7 +849,8 @@ int icem_set_dense_model(icem_planner_t* p, int32_t obs_dim, const float* w_obs,
 int icem_set_articulated_model(icem_planner_t* p, const icem_articulated_model_t* a) {
   ICEM_API_BEGIN
   if (!p || !a) throw InvalidArg("null argument");
-  if (p->cfg.dynamics != ICEM_DYN_HALFCHEETAH && p->cfg.dynamics != ICEM_DYN_HUMANOID_STANDUP)
+  if (p->cfg.dynamics != ICEM_DYN_HALFCHEETAH && p->cfg.dynamics != ICEM_DYN_HUMANOID_STANDUP &&
+      p->cfg.dynamics != ICEM_DYN_ARTICULATED)
     throw InvalidArg("planner was not created with an articulated dynamics id");
   if (a->nb < 1 || a->nb > kArtMaxBodies || a->nv < 1 || a->nv > kArtMaxDofs || a->nc < 0 ||
       a->nc > kArtMaxContacts || a->nq < a->nv || a->nq + a->nv > 64 || a->nsub < 1)

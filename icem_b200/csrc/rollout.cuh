@@ -38,8 +38,13 @@ struct SamplerConst {
 struct CostConst {
   int kind;             // ICEM_COST_*
   int reduce;           // ICEM_REDUCE_*
-  int idx_a, idx_b;     // cheetah: (root angle, x velocity) observation indices; humanoid: (root z, -)
+  int idx_a, idx_b;     // cheetah: (root angle, x velocity) observation indices; humanoid: (root z, -);
+                        // locomotion: (z index, first index of the bounded state entries)
   int penalise_flipping;
+  // ICEM_COST_LOCOMOTION (Hopper / Ant, environments/mujoco.py:153-176, 196-231):
+  //   -(x' - x) / dt + w_unhealthy * unhealthy(obs) + w_ctrl * |a|^2,   x = obs[0] before / after the step
+  float inv_dt, w_ctrl, w_unhealthy, z_lo, z_hi, state_bound;
+  int z_strict;         // Hopper: z_lo < z < z_hi; Ant: z_lo <= z <= z_hi
 };
 
 struct RolloutArgs {
@@ -68,10 +73,17 @@ struct RolloutArgs {
 
 // ---------------------------------------------------------------------------------------------
 // cost of one step on the PRE-action observation
-template <class Dyn>
+template <class Dyn, bool kNextObs>
 __device__ __forceinline__ float step_cost(const CostConst& cc, const Dyn& dyn, const float* act, int d) {
   float a2 = 0.f;
   for (int m = 0; m < d; ++m) a2 = fmaf(act[m], act[m], a2);   // smem broadcast reads, all lanes redundantly
+  if constexpr (kNextObs) {
+    // the part of the locomotion cost known BEFORE the step (the x-velocity term needs next_obs, added by the caller)
+    const float z = dyn.obs(cc.idx_a);
+    const bool z_ok = cc.z_strict ? (z > cc.z_lo && z < cc.z_hi) : (z >= cc.z_lo && z <= cc.z_hi);
+    const bool healthy = z_ok && dyn.state_healthy(cc.idx_b, cc.state_bound);
+    return (healthy ? 0.f : cc.w_unhealthy) + cc.w_ctrl * a2;
+  }
   if (cc.kind == 0) {   // environments/mujoco.py:67-99
     const float ang = dyn.obs(cc.idx_a), vel = dyn.obs(cc.idx_b);
     float c = 0.f;
@@ -160,7 +172,10 @@ __device__ __forceinline__ void fill_normals(float* dst, int count, uint32_t gro
   }
 }
 
-template <class Dyn, bool kSample, bool kRollout>
+// kNextObs: the cost reads next_obs (ICEM_COST_LOCOMOTION).  A template flag, not a runtime branch: the fused kernel's
+// rollout loop is sensitive to anything that changes its register allocation (measured: +2 % per plan step with the
+// branch compiled into the common instantiation).
+template <class Dyn, bool kSample, bool kRollout, bool kNextObs = false>
 __global__ void __launch_bounds__(Dyn::kWarpsPerCta * 32, Dyn::kMinCtasPerSm)
 rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Params dp) {
   extern __shared__ __align__(128) float smem[];
@@ -197,12 +212,13 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
   const int dyn_floats = (Dyn::warp_floats(dp) + 3) & ~3;
   const int scratch_floats = z_floats > dyn_floats ? z_floats : dyn_floats;
   const int ntile = kSample ? 1 : 2;                   // loads are double-buffered
-  const int warp_floats = ntile * tile_floats + scratch_floats + 4;
+  const int warp_floats = ntile * tile_floats + scratch_floats + 8;
   float* w_base = s_warp0 + (size_t)warp * warp_floats;
   float* w_tile = w_base;
   float* w_z = w_tile + ntile * tile_floats;
   float* w_dyn = w_z;
   uint64_t* w_bar = reinterpret_cast<uint64_t*>(w_dyn + scratch_floats);   // 2 x 8 B
+  float* w_stash = reinterpret_cast<float*>(w_bar + 2);                    // 2 floats kept across a step (locomotion cost)
 
   if (kSample && !sc.white)
     for (int i = threadIdx.x; i < h * K2; i += blockDim.x) s_G[(i / K2) * gs + (i % K2)] = sc.G[i];
@@ -350,11 +366,24 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
       for (int t = 0; t < h; ++t) {
         if (Dyn::kCtaLockstep) asm volatile("bar.sync 1, %0;" :: "r"(n_active * 32) : "memory");
         const float* act = tile + t * d;
-        const float c = step_cost(cc, dyn, act, d);
-        if (cc.reduce == 0) total += c;
-        else if (cc.reduce == 1) total = fminf(total, c);
-        else total = c;
-        if (t + 1 < h) dyn.step(act);      // the final predicted state is never scored (F9)
+        const float c = step_cost<Dyn, kNextObs>(cc, dyn, act, d);
+        if constexpr (!kNextObs) {
+          if (cc.reduce == 0) total += c;
+          else if (cc.reduce == 1) total = fminf(total, c);
+          else total = c;
+          if (t + 1 < h) dyn.step(act);      // the final predicted state is never scored (F9)
+        } else {
+          // locomotion costs read next_obs (mujoco.py:168, 222): every step is simulated, and what must survive the
+          // step waits in shared memory, not in registers of the hot loop
+          if (lane == 0) { w_stash[0] = dyn.obs(0); w_stash[1] = c; }
+          dyn.step(act);
+          __syncwarp();
+          const float cf = w_stash[1] - (dyn.obs(0) - w_stash[0]) * cc.inv_dt;
+          __syncwarp();
+          if (cc.reduce == 0) total += cf;
+          else if (cc.reduce == 1) total = fminf(total, cf);
+          else total = cf;
+        }
       }
       if (lane == 0) ICEM_P_COSTS[row] = total;
     }
@@ -377,7 +406,7 @@ inline size_t rollout_smem_bytes(const SamplerConst& sc, const typename Dyn::Par
   const int z_floats = kSample ? ((sc.white ? 0 : d * gs) + 3) & ~3 : 0;
   const int dyn_floats = (Dyn::warp_floats(dp) + 3) & ~3;
   const int ntile = kSample ? 1 : 2;
-  const size_t warp_floats = (size_t)ntile * stride + (z_floats > dyn_floats ? z_floats : dyn_floats) + 4;
+  const size_t warp_floats = (size_t)ntile * stride + (z_floats > dyn_floats ? z_floats : dyn_floats) + 8;
   return (f + warps * warp_floats) * sizeof(float);
 }
 

@@ -152,6 +152,9 @@ _ARTICULATED = {
     # name -> (dynamics id string, nq, nv, act_dim, ctrl bound, obs_dim (reference layout), reset noise)
     "HalfCheetah": dict(dynamics="halfcheetah", nq=9, nv=9, act_dim=6, bound=1.0),
     "HumanoidStandup": dict(dynamics="humanoid_standup", nq=24, nv=23, act_dim=17, bound=0.4),
+    # generic articulated models (ICEM_DYN_ARTICULATED + tables of robots.py)
+    "Hopper": dict(dynamics="articulated", robot="hopper", nq=6, nv=6, act_dim=3, bound=1.0),
+    "Ant": dict(dynamics="articulated", robot="ant", nq=15, nv=14, act_dim=8, bound=1.0),
 }
 
 
@@ -187,11 +190,21 @@ class _DeviceSimEnv(_EnvBase):
     # -- device model --------------------------------------------------------------------------------
     def _simulator(self):
         if self._sim is None:      # created lazily: after fork()s of the host process
+            spec = self.cuda_cost_spec()
             self._sim = Planner(PlannerSettings(
                 horizon=2, num_simulated_trajectories=2, action_low=self.action_space.low,
-                action_high=self.action_space.high, dynamics=self.cuda_dynamics, cost=self.cuda_cost_spec()[0],
+                action_high=self.action_space.high, dynamics=self.cuda_dynamics, cost=spec[0],
+                cost_params=spec[2] if len(spec) > 2 else None, articulated_model=self.cuda_articulated_model(),
+                obs_offset=0 if self.cuda_dynamics == "articulated" else None,
                 obs_dim=self.observation_space.shape[0], device=self.device))
         return self._sim
+
+    def cuda_articulated_model(self):
+        """robots.CompiledModel for dynamics="articulated" (None: the built-in tables of the dynamics id)."""
+        if self.cuda_dynamics != "articulated":
+            return None
+        from .robots import get_model
+        return get_model(self.spec["robot"])
 
     def __getstate__(self):
         d = dict(self.__dict__)
@@ -220,11 +233,12 @@ class _DeviceSimEnv(_EnvBase):
     def step(self, action):
         a = np.clip(np.asarray(action, np.float64), self.action_space.low, self.action_space.high)
         obs = self._obs()
-        cost = float(self.cost_fn(obs, a, None))
         nxt, _, _ = self._simulator().sim_step(self._state, a)
         self._state = nxt
         self._t += self.dt
-        return self._obs(), -cost, False, {}
+        nobs = self._obs()
+        cost = float(self.cost_fn(obs, a, nobs))
+        return nobs, -cost, False, {}
 
     def simulate(self, state, action):
         self.set_GT_state(state)
@@ -305,7 +319,89 @@ class HumanoidStandup(_DeviceSimEnv):
         return self._obs()
 
 
+def locomotion_cost_fn(observation, action, next_obs, *, dt, ctrl_weight, unhealthy_weight, z_index, z_lo, z_hi,
+                       z_strict, state_bound):
+    """environments/mujoco.py:153-176 (Ant) / :196-231 (Hopper), vectorised over leading dims.  Hopper's
+    `np.logical_and(healthy_state, healthy_z, healthy_angle)` passes the angle test as the OUT argument, so the
+    angle range never takes part (kept that way)."""
+    observation, action, next_obs = np.asarray(observation), np.asarray(action), np.asarray(next_obs)
+    z = observation[..., z_index]
+    healthy = (z_lo < z) * (z < z_hi) if z_strict else (z_lo <= z) * (z <= z_hi)
+    if state_bound > 0:
+        st = observation[..., 2:]
+        healthy = healthy * np.all(np.logical_and(-state_bound < st, st < state_bound), axis=-1)
+    unhealthy = 1 - np.isfinite(observation).all(axis=-1) * healthy
+    x_velocity = (next_obs[..., 0] - observation[..., 0]) / dt
+    return -x_velocity + unhealthy_weight * unhealthy + ctrl_weight * np.sum(np.square(action), axis=-1)
+
+
+class _LocomotionEnv(_DeviceSimEnv):
+    """Hopper / Ant stand-ins: obs = qpos ++ qvel (+ zeros where the reference appends contact forces)."""
+    cost_params = None
+    obs_pad = 0
+
+    def __init__(self, *, name, device=0, **kwargs):
+        spec = _ARTICULATED[self.kind]
+        n = spec["nq"] + spec["nv"] + self.obs_pad
+        self.observation_space = Box(-np.inf * np.ones(n), np.inf * np.ones(n))
+        super().__init__(name=name, device=device, **kwargs)
+        self.store_init_arguments(locals())
+
+    def _qpos0(self):
+        from .robots import get_model
+        return get_model(self.spec["robot"]).qpos0.copy()
+
+    def cuda_cost_spec(self):
+        return "locomotion", False, dict(self.cost_params, dt=self.dt)
+
+    def cost_fn(self, observation, action, next_obs):
+        return locomotion_cost_fn(observation, action, next_obs, dt=self.dt, **self.cost_params)
+
+    def _obs(self):
+        return np.concatenate([self._state, np.zeros(self.obs_pad)])
+
+
+class Hopper(_LocomotionEnv):
+    """Stand-in for environments/mujoco.py:179-231 (gym Hopper-v3 with exclude_current_positions_from_observation
+    false: obs = qpos(6) ++ clip(qvel(6), -10, 10) = 12, like gym's hopper_v3._get_obs)."""
+    kind = "Hopper"
+    dt = 0.008
+    cost_params = dict(ctrl_weight=1e-3, unhealthy_weight=200.0, z_index=1, z_lo=0.7, z_hi=float("inf"), z_strict=True,
+                       state_bound=100.0)
+
+    def _obs(self):
+        return np.concatenate([self._state[:6], np.clip(self._state[6:], -10.0, 10.0)])
+
+    def reset(self):
+        c = 5e-3            # gym hopper_v3 reset_noise_scale
+        self._state = np.concatenate([self._qpos0() + self._rs.uniform(-c, c, 6), self._rs.uniform(-c, c, 6)])
+        self._t = 0.0
+        return self._obs()
+
+
+class Ant(_LocomotionEnv):
+    """Stand-in for environments/mujoco.py:134-176 (gym Ant-v3, 113-wide observation: qpos(15) ++ qvel(14) ++ 84
+    clipped contact forces; the cost reads obs[0], obs[2] and finiteness only, so the force block is zeros)."""
+    kind = "Ant"
+    dt = 0.05
+    obs_pad = 84
+    cost_params = dict(ctrl_weight=0.5, unhealthy_weight=100.0, z_index=2, z_lo=0.2, z_hi=1.0, z_strict=False,
+                       state_bound=0.0)
+
+    def reset(self):
+        c = 0.1             # gym ant_v3 reset_noise_scale
+        qpos = self._qpos0() + self._rs.uniform(-c, c, 15)
+        qpos[3:7] /= np.linalg.norm(qpos[3:7])
+        self._state = np.concatenate([qpos, c * self._rs.randn(14)])
+        self._t = 0.0
+        return self._obs()
+
+
 def make_env(kind, device=0, **kwargs):
+    if kind == "Hopper":
+        return Hopper(name=kind, device=device, **kwargs)
+    if kind == "Ant":
+        return Ant(name=kind, device=device, **kwargs)
     if kind == "HalfCheetah":
         return HalfCheetahMaybeWithPosition(name=kind, device=device, **kwargs)
     if kind == "HumanoidStandup":

@@ -63,6 +63,8 @@ def register(override_mpc_icem=False, standin_envs=True):
         mod = types.ModuleType("environments.mujoco")
         mod.HalfCheetahMaybeWithPosition = envs.HalfCheetahMaybeWithPosition
         mod.HumanoidStandup = envs.HumanoidStandup
+        mod.Hopper = envs.Hopper
+        mod.Ant = envs.Ant
         mod.__doc__ = "device-simulated stand-ins registered by icem_b200.launch"
         sys.modules["environments.mujoco"] = mod
 

@@ -102,7 +102,9 @@ class CudaGroundTruthModel(_GTBase):
         self.is_trained = True
 
     def cuda_spec(self):
-        return dict(dynamics=self.env.cuda_dynamics, dense=None, obs_dim=self.env.observation_space.shape[0])
+        model = self.env.cuda_articulated_model() if hasattr(self.env, "cuda_articulated_model") else None
+        return dict(dynamics=self.env.cuda_dynamics, dense=None, obs_dim=self.env.observation_space.shape[0],
+                    articulated_model=model)
 
     def start_state(self, observation, model_state):
         if model_state is None:

@@ -41,11 +41,23 @@ class PlannerSettings:
     planner: str = "icem"                # "icem" (MpcICem) | "cem_std" (MpcCemStd) | "random" (MpcRandom)
     action_change_frequency: int = 0     # random only (controllers/mpc.py:91)
     num_problems: int = 1                # independent MPC problems batched in one handle (plan_batch)
+    cost_params: Optional[dict] = None   # cost="locomotion": dt, ctrl_weight, unhealthy_weight, z_lo, z_hi, state_bound,
+                                         # z_index, z_strict (environments/mujoco.py:153-176, 196-231)
     execute_best_elite: bool = True      # cem_std only (controllers/mpc.py:237-240)
     shift_means: bool = True             # cem_std only (controllers/mpc.py:243-248)
     bounds_like_levine: bool = False     # cem_std only (controllers/mpc.py:290-301)
     articulated_model: object = None     # robots.CompiledModel; None = the built-in tables for `dynamics`
     obs_offset: Optional[int] = None
+
+
+def _cost_fields(cp):
+    cp = cp or {}
+    inf = 3.0e38          # float32-representable stand-in for an open range end
+    return dict(cost_z_index=int(cp.get("z_index", 0)), cost_z_strict=int(bool(cp.get("z_strict", False))),
+                cost_dt=float(cp.get("dt", 0.0)), cost_ctrl_weight=float(cp.get("ctrl_weight", 0.0)),
+                cost_unhealthy_weight=float(cp.get("unhealthy_weight", 0.0)),
+                cost_z_lo=float(max(cp.get("z_lo", -inf), -inf)), cost_z_hi=float(min(cp.get("z_hi", inf), inf)),
+                cost_state_bound=float(cp.get("state_bound", 0.0)))
 
 
 class Planner:
@@ -74,6 +86,7 @@ class Planner:
             execute_best_elite=int(bool(s.execute_best_elite)), shift_means=int(bool(s.shift_means)),
             bounds_like_levine=int(bool(s.bounds_like_levine)),
             action_change_frequency=int(s.action_change_frequency), num_problems=int(s.num_problems),
+            **_cost_fields(s.cost_params),
             factor_decrease_num=float(s.factor_decrease_num), alpha=float(s.alpha), init_std=float(s.init_std),
             fraction_elites_reused=float(s.fraction_elites_reused), noise_beta=float(s.noise_beta),
             seed=int(s.seed) & (2 ** 64 - 1), action_low=fptr(self._low), action_high=fptr(self._high))
@@ -82,8 +95,10 @@ class Planner:
         self.k = lib.icem_num_elites(self._h)
         self.iters = int(s.opt_iterations)
         self.K = self.h // 2 + 1
-        if s.dynamics in ("halfcheetah", "humanoid_standup") and s.articulated_model is not False:
+        if s.dynamics in ("halfcheetah", "humanoid_standup", "articulated") and s.articulated_model is not False:
             from . import robots
+            if s.dynamics == "articulated" and s.articulated_model is None:
+                raise ValueError('dynamics="articulated" needs settings.articulated_model (robots.get_model(...))')
             model = s.articulated_model if s.articulated_model is not None else robots.get_model(s.dynamics)
             obs_offset = s.obs_offset
             if obs_offset is None:     # HalfCheetah's 17-wide observation drops qpos[0] (environments/mujoco.py:80-82)

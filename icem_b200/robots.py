@@ -194,7 +194,63 @@ def humanoid_standup() -> RobotDescription:
                             root_qpos0=(0.0, 0.0, 0.105, math.sqrt(0.5), 0.0, -math.sqrt(0.5), 0.0))
 
 
-ROBOTS = {"halfcheetah": half_cheetah, "humanoid_standup": humanoid_standup}
+def hopper() -> RobotDescription:
+    """gym `hopper.xml` (Hopper-v3: timestep 0.002, frame_skip 4), planar: slide x, slide z, hinge y root, then
+    thigh / leg / foot hinges about -y.  The XML is written in global coordinates (torso at z = 1.25); here every body
+    frame sits at its joint and the root slide carries the height, so qpos[1] is the absolute torso height the
+    reference's `unhealthy_states` reads (environments/mujoco.py:196-212)."""
+    d2r = math.pi / 180.0
+
+    def hinge(name, pos, rng):
+        return Joint(name, "hinge", axis=(0, -1, 0), pos=pos, range=(rng[0] * d2r, rng[1] * d2r), damping=1.0,
+                     armature=1.0)
+
+    bodies = [
+        Body("torso", -1, (0, 0, 0),
+             joints=[Joint("rootx", "slide", axis=(1, 0, 0)), Joint("rootz", "slide", axis=(0, 0, 1)),
+                     Joint("rooty", "hinge", axis=(0, 1, 0))],
+             geoms=[Geom("torso", "capsule", 0.05, fromto=(0, 0, 0.2, 0, 0, -0.2))]),
+        Body("thigh", 0, (0, 0, -0.2), joints=[hinge("thigh_joint", (0, 0, 0), (-150, 0))],
+             geoms=[Geom("thigh", "capsule", 0.05, fromto=(0, 0, 0, 0, 0, -0.45))]),
+        Body("leg", 1, (0, 0, -0.7), joints=[hinge("leg_joint", (0, 0, 0.25), (-150, 0))],
+             geoms=[Geom("leg", "capsule", 0.04, fromto=(0, 0, 0.25, 0, 0, -0.25))]),
+        Body("foot", 2, (0.065, 0, -0.25), joints=[hinge("foot_joint", (-0.065, 0, 0), (-45, 45))],
+             geoms=[Geom("foot", "capsule", 0.06, fromto=(-0.195, 0, 0, 0.195, 0, 0))]),
+    ]
+    acts = [Actuator("thigh_joint", 200), Actuator("leg_joint", 200), Actuator("foot_joint", 200)]
+    return RobotDescription("hopper", bodies, acts, timestep=0.002, frame_skip=4, ctrl_limit=1.0, friction=0.9,
+                            contact_stiffness=2.0e4, contact_damping=1.5, contact_damping_max=120.0,
+                            friction_viscous=120.0, root_qpos0=(0.0, 1.25, 0.0))
+
+
+def ant() -> RobotDescription:
+    """gym `ant.xml` (Ant-v3: timestep 0.01, frame_skip 5): free root (sphere torso) and four two-joint legs (hip about
+    z, ankle about a horizontal axis); density 5, armature 1, damping 1, gear 150.  The XML's jointless leg-root
+    bodies are merged into the torso (their capsules become torso geoms)."""
+    d2r = math.pi / 180.0
+
+    def hinge(name, axis, rng):
+        return Joint(name, "hinge", axis=axis, range=(rng[0] * d2r, rng[1] * d2r), damping=1.0, armature=1.0)
+
+    legs = [  # name, (sx, sy), ankle axis, ankle range
+        ("1", (1, 1), (-1, 1, 0), (30, 70)), ("2", (-1, 1), (1, 1, 0), (-70, -30)),
+        ("3", (-1, -1), (-1, 1, 0), (-70, -30)), ("4", (1, -1), (1, 1, 0), (30, 70))]
+    torso_geoms = [Geom("torso", "sphere", 0.25)]
+    bodies = [Body("torso", -1, (0, 0, 0), joints=[Joint("root", "free")], geoms=torso_geoms)]
+    for n, (sx, sy), axis, rng in legs:
+        torso_geoms.append(Geom(f"aux_{n}", "capsule", 0.08, fromto=(0, 0, 0, 0.2 * sx, 0.2 * sy, 0)))
+        hip = len(bodies)
+        bodies.append(Body(f"aux_{n}", 0, (0.2 * sx, 0.2 * sy, 0), joints=[hinge(f"hip_{n}", (0, 0, 1), (-30, 30))],
+                           geoms=[Geom(f"leg_{n}", "capsule", 0.08, fromto=(0, 0, 0, 0.2 * sx, 0.2 * sy, 0))]))
+        bodies.append(Body(f"ankle_{n}", hip, (0.2 * sx, 0.2 * sy, 0), joints=[hinge(f"ankle_{n}", axis, rng)],
+                           geoms=[Geom(f"ankle_{n}", "capsule", 0.08, fromto=(0, 0, 0, 0.4 * sx, 0.4 * sy, 0))]))
+    acts = [Actuator(j, 150) for j in ("hip_4", "ankle_4", "hip_1", "ankle_1", "hip_2", "ankle_2", "hip_3", "ankle_3")]
+    return RobotDescription("ant", bodies, acts, timestep=0.01, frame_skip=5, ctrl_limit=1.0, density=5.0,
+                            friction=1.0, contact_stiffness=1.0e3, contact_damping=1.5, contact_damping_max=20.0,
+                            friction_viscous=20.0, root_qpos0=(0.0, 0.0, 0.75, 1.0, 0.0, 0.0, 0.0))
+
+
+ROBOTS = {"halfcheetah": half_cheetah, "humanoid_standup": humanoid_standup, "hopper": hopper, "ant": ant}
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define ICEM_ABI_VERSION 4
+#define ICEM_ABI_VERSION 5
 
 /* status codes */
 enum { ICEM_OK = 0, ICEM_ERR_INVALID = 1, ICEM_ERR_CUDA = 2, ICEM_ERR_STATE = 3, ICEM_ERR_UNSUPPORTED = 4,
@@ -34,13 +34,17 @@ enum {
                                     (models/abstract_models.py:17-53 with a dense `predict`) */
   ICEM_DYN_HALFCHEETAH = 1,      /* ground-truth planar articulated body (stands in for gym HalfCheetah-v3) */
   ICEM_DYN_HUMANOID_STANDUP = 2, /* ground-truth 3-D articulated body (stands in for gym HumanoidStandup-v2) */
-  ICEM_DYN_MLP = 3               /* dense MLP forward model (tensor-core rollout) */
+  ICEM_DYN_MLP = 3,              /* dense MLP forward model (tensor-core rollout) */
+  ICEM_DYN_ARTICULATED = 4       /* any articulated body given through icem_set_articulated_model (Hopper, Ant, ...) */
 };
 
 /* per-step cost functions (env.cost_fn, controllers/abstract_controller.py:70,78-80) */
 enum {
   ICEM_COST_HALFCHEETAH = 0,     /* environments/mujoco.py:67-99  */
-  ICEM_COST_HUMANOID_STANDUP = 1 /* environments/mujoco.py:259-277 */
+  ICEM_COST_HUMANOID_STANDUP = 1,/* environments/mujoco.py:259-277 */
+  ICEM_COST_LOCOMOTION = 2       /* Ant (environments/mujoco.py:153-176) and Hopper (:196-231):
+                                    -(next_obs[0] - obs[0]) / dt + w_unhealthy * unhealthy(obs) + w_ctrl * |a|^2,
+                                    parameters in icem_config_t.cost_*; reads next_obs, so all h steps are simulated */
 };
 
 /* action sampler / planner family */
@@ -87,11 +91,18 @@ typedef struct icem_config {
                                      settings and model, own start state / mean / std / elites each, Philox seed + i;
                                      every kernel of a plan step covers all problems (grid.y = problem).  See
                                      icem_plan_batch. */
+  int32_t cost_z_index;           /* LOCOMOTION: observation index of the height (Hopper 1, Ant 2) */
+  int32_t cost_z_strict;          /* LOCOMOTION: 1 = z_lo < z < z_hi (Hopper, mujoco.py:205), 0 = z_lo <= z <= z_hi (Ant, :149) */
   double factor_decrease_num;     /* gamma */
   double alpha;
   double init_std;
   double fraction_elites_reused;
   double noise_beta;
+  double cost_dt;                 /* LOCOMOTION: env.dt = timestep * frame_skip */
+  double cost_ctrl_weight;        /* LOCOMOTION: _ctrl_cost_weight (Hopper 1e-3, Ant 0.5) */
+  double cost_unhealthy_weight;   /* LOCOMOTION: 200 (Hopper, mujoco.py:227) / 100 (Ant, :171) */
+  double cost_z_lo, cost_z_hi;    /* LOCOMOTION: _healthy_z_range */
+  double cost_state_bound;        /* LOCOMOTION: Hopper |states[..., 2:]| < bound (_healthy_state_range); <= 0: none */
   uint64_t seed;                  /* Philox key (production noise) */
   const float* action_low;        /* [d] env.action_space.low  (float32 like gym.spaces.Box) */
   const float* action_high;       /* [d] */

@@ -270,17 +270,20 @@ class ArticulatedModel:
     def step(self, obs, act):
         raise NotImplementedError("articulated models step on the full state (step_state), not the observation")
 
-    def rollout(self, start_state, actions):
-        """PRE-action observation of every step: [p,h,obs_dim]."""
+    def rollout(self, start_state, actions, with_final=False):
+        """PRE-action observation of every step: [p,h,obs_dim]; `with_final` appends the observation
+        after the last action ([p,h+1,obs_dim]) for costs that read next_obs (Hopper / Ant)."""
         p, h, _ = actions.shape
-        out = np.empty((p, h, self.obs_dim))
+        out = np.empty((p, h + (1 if with_final else 0), self.obs_dim))
         for lo in range(0, p, self.max_chunk):
             hi = min(p, lo + self.max_chunk)
             st = np.broadcast_to(np.asarray(start_state, np.float64), (hi - lo, self.state_dim)).copy()
             for t in range(h):
                 out[lo:hi, t] = st[:, self.obs_skip:]
-                if t + 1 < h:
+                if t + 1 < h or with_final:
                     st = self.step_state(st, np.asarray(actions[lo:hi, t], np.float64))
+            if with_final:
+                out[lo:hi, h] = st[:, self.obs_skip:]
         return out
 
     # ---- diagnostics for the physics tests ---------------------------------------------------------------------
@@ -296,6 +299,6 @@ class ArticulatedModel:
 
 
 def make_model(name, obs_skip=None) -> ArticulatedModel:
-    if obs_skip is None:
+    if obs_skip is None:      # HalfCheetah's 17-wide observation drops qpos[0]; every other env keeps the full state
         obs_skip = 1 if name == "halfcheetah" else 0
     return ArticulatedModel(get_model(name), obs_skip=obs_skip)

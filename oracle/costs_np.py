@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY.  Citations relative to /root/reference/icem/.
 Signature: cost(observations[..., obs_dim], actions[..., d]) -> [...]; `next_obs` is ignored by
-both reference functions, so it is not an argument here.
+the HalfCheetah / HumanoidStandup functions, so it is not an argument there; the Hopper / Ant costs
+ read it and take it explicitly.
 """
 import math
 
@@ -29,3 +30,29 @@ def halfcheetah_cost(obs, act, penalise_flipping=True):
 def humanoid_standup_cost(obs, act):
     """environments/mujoco.py:259-277 (obs[2] = root z because _get_obs keeps the full qpos, :241-252)."""
     return -obs[..., 2] + 0.1 * np.square(act).sum(axis=-1)
+
+
+HOPPER = dict(dt=0.008, ctrl_weight=1e-3, healthy_state_range=(-100.0, 100.0), healthy_z_range=(0.7, float("inf")),
+              healthy_angle_range=(-0.2, 0.2))       # gym Hopper-v3 defaults (frame_skip 4 x timestep 0.002)
+ANT = dict(dt=0.05, ctrl_weight=0.5, healthy_z_range=(0.2, 1.0))       # gym Ant-v3 defaults
+
+
+def hopper_cost(obs, act, next_obs, p=HOPPER):
+    """environments/mujoco.py:196-231.  Line 208 is `np.logical_and(healthy_state, healthy_z, healthy_angle)`:
+    the third positional argument of a ufunc is `out`, so the angle test is overwritten, not combined."""
+    z, state = obs[..., 1], obs[..., 2:]
+    lo, hi = p["healthy_state_range"]
+    healthy_state = np.all(np.logical_and(lo < state, state < hi), axis=-1)
+    healthy_z = (p["healthy_z_range"][0] < z) * (z < p["healthy_z_range"][1])
+    is_healthy = np.logical_and(healthy_state, healthy_z)
+    unhealthy = 1 - np.isfinite(obs).all(axis=-1) * is_healthy
+    x_velocity = (next_obs[..., 0] - obs[..., 0]) / p["dt"]
+    return -x_velocity + 200 * unhealthy + p["ctrl_weight"] * np.sum(np.square(act), axis=-1)
+
+
+def ant_cost(obs, act, next_obs, p=ANT):
+    """environments/mujoco.py:146-176."""
+    lo, hi = p["healthy_z_range"]
+    unhealthy = 1 - np.isfinite(obs).all(axis=-1) * (lo <= obs[..., 2]) * (obs[..., 2] <= hi)
+    x_velocity = (next_obs[..., 0] - obs[..., 0]) / p["dt"]
+    return -x_velocity + 100 * unhealthy + p["ctrl_weight"] * np.sum(np.square(act), axis=-1)

@@ -23,7 +23,7 @@ def case(name, n=6, h=12, seed=5):
 
 
 def main():
-    for name in ("halfcheetah", "humanoid_standup"):
+    for name in ("halfcheetah", "humanoid_standup", "hopper", "ant"):
         mod, start, actions = case(name)
         obs = mod.rollout(start, actions)
         np.savez_compressed(os.path.join(OUT, f"articulated_{name}.npz"), start=start, actions=actions,

@@ -1,0 +1,57 @@
+"""tests/golden/costs_locomotion.npz: the reference's OWN Hopper / Ant cost functions
+(/root/reference/icem/environments/mujoco.py:146-176, 196-231) evaluated on seeded inputs.  TEST INFRASTRUCTURE.
+
+    python -m oracle.make_golden_costs        # this container only (needs /root/reference)
+
+The env classes cannot be constructed here (gym / mujoco-py absent), so `cost_fn`, `unhealthy_states` and
+`are_states_unhealthy` are called unbound on a stub carrying the gym-v3 default attributes they read."""
+import os
+import types
+
+import numpy as np
+
+from oracle import costs_np, ref_loader
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def inputs():
+    rs = np.random.RandomState(7)
+    ho = rs.randn(60, 9, 12)
+    ho[..., 1] += 1.0                       # heights around the 0.7 threshold
+    ho[3, 2, 5] = 150.0                     # outside the +-100 state range
+    ho[4, 1, 7] = np.nan
+    ho[5, :, 2] = 0.5                       # angle outside +-0.2: must NOT matter (logical_and out= quirk)
+    hn = ho + 0.01 * rs.randn(*ho.shape)
+    ha = rs.uniform(-1, 1, (60, 9, 3))
+    ao = rs.randn(40, 5, 113)
+    ao[..., 2] = rs.uniform(0.0, 1.2, (40, 5))
+    ao[0, 0, 2], ao[0, 1, 2] = 0.2, 1.0     # the closed interval ends are healthy
+    ao[2, 1, 50] = np.inf
+    an = ao + 0.01 * rs.randn(*ao.shape)
+    aa = rs.uniform(-1, 1, (40, 5, 8))
+    return (ho, ha, hn), (ao, aa, an)
+
+
+def reference_costs():
+    ref_loader.load_reference()
+    import environments.mujoco as rm
+    hp, ap = costs_np.HOPPER, costs_np.ANT
+    hs = types.SimpleNamespace(dt=hp["dt"], _ctrl_cost_weight=hp["ctrl_weight"],
+                               _healthy_state_range=hp["healthy_state_range"], _healthy_z_range=hp["healthy_z_range"],
+                               _healthy_angle_range=hp["healthy_angle_range"])
+    hs.unhealthy_states = lambda st: rm.Hopper.unhealthy_states(hs, st)
+    as_ = types.SimpleNamespace(dt=ap["dt"], _ctrl_cost_weight=ap["ctrl_weight"], _healthy_z_range=ap["healthy_z_range"])
+    as_.are_states_unhealthy = lambda st: rm.Ant.are_states_unhealthy(as_, st)
+    (ho, ha, hn), (ao, aa, an) = inputs()
+    return rm.Hopper.cost_fn(hs, ho.copy(), ha, hn), rm.Ant.cost_fn(as_, ao.copy(), aa, an)
+
+
+def main():
+    h, a = reference_costs()
+    np.savez_compressed(os.path.join(OUT, "costs_locomotion.npz"), hopper=h, ant=a)
+    print("hopper", h.shape, float(np.nanmean(h > 100)), "ant", a.shape, float(np.mean(a > 50)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,54 @@
+"""CPU tests of the Hopper / Ant additions: the NumPy restatement of their cost functions against the
+reference's own code (fixture tests/golden/costs_locomotion.npz, re-checked live when /root/reference exists), the
+product-side cost function the stand-in envs use, and the rollout `with_final` path the costs need."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import costs_np
+from oracle.make_golden_costs import inputs
+
+
+def test_oracle_costs_match_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "costs_locomotion.npz"))
+    (ho, ha, hn), (ao, aa, an) = inputs()
+    np.testing.assert_array_equal(costs_np.hopper_cost(ho, ha, hn), g["hopper"])
+    np.testing.assert_array_equal(costs_np.ant_cost(ao, aa, an), g["ant"])
+    assert np.isnan(g["hopper"]).sum() == 0           # a NaN observation is unhealthy, not NaN-cost... unless x is NaN
+    assert 0.2 < np.mean(g["hopper"] > 100) < 0.8 and 0.1 < np.mean(g["ant"] > 50) < 0.6
+    # Hopper quirk (mujoco.py:208): an angle outside +-0.2 alone does not make a state unhealthy
+    assert np.all(g["hopper"][5][ho[5, :, 1] > 0.7] < 100)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/icem"), reason="needs the reference sources")
+def test_oracle_costs_match_reference_live():
+    from oracle.make_golden_costs import reference_costs
+    h, a = reference_costs()
+    (ho, ha, hn), (ao, aa, an) = inputs()
+    np.testing.assert_array_equal(costs_np.hopper_cost(ho, ha, hn), h)
+    np.testing.assert_array_equal(costs_np.ant_cost(ao, aa, an), a)
+
+
+def test_env_cost_function_equals_the_oracle():
+    """icem_b200.envs.locomotion_cost_fn (what the stand-in envs and `elite_samples` evaluate) == the restatement."""
+    from icem_b200 import envs
+    (ho, ha, hn), (ao, aa, an) = inputs()
+    got = envs.locomotion_cost_fn(ho, ha, hn, dt=envs.Hopper.dt, **envs.Hopper.cost_params)
+    np.testing.assert_array_equal(got, costs_np.hopper_cost(ho, ha, hn))
+    got = envs.locomotion_cost_fn(ao, aa, an, dt=envs.Ant.dt, **envs.Ant.cost_params)
+    np.testing.assert_array_equal(got, costs_np.ant_cost(ao, aa, an))
+
+
+def test_rollout_with_final_observation():
+    from oracle.articulated_np import make_model
+    mod = make_model("hopper")
+    m = mod.m
+    rs = np.random.RandomState(0)
+    start = np.concatenate([m.qpos0, 0.01 * rs.randn(m.nv)])
+    acts = rs.uniform(-1, 1, (3, 5, m.nu))
+    a, b = mod.rollout(start, acts), mod.rollout(start, acts, with_final=True)
+    assert b.shape == (3, 6, 12)
+    np.testing.assert_array_equal(a, b[:, :5])
+    last = mod.step_state(np.concatenate([b[:, 4]], axis=0), acts[:, 4])
+    np.testing.assert_allclose(b[:, 5], last, atol=1e-12)
