@@ -48,8 +48,13 @@ def test_single_transition_matches_oracle(hidden):
     p.close()
 
 
+@pytest.mark.parametrize("two_cta", [False, True])
 @pytest.mark.parametrize("hidden,n", [(256, 1000), (128, 300), (64, 129)])
-def test_tensor_core_rollout_costs_match_oracle(hidden, n):
+def test_tensor_core_rollout_costs_match_oracle(hidden, n, two_cta, monkeypatch):
+    """Both tensor-core schedules: one 128-row tile per SM (mlp_rollout.cuh, default) and the CTA-pair kernel with
+    `tcgen05 cta_group::2` and two tiles per SM in flight (mlp_rollout_2cta.cuh, ICEM_B200_MLP_2CTA=1)."""
+    if two_cta:
+        monkeypatch.setenv("ICEM_B200_MLP_2CTA", "1")
     p, mod = _planner(hidden)
     rs = np.random.RandomState(1)
     acts = rs.uniform(-1, 1, (n, 12, 6)).astype(np.float32)
