@@ -1,3 +1,9 @@
-python -m pytest tests/test_gpu_batched.py tests/test_gpu_random.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2
-for i in 1 2; do python bench.py --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('bench', d['value'], d['ms_per_step'], d['roofline']['kernel_ms_avg'])"; done
+for i in 1 2; do
+for v in "" _ab; do
+ICEM_B200_LIB=icem_b200/lib/libicem_b200$v.so python bench.py --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('bench$v', d['value'], d['ms_per_step'])"
+done; done
+ICEM_B200_LIB=icem_b200/lib/libicem_b200_ab.so python bench.py --workload halfcheetah_gt_n4096 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('cheetah_ab', d['value'], d['ms_per_step'])"
+python bench.py --workload halfcheetah_gt_n4096 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('cheetah', d['value'], d['ms_per_step'])"
