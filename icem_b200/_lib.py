@@ -7,7 +7,7 @@ import numpy as np
 LIB_PATH = os.environ.get("ICEM_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
                                                            "libicem_b200.so")
 
-ICEM_ABI_VERSION = 5
+ICEM_ABI_VERSION = 6
 DYN = {"dense_tanh": 0, "halfcheetah": 1, "humanoid_standup": 2, "mlp": 3, "articulated": 4}
 COST = {"halfcheetah": 0, "humanoid_standup": 1, "locomotion": 2}
 REDUCE = {"sum": 0, "best": 1, "final": 2}
@@ -26,10 +26,12 @@ class IcemConfig(C.Structure):
         ("rank", C.c_int32), ("planner", C.c_int32), ("execute_best_elite", C.c_int32), ("shift_means", C.c_int32),
         ("bounds_like_levine", C.c_int32), ("action_change_frequency", C.c_int32),
         ("num_problems", C.c_int32), ("cost_z_index", C.c_int32), ("cost_z_strict", C.c_int32),
+        ("cost_velocity_index1", C.c_int32), ("cost_reserved", C.c_int32),
         ("factor_decrease_num", C.c_double), ("alpha", C.c_double), ("init_std", C.c_double),
         ("fraction_elites_reused", C.c_double), ("noise_beta", C.c_double),
         ("cost_dt", C.c_double), ("cost_ctrl_weight", C.c_double), ("cost_unhealthy_weight", C.c_double),
         ("cost_z_lo", C.c_double), ("cost_z_hi", C.c_double), ("cost_state_bound", C.c_double),
+        ("cost_forward_weight", C.c_double),
         ("seed", C.c_uint64),
         ("action_low", C.POINTER(C.c_float)), ("action_high", C.POINTER(C.c_float)),
     ]

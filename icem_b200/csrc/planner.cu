@@ -242,7 +242,11 @@ static CostConst cost_const(icem_planner* p) {
     // environments/mujoco.py:153-176 (Ant), 196-231 (Hopper)
     cc.idx_a = p->cfg.cost_z_index;
     cc.idx_b = 2;                        // Hopper bounds states[..., 2:] (mujoco.py:199)
-    cc.inv_dt = (float)(1.0 / p->cfg.cost_dt);
+    const double w_fwd = p->cfg.cost_forward_weight != 0.0 ? p->cfg.cost_forward_weight : 1.0;
+    cc.vel_index = p->cfg.cost_velocity_index1 - 1;
+    cc.w_fwd = (float)w_fwd;
+    // finite-difference velocity: the post-step term is -(x' - x) * w_fwd / dt; with an observed velocity it vanishes
+    cc.inv_dt = cc.vel_index >= 0 ? 0.f : (float)(w_fwd / p->cfg.cost_dt);
     cc.w_ctrl = (float)p->cfg.cost_ctrl_weight;
     cc.w_unhealthy = (float)p->cfg.cost_unhealthy_weight;
     cc.z_lo = (float)p->cfg.cost_z_lo;

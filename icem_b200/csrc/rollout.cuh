@@ -45,6 +45,8 @@ struct CostConst {
   //   -(x' - x) / dt + w_unhealthy * unhealthy(obs) + w_ctrl * |a|^2,   x = obs[0] before / after the step
   float inv_dt, w_ctrl, w_unhealthy, z_lo, z_hi, state_bound;
   int z_strict;         // Hopper: z_lo < z < z_hi; Ant: z_lo <= z <= z_hi
+  int vel_index;        // >= 0: x velocity = obs[vel_index] (Humanoid, mujoco.py:333; inv_dt is 0 then); -1: finite difference
+  float w_fwd;          // weight of the velocity term
 };
 
 struct RolloutArgs {
@@ -82,7 +84,8 @@ __device__ __forceinline__ float step_cost(const CostConst& cc, const Dyn& dyn, 
     const float z = dyn.obs(cc.idx_a);
     const bool z_ok = cc.z_strict ? (z > cc.z_lo && z < cc.z_hi) : (z >= cc.z_lo && z <= cc.z_hi);
     const bool healthy = z_ok && dyn.state_healthy(cc.idx_b, cc.state_bound);
-    return (healthy ? 0.f : cc.w_unhealthy) + cc.w_ctrl * a2;
+    const float vel = cc.vel_index >= 0 ? cc.w_fwd * dyn.obs(cc.vel_index) : 0.f;
+    return (healthy ? 0.f : cc.w_unhealthy) + cc.w_ctrl * a2 - vel;
   }
   if (cc.kind == 0) {   // environments/mujoco.py:67-99
     const float ang = dyn.obs(cc.idx_a), vel = dyn.obs(cc.idx_b);

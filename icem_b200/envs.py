@@ -155,6 +155,7 @@ _ARTICULATED = {
     # generic articulated models (ICEM_DYN_ARTICULATED + tables of robots.py)
     "Hopper": dict(dynamics="articulated", robot="hopper", nq=6, nv=6, act_dim=3, bound=1.0),
     "Ant": dict(dynamics="articulated", robot="ant", nq=15, nv=14, act_dim=8, bound=1.0),
+    "Humanoid": dict(dynamics="articulated", robot="humanoid", nq=24, nv=23, act_dim=17, bound=0.4),
 }
 
 
@@ -320,8 +321,9 @@ class HumanoidStandup(_DeviceSimEnv):
 
 
 def locomotion_cost_fn(observation, action, next_obs, *, dt, ctrl_weight, unhealthy_weight, z_index, z_lo, z_hi,
-                       z_strict, state_bound):
-    """environments/mujoco.py:153-176 (Ant) / :196-231 (Hopper), vectorised over leading dims.  Hopper's
+                       z_strict, state_bound, velocity_index=-1, forward_weight=1.0):
+    """environments/mujoco.py:153-176 (Ant) / :196-231 (Hopper) / :314-343 (Humanoid: the x velocity is read from the
+    observation instead of differenced), vectorised over leading dims.  Hopper's
     `np.logical_and(healthy_state, healthy_z, healthy_angle)` passes the angle test as the OUT argument, so the
     angle range never takes part (kept that way)."""
     observation, action, next_obs = np.asarray(observation), np.asarray(action), np.asarray(next_obs)
@@ -331,8 +333,11 @@ def locomotion_cost_fn(observation, action, next_obs, *, dt, ctrl_weight, unheal
         st = observation[..., 2:]
         healthy = healthy * np.all(np.logical_and(-state_bound < st, st < state_bound), axis=-1)
     unhealthy = 1 - np.isfinite(observation).all(axis=-1) * healthy
-    x_velocity = (next_obs[..., 0] - observation[..., 0]) / dt
-    return -x_velocity + unhealthy_weight * unhealthy + ctrl_weight * np.sum(np.square(action), axis=-1)
+    if velocity_index >= 0:
+        x_velocity = observation[..., velocity_index]
+    else:
+        x_velocity = (next_obs[..., 0] - observation[..., 0]) / dt
+    return -forward_weight * x_velocity + unhealthy_weight * unhealthy + ctrl_weight * np.sum(np.square(action), axis=-1)
 
 
 class _LocomotionEnv(_DeviceSimEnv):
@@ -397,7 +402,28 @@ class Ant(_LocomotionEnv):
         return self._obs()
 
 
+class Humanoid(_LocomotionEnv):
+    """Stand-in for environments/mujoco.py:279-343 (gym Humanoid-v3 with exclude_current_positions_from_observation
+    false: 378-wide observation = qpos(24) ++ qvel(23) ++ inertia / velocity / force blocks the cost never reads,
+    zeros here).  Cost: -1.25 * obs[nq] + 100 * [z outside (1, 2)] + 0.1 |a|^2."""
+    kind = "Humanoid"
+    dt = 0.015
+    obs_pad = 331
+    cost_params = dict(ctrl_weight=0.1, unhealthy_weight=100.0, z_index=2, z_lo=1.0, z_hi=2.0, z_strict=True,
+                       state_bound=0.0, velocity_index=24, forward_weight=1.25)
+
+    def reset(self):
+        c = 0.01            # gym humanoid_v3 reset_noise_scale
+        qpos = self._qpos0() + self._rs.uniform(-c, c, 24)
+        qpos[3:7] /= np.linalg.norm(qpos[3:7])
+        self._state = np.concatenate([qpos, self._rs.uniform(-c, c, 23)])
+        self._t = 0.0
+        return self._obs()
+
+
 def make_env(kind, device=0, **kwargs):
+    if kind == "Humanoid":
+        return Humanoid(name=kind, device=device, **kwargs)
     if kind == "Hopper":
         return Hopper(name=kind, device=device, **kwargs)
     if kind == "Ant":

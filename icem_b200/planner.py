@@ -42,7 +42,8 @@ class PlannerSettings:
     action_change_frequency: int = 0     # random only (controllers/mpc.py:91)
     num_problems: int = 1                # independent MPC problems batched in one handle (plan_batch)
     cost_params: Optional[dict] = None   # cost="locomotion": dt, ctrl_weight, unhealthy_weight, z_lo, z_hi, state_bound,
-                                         # z_index, z_strict (environments/mujoco.py:153-176, 196-231)
+                                         # z_index, z_strict, velocity_index, forward_weight
+                                         # (environments/mujoco.py:153-176, 196-231, 314-343)
     execute_best_elite: bool = True      # cem_std only (controllers/mpc.py:237-240)
     shift_means: bool = True             # cem_std only (controllers/mpc.py:243-248)
     bounds_like_levine: bool = False     # cem_std only (controllers/mpc.py:290-301)
@@ -57,7 +58,9 @@ def _cost_fields(cp):
                 cost_dt=float(cp.get("dt", 0.0)), cost_ctrl_weight=float(cp.get("ctrl_weight", 0.0)),
                 cost_unhealthy_weight=float(cp.get("unhealthy_weight", 0.0)),
                 cost_z_lo=float(max(cp.get("z_lo", -inf), -inf)), cost_z_hi=float(min(cp.get("z_hi", inf), inf)),
-                cost_state_bound=float(cp.get("state_bound", 0.0)))
+                cost_state_bound=float(cp.get("state_bound", 0.0)),
+                cost_velocity_index1=int(cp.get("velocity_index", -1)) + 1, cost_reserved=0,
+                cost_forward_weight=float(cp.get("forward_weight", 1.0)))
 
 
 class Planner:

@@ -250,7 +250,17 @@ def ant() -> RobotDescription:
                             friction_viscous=20.0, root_qpos0=(0.0, 0.0, 0.75, 1.0, 0.0, 0.0, 0.0))
 
 
-ROBOTS = {"halfcheetah": half_cheetah, "humanoid_standup": humanoid_standup, "hopper": hopper, "ant": ant}
+def humanoid() -> RobotDescription:
+    """gym `humanoid.xml` (Humanoid-v3): the same body, joints and gears as `humanoidstandup.xml`, starting upright with
+    the root at z = 1.4 instead of lying on its back."""
+    d = humanoid_standup()
+    d.name = "humanoid"
+    d.root_qpos0 = (0.0, 0.0, 1.4, 1.0, 0.0, 0.0, 0.0)
+    return d
+
+
+ROBOTS = {"halfcheetah": half_cheetah, "humanoid_standup": humanoid_standup, "hopper": hopper, "ant": ant,
+          "humanoid": humanoid}
 
 
 # ---------------------------------------------------------------------------------------------------------------

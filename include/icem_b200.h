@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define ICEM_ABI_VERSION 5
+#define ICEM_ABI_VERSION 6
 
 /* status codes */
 enum { ICEM_OK = 0, ICEM_ERR_INVALID = 1, ICEM_ERR_CUDA = 2, ICEM_ERR_STATE = 3, ICEM_ERR_UNSUPPORTED = 4,
@@ -42,9 +42,11 @@ enum {
 enum {
   ICEM_COST_HALFCHEETAH = 0,     /* environments/mujoco.py:67-99  */
   ICEM_COST_HUMANOID_STANDUP = 1,/* environments/mujoco.py:259-277 */
-  ICEM_COST_LOCOMOTION = 2       /* Ant (environments/mujoco.py:153-176) and Hopper (:196-231):
-                                    -(next_obs[0] - obs[0]) / dt + w_unhealthy * unhealthy(obs) + w_ctrl * |a|^2,
-                                    parameters in icem_config_t.cost_*; reads next_obs, so all h steps are simulated */
+  ICEM_COST_LOCOMOTION = 2       /* Ant (environments/mujoco.py:153-176), Hopper (:196-231), Humanoid (:314-343):
+                                    -w_fwd * x_velocity + w_unhealthy * unhealthy(obs) + w_ctrl * |a|^2 with
+                                    x_velocity = (next_obs[0] - obs[0]) / dt (Ant, Hopper; reads next_obs, so all h
+                                    steps are simulated) or obs[cost_velocity_index] (Humanoid); parameters in
+                                    icem_config_t.cost_* */
 };
 
 /* action sampler / planner family */
@@ -93,6 +95,9 @@ typedef struct icem_config {
                                      icem_plan_batch. */
   int32_t cost_z_index;           /* LOCOMOTION: observation index of the height (Hopper 1, Ant 2) */
   int32_t cost_z_strict;          /* LOCOMOTION: 1 = z_lo < z < z_hi (Hopper, mujoco.py:205), 0 = z_lo <= z <= z_hi (Ant, :149) */
+  int32_t cost_velocity_index1;   /* LOCOMOTION: 0 = x velocity by finite difference of obs[0]; k > 0 = read obs[k - 1]
+                                     (Humanoid: observation[nq], mujoco.py:333) */
+  int32_t cost_reserved;          /* keeps the doubles 8-byte aligned; must be 0 */
   double factor_decrease_num;     /* gamma */
   double alpha;
   double init_std;
@@ -103,6 +108,7 @@ typedef struct icem_config {
   double cost_unhealthy_weight;   /* LOCOMOTION: 200 (Hopper, mujoco.py:227) / 100 (Ant, :171) */
   double cost_z_lo, cost_z_hi;    /* LOCOMOTION: _healthy_z_range */
   double cost_state_bound;        /* LOCOMOTION: Hopper |states[..., 2:]| < bound (_healthy_state_range); <= 0: none */
+  double cost_forward_weight;     /* LOCOMOTION: weight of the velocity term (Humanoid _forward_reward_weight 1.25); 0 = 1 */
   uint64_t seed;                  /* Philox key (production noise) */
   const float* action_low;        /* [d] env.action_space.low  (float32 like gym.spaces.Box) */
   const float* action_high;       /* [d] */

@@ -56,3 +56,17 @@ def ant_cost(obs, act, next_obs, p=ANT):
     unhealthy = 1 - np.isfinite(obs).all(axis=-1) * (lo <= obs[..., 2]) * (obs[..., 2] <= hi)
     x_velocity = (next_obs[..., 0] - obs[..., 0]) / p["dt"]
     return -x_velocity + 100 * unhealthy + p["ctrl_weight"] * np.sum(np.square(act), axis=-1)
+
+
+HUMANOID = dict(nq=24, exclude_current_positions=False, forward_weight=1.25, ctrl_weight=0.1,
+                healthy_z_range=(1.0, 2.0))       # gym Humanoid-v3 defaults
+
+
+def humanoid_cost(obs, act, next_obs=None, p=HUMANOID):
+    """environments/mujoco.py:301-343: the velocity is READ from the observation (index nq with positions kept, nq - 2
+    without), the height test is strict, the penalty is the literal 100."""
+    z = obs[..., 0] if p["exclude_current_positions"] else obs[..., 2]
+    lo, hi = p["healthy_z_range"]
+    unhealthy = 1 - np.isfinite(obs).all(axis=-1) * ((lo < z) * (z < hi))
+    x_velocity = obs[..., p["nq"] - 2] if p["exclude_current_positions"] else obs[..., p["nq"]]
+    return -p["forward_weight"] * x_velocity + 100 * unhealthy + p["ctrl_weight"] * np.sum(np.square(act), axis=-1)

@@ -33,6 +33,27 @@ def inputs():
     return (ho, ha, hn), (ao, aa, an)
 
 
+def humanoid_inputs():
+    rs = np.random.RandomState(8)
+    o = rs.randn(30, 6, 378)
+    o[..., 2] = rs.uniform(0.8, 2.2, (30, 6))
+    o[0, 0, 2], o[0, 1, 2] = 1.0, 2.0          # the open interval ends are unhealthy
+    o[1, 2, 300] = np.nan
+    return o, rs.uniform(-0.4, 0.4, (30, 6, 17)), o + 0.01 * rs.randn(*o.shape)
+
+
+def reference_humanoid_costs():
+    ref_loader.load_reference()
+    import environments.mujoco as rm
+    hp = costs_np.HUMANOID
+    st = types.SimpleNamespace(_exclude_current_positions_from_observation=hp["exclude_current_positions"],
+                               _healthy_z_range=hp["healthy_z_range"], _forward_reward_weight=hp["forward_weight"],
+                               _ctrl_cost_weight=hp["ctrl_weight"], model=types.SimpleNamespace(nq=hp["nq"]))
+    st.unhealthy_states = lambda s: rm.Humanoid.unhealthy_states(st, s)
+    o, a, n = humanoid_inputs()
+    return rm.Humanoid.cost_fn(st, o.copy(), a, n)
+
+
 def reference_costs():
     ref_loader.load_reference()
     import environments.mujoco as rm
@@ -49,7 +70,9 @@ def reference_costs():
 
 def main():
     h, a = reference_costs()
-    np.savez_compressed(os.path.join(OUT, "costs_locomotion.npz"), hopper=h, ant=a)
+    hu = reference_humanoid_costs()
+    np.savez_compressed(os.path.join(OUT, "costs_locomotion.npz"), hopper=h, ant=a, humanoid=hu)
+    print("humanoid", hu.shape, float(np.mean(hu > 50)))
     print("hopper", h.shape, float(np.nanmean(h > 100)), "ant", a.shape, float(np.mean(a > 50)))
 
 

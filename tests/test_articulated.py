@@ -33,11 +33,11 @@ def _lifted_state(m, rs, P):
     return q, 1.5 * rs.randn(P, m.nv)
 
 
-@pytest.mark.parametrize("name", ["halfcheetah", "humanoid_standup", "hopper", "ant"])
+@pytest.mark.parametrize("name", ["halfcheetah", "humanoid_standup", "hopper", "ant", "humanoid"])
 def test_tables(name):
     m = robots.get_model(name)
     dims = {"halfcheetah": (7, 9, 9, 6, 16), "humanoid_standup": (13, 24, 23, 17, 29), "hopper": (4, 6, 6, 3, 8),
-            "ant": (9, 15, 14, 8, 25)}[name]
+            "ant": (9, 15, 14, 8, 25), "humanoid": (13, 24, 23, 17, 29)}[name]
     assert (m.nb, m.nq, m.nv, m.nu, m.nc) == dims
     assert np.all(m.body_parent < np.arange(m.nb))
     assert np.all(np.diff(m.con_body) >= 0)

@@ -11,7 +11,8 @@ from oracle.icem_np import reduce_costs
 
 pytestmark = pytest.mark.gpu
 
-ENVS = {"hopper": ("Hopper", costs_np.hopper_cost), "ant": ("Ant", costs_np.ant_cost)}
+ENVS = {"hopper": ("Hopper", costs_np.hopper_cost), "ant": ("Ant", costs_np.ant_cost),
+        "humanoid": ("Humanoid", costs_np.humanoid_cost)}
 
 
 def _planner(robot, n=64, **over):
@@ -20,8 +21,8 @@ def _planner(robot, n=64, **over):
     from icem_b200.robots import get_model
     m = get_model(robot)
     env_cls = getattr(envs, ENVS[robot][0])
-    kw = dict(horizon=20, num_simulated_trajectories=n, action_low=-np.ones(m.nu, np.float32),
-              action_high=np.ones(m.nu, np.float32), dynamics="articulated", articulated_model=m, obs_offset=0,
+    kw = dict(horizon=20, num_simulated_trajectories=n, action_low=-m.ctrl_limit * np.ones(m.nu, np.float32),
+              action_high=m.ctrl_limit * np.ones(m.nu, np.float32), dynamics="articulated", articulated_model=m, obs_offset=0,
               cost="locomotion", cost_params=dict(env_cls.cost_params, dt=env_cls.dt), obs_dim=m.nq + m.nv,
               opt_iterations=3, factor_decrease_num=1.25, noise_beta=0.25, keep_iteration_actions=True)
     kw.update(over)
@@ -35,7 +36,7 @@ def test_env_step_matches_oracle(robot):
     rs = np.random.RandomState(0)
     st = np.concatenate([m.qpos0, 0.1 * rs.randn(m.nv)])
     for t in range(40):
-        u = rs.uniform(-1, 1, m.nu) * (1.5 if t % 7 == 0 else 1.0)
+        u = rs.uniform(-1, 1, m.nu) * m.ctrl_limit * (1.5 if t % 7 == 0 else 1.0)
         ref = mod.step_state(st[None], u[None])[0]
         got, obs, _ = p.sim_step(st, u, obs_dim=m.nq + m.nv)
         assert np.abs(got - ref).max() <= 2e-4, (t, np.abs(got - ref).max())
@@ -51,7 +52,7 @@ def test_rollout_costs_match_oracle(robot, reduce):
     mod = make_model(robot)
     rs = np.random.RandomState(3)
     n, h = 96, 20
-    acts = rs.uniform(-1, 1, (n, h, m.nu)).astype(np.float32)
+    acts = (m.ctrl_limit * rs.uniform(-1, 1, (n, h, m.nu))).astype(np.float32)
     start = np.concatenate([m.qpos0, 0.05 * rs.randn(m.nv)]).astype(np.float32).astype(np.float64)
     obs = mod.rollout(start, acts.astype(np.float64), with_final=True)
     if robot == "hopper":
@@ -62,7 +63,7 @@ def test_rollout_costs_match_oracle(robot, reduce):
     d = np.abs(got - ref)
     # a trajectory whose height crosses the healthy threshold within fp32 error of it flips a 100 / 200 penalty
     z = obs[:, :-1, 1 if robot == "hopper" else 2]
-    lo = 0.7 if robot == "hopper" else 0.2
+    lo = {"hopper": 0.7, "ant": 0.2, "humanoid": 2.0}[robot]
     safe = np.all(np.abs(z - lo) > 5e-3, axis=1) & np.all(np.abs(z - 1.0) > 5e-3, axis=1)
     assert safe.mean() > 0.7
     assert np.median(d[safe]) <= 2e-3, np.median(d[safe])
@@ -93,7 +94,7 @@ def test_unhealthy_penalty_and_state_bound():
         p.close()
 
 
-@pytest.mark.parametrize("env_name", ["Hopper", "Ant"])
+@pytest.mark.parametrize("env_name", ["Hopper", "Ant", "Humanoid"])
 def test_controller_on_locomotion_envs(env_name):
     from icem_b200 import envs
     from icem_b200.controller import MpcICemB200
@@ -111,7 +112,7 @@ def test_controller_on_locomotion_envs(env_name):
     ret = 0.0
     for t in range(15):
         ac = ctrl.get_action(ob, state=env.get_GT_state())
-        assert np.all(np.abs(ac) <= 1.0 + 1e-6)
+        assert np.all(np.abs(ac) <= env.action_space.high + 1e-6)
         if t == 3:         # the elites' lazily materialised rollouts reproduce the planner's costs
             el = ctrl.elite_samples
             _, costs, _ = ctrl._planner.elites()

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import costs_np
-from oracle.make_golden_costs import inputs
+from oracle.make_golden_costs import humanoid_inputs, inputs
 
 
 def test_oracle_costs_match_reference_golden(golden_dir):
@@ -15,6 +15,9 @@ def test_oracle_costs_match_reference_golden(golden_dir):
     (ho, ha, hn), (ao, aa, an) = inputs()
     np.testing.assert_array_equal(costs_np.hopper_cost(ho, ha, hn), g["hopper"])
     np.testing.assert_array_equal(costs_np.ant_cost(ao, aa, an), g["ant"])
+    o, a, n = humanoid_inputs()
+    np.testing.assert_array_equal(costs_np.humanoid_cost(o, a, n), g["humanoid"])
+    assert g["humanoid"][0, 0] > 50 and g["humanoid"][0, 1] > 50 and 0.2 < np.mean(g["humanoid"] > 50) < 0.8
     assert np.isnan(g["hopper"]).sum() == 0           # a NaN observation is unhealthy, not NaN-cost... unless x is NaN
     assert 0.2 < np.mean(g["hopper"] > 100) < 0.8 and 0.1 < np.mean(g["ant"] > 50) < 0.6
     # Hopper quirk (mujoco.py:208): an angle outside +-0.2 alone does not make a state unhealthy
@@ -23,7 +26,9 @@ def test_oracle_costs_match_reference_golden(golden_dir):
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/icem"), reason="needs the reference sources")
 def test_oracle_costs_match_reference_live():
-    from oracle.make_golden_costs import reference_costs
+    from oracle.make_golden_costs import reference_costs, reference_humanoid_costs
+    o, ac, n = humanoid_inputs()
+    np.testing.assert_array_equal(costs_np.humanoid_cost(o, ac, n), reference_humanoid_costs())
     h, a = reference_costs()
     (ho, ha, hn), (ao, aa, an) = inputs()
     np.testing.assert_array_equal(costs_np.hopper_cost(ho, ha, hn), h)
@@ -38,6 +43,9 @@ def test_env_cost_function_equals_the_oracle():
     np.testing.assert_array_equal(got, costs_np.hopper_cost(ho, ha, hn))
     got = envs.locomotion_cost_fn(ao, aa, an, dt=envs.Ant.dt, **envs.Ant.cost_params)
     np.testing.assert_array_equal(got, costs_np.ant_cost(ao, aa, an))
+    o, a, n = humanoid_inputs()
+    got = envs.locomotion_cost_fn(o, a, n, dt=envs.Humanoid.dt, **envs.Humanoid.cost_params)
+    np.testing.assert_array_equal(got, costs_np.humanoid_cost(o, a, n))
 
 
 def test_rollout_with_final_observation():
