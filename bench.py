@@ -226,12 +226,20 @@ def run_ours(args):
             traffic = json.load(open(prof)).get(name)
         except Exception:
             traffic = None
+    compute = None
+    prof_c = os.path.join(ROOT, "profiles", "compute.json")
+    if os.path.exists(prof_c):
+        try:
+            compute = json.load(open(prof_c)).get(name)
+        except Exception:
+            compute = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel": "rollout_kernel<sample,rollout> (fused)",
                 "kernel_ms_avg": avg_kernel_ms, "kernel_share_of_step": rollout_ms / max(total_ms, 1e-9)
                 if world == 1 else None,
                 "algorithmic_bytes_per_trajectory": bytes_per_traj,
-                "note": "compute/latency-bound kernel (fp32 dynamics); HBM fraction reported as the contract asks"}
+                "note": "compute/latency-bound kernel (fp32 dynamics); HBM fraction reported as the contract asks",
+                "compute": compute}
     if w.get("mlp"):
         # tensor-core rollout: FLOP roofline of mlp_rollout_kernel timed alone (sampler excluded)
         od, ad, hid, _ = w["mlp"]

@@ -76,3 +76,24 @@ def test_launcher_reaches_c_abi_and_fails_loudly_without_gpu(tmp_path):
     assert res.returncode != 0
     assert "IcemError" in res.stderr and "cuda" in res.stderr.lower(), res.stderr[-2000:]
     assert "MpcICemB200" in res.stderr or "controller.py" in res.stderr
+
+
+def test_register_adds_every_plugin_entry():
+    """icem_b200.launch.register: controller / model registry entries and the stand-in env module."""
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from icem_b200 import launch\n"
+        "launch.prepare_paths(shims=%r); launch.register(override_mpc_icem=True)\n"
+        "import controllers, models, environments.mujoco as m\n"
+        "t = controllers.ControllerFactory.valid_base_controllers\n"
+        "assert t['mpc-icem-b200'][1] == 'MpcICemB200' and t['mpc-cem-std-b200'][1] == 'MpcCemStdB200'\n"
+        "assert t['mpc-random-b200'][1] == 'MpcRandomB200' and t['mpc-icem'][0] == 'icem_b200.controller'\n"
+        "assert t['mpc-random'][1] == 'MpcRandomB200'\n"
+        "assert {'CudaGroundTruthModel', 'CudaDenseTanhModel', 'CudaMlpModel'} <= set(models.models_dict)\n"
+        "for n in ('HalfCheetahMaybeWithPosition', 'HumanoidStandup', 'Hopper', 'Ant', 'Humanoid'):\n"
+        "    assert hasattr(m, n), n\n"
+        "cls = controllers.controller_from_string('mpc-random-b200')\n"
+        "from controllers.abstract_controller import ModelBasedController\n"
+        "assert issubclass(cls, ModelBasedController)\n" % (ROOT, os.path.join(ROOT, "oracle", "shims")))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
