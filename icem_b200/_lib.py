@@ -94,6 +94,7 @@ SIGNATURES = {
     "icem_get_costs": (C.c_int, [_H, C.c_int32, _F, C.c_int32]),
     "icem_get_actions": (C.c_int, [_H, C.c_int32, _F, C.c_int32]),
     "icem_sim_step": (C.c_int, [_H, _D, C.c_int32, _D, _D, _D, C.c_int32, _D]),
+    "icem_sim_step_batch": (C.c_int, [_H, C.c_int32, _D, C.c_int32, _D, _D]),
     "icem_state_dim": (C.c_int, [_H]),
     "icem_observe": (C.c_int, [_H, _D, C.c_int32, _D, C.c_int32]),
     "icem_op_sample": (C.c_int, [_H, C.c_int32, _F, _F, _F, _F, _F]),

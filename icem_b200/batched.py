@@ -101,6 +101,22 @@ class FusedEpisodeBatch(EpisodeBatch):
         states = np.stack([fm.start_state(ob, env.get_GT_state()) for env, ob in zip(self.envs, self.obs)])
         return self.controller._planner.plan_batch(states)
 
+    def step(self, mode="train"):
+        """Plan all episodes (one graph launch) and step all envs (one launch of B transitions, icem_sim_step_batch)
+        instead of B env.step calls of one small launch + synchronisation each."""
+        actions = self.plan(mode)
+        envs = self.envs
+        acts = np.stack([np.clip(a, e.action_space.low, e.action_space.high) for a, e in zip(actions, envs)])
+        prev_obs = list(self.obs)
+        nxt = self.controller._planner.sim_step_batch(np.stack([e._state for e in envs]), acts)
+        rewards = np.empty(len(self))
+        for i, e in enumerate(envs):
+            e._state = nxt[i]
+            e._t += e.dt
+            self.obs[i] = e._obs()
+            rewards[i] = -float(e.cost_fn(prev_obs[i], acts[i], self.obs[i]))
+        return actions, rewards, np.zeros(len(self), dtype=bool)
+
 
 def make_fused_episode_batch(env_name, num_episodes, controller_params, seed=0, device=0, controller_cls=None):
     from . import envs as envs_mod

@@ -485,6 +485,7 @@ static RefitArgs refit_args(icem_planner* p, int i) {
 static int select_grid(icem_planner* p, int rows) {
   return std::max(1, std::min(p->sm_count, (rows + 2047) / 2048));
 }
+static size_t select_smem(int k) { return (size_t)k * sizeof(unsigned long long); }
 
 // enqueue all CEM iterations of one plan step on the planner's stream
 static void enqueue_iterations(icem_planner* p, bool time_rollouts) {
@@ -503,7 +504,7 @@ static void enqueue_iterations(icem_planner* p, bool time_rollouts) {
     s.cand = p->cand.p; s.ticket = p->ticket.p;
     s.prob_actions = p->actions_per; s.prob_costs = p->costs_per; s.prob_cand = p->sm_count * p->k;
     RefitArgs r = refit_args(p, i);
-    const size_t smem = (size_t)p->k * sizeof(unsigned long long);
+    const size_t smem = select_smem(p->k);
     if (p->cfg.world_size == 1) {
       select_kernel<<<dim3(select_grid(p, ip.rows_cap), p->B), kSelectThreads, smem, p->stream>>>(s, r, 1);
       ICEM_CUDA(cudaGetLastError());
@@ -522,10 +523,17 @@ static void enqueue_iterations(icem_planner* p, bool time_rollouts) {
 }
 
 // state_dev <- f(state_dev, executed action): closed loop on the device
+// blockIdx.x = instance (icem_sim_step_batch): element strides between instances, 0 for a single transition
+struct AdvanceBatch { int state_stride, action_stride, obs_stride; };
+
 template <class Dyn>
 __global__ void advance_kernel(typename Dyn::Params dp, float* state, const float* action, float* next_state,
-                               float* obs_out, int obs_dim) {
+                               float* obs_out, int obs_dim, AdvanceBatch ab) {
   extern __shared__ __align__(128) float smem[];
+  state += (size_t)blockIdx.x * ab.state_stride;
+  if (action) action += (size_t)blockIdx.x * ab.action_stride;
+  if (next_state) next_state += (size_t)blockIdx.x * ab.state_stride;
+  if (obs_out) obs_out += (size_t)blockIdx.x * ab.obs_stride;
   float* s_dyn = smem;
   float* w_dyn = s_dyn + ((Dyn::cta_floats(dp) + 3) & ~3);
   float* s_act = w_dyn + ((Dyn::warp_floats(dp) + 3) & ~3);
@@ -545,37 +553,38 @@ __global__ void advance_kernel(typename Dyn::Params dp, float* state, const floa
 
 template <class Dyn>
 static void launch_advance(icem_planner* p, const typename Dyn::Params& dp, float* state, const float* action,
-                           float* next_state, float* obs_out, int obs_dim) {
+                           float* next_state, float* obs_out, int obs_dim, int batch = 1, AdvanceBatch ab = {0, 0, 0}) {
   const size_t smem = (((Dyn::cta_floats(dp) + 3) & ~3) + ((Dyn::warp_floats(dp) + 3) & ~3) + dp.act_dim + 4) *
                       sizeof(float);
   auto kern = advance_kernel<Dyn>;
   if (smem > 48 * 1024)
     ICEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<1, 32, smem, p->stream>>>(dp, state, action, next_state, obs_out, obs_dim);
+  kern<<<batch, 32, smem, p->stream>>>(dp, state, action, next_state, obs_out, obs_dim, ab);
   ICEM_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
 static void advance_dyn(icem_planner* p, float* state, const float* action, float* next_state, float* obs_out,
-                        int obs_dim) {
+                        int obs_dim, int batch = 1, AdvanceBatch ab = {0, 0, 0}) {
   switch (p->cfg.dynamics) {
     case ICEM_DYN_MLP:
+      if (batch != 1) throw Unsupported("batched transitions are not available for the MLP model");
       mlp_advance_kernel<<<1, 256, 0, p->stream>>>(p->mlp, state, action, next_state, obs_out, obs_dim);
       ICEM_CUDA(cudaGetLastError());
       g_launches.fetch_add(1, std::memory_order_relaxed);
       break;
     case ICEM_DYN_DENSE_TANH:
-      launch_advance<DenseTanh>(p, p->dense, state, action, next_state, obs_out, obs_dim);
+      launch_advance<DenseTanh>(p, p->dense, state, action, next_state, obs_out, obs_dim, batch, ab);
       break;
     case ICEM_DYN_HALFCHEETAH:
     case ICEM_DYN_HUMANOID_STANDUP:
     case ICEM_DYN_ARTICULATED:
       if (Articulated<12>::fits(p->art.nb, p->art.nv, p->art.nc))
-        launch_advance<Articulated<12>>(p, art_params<12>(p), state, action, next_state, obs_out, obs_dim);
+        launch_advance<Articulated<12>>(p, art_params<12>(p), state, action, next_state, obs_out, obs_dim, batch, ab);
       else if (Articulated<24>::fits(p->art.nb, p->art.nv, p->art.nc))
-        launch_advance<Articulated<24>>(p, art_params<24>(p), state, action, next_state, obs_out, obs_dim);
+        launch_advance<Articulated<24>>(p, art_params<24>(p), state, action, next_state, obs_out, obs_dim, batch, ab);
       else
-        launch_advance<Articulated<32>>(p, art_params<32>(p), state, action, next_state, obs_out, obs_dim);
+        launch_advance<Articulated<32>>(p, art_params<32>(p), state, action, next_state, obs_out, obs_dim, batch, ab);
       break;
     default:
       throw Unsupported("dynamics id not supported by this build");
@@ -1354,6 +1363,32 @@ int icem_sim_step(icem_planner_t* p, const double* state, int32_t state_dim, con
   ICEM_API_END
 }
 
+int icem_sim_step_batch(icem_planner_t* p, int32_t n, const double* states, int32_t state_dim, const double* actions,
+                        double* next_states) {
+  ICEM_API_BEGIN
+  if (!p || !states || !actions || !next_states) throw InvalidArg("null argument");
+  if (n < 1 || n > 65535) throw InvalidArg("n must be in [1, 65535]");
+  require_model(p);
+  if (state_dim != p->state_dim) throw InvalidArg("state_dim does not match the forward model");
+  ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  const int sd = p->state_dim, d = p->d;
+  DevBuf<float> buf;
+  buf.alloc((size_t)n * (2 * sd + d));
+  std::vector<float> h((size_t)n * (sd + d));
+  for (size_t i = 0; i < (size_t)n * sd; ++i) h[i] = (float)states[i];
+  for (size_t i = 0; i < (size_t)n * d; ++i) h[(size_t)n * sd + i] = (float)actions[i];
+  ICEM_CUDA(cudaMemcpyAsync(buf.p, h.data(), h.size() * 4, cudaMemcpyHostToDevice, p->stream));
+  float* d_state = buf.p;
+  float* d_act = buf.p + (size_t)n * sd;
+  float* d_next = d_act + (size_t)n * d;
+  advance_dyn(p, d_state, d_act, d_next, nullptr, 0, n, AdvanceBatch{sd, d, 0});
+  std::vector<float> r((size_t)n * sd);
+  ICEM_CUDA(cudaMemcpyAsync(r.data(), d_next, r.size() * 4, cudaMemcpyDeviceToHost, p->stream));
+  ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  for (size_t i = 0; i < r.size(); ++i) next_states[i] = r[i];
+  ICEM_API_END
+}
+
 int icem_observe(icem_planner_t* p, const double* state, int32_t state_dim, double* obs_out, int32_t obs_dim) {
   return icem_sim_step(p, state, state_dim, nullptr, nullptr, obs_out, obs_dim, nullptr);
 }
@@ -1486,7 +1521,7 @@ int icem_op_topk(icem_planner_t* p, int32_t n, const float* costs, int32_t k, in
   s.costs = d_cost.p; s.actions = d_dummy.p; s.ss = reinterpret_cast<StepState*>(d_ss.p);
   s.cand = d_cand.p; s.ticket = d_ticket.p; s.send_keys = d_send.p; s.send_actions = d_dummy.p;
   RefitArgs r{};
-  select_kernel<<<select_grid(p, n), kSelectThreads, (size_t)k * sizeof(unsigned long long), p->stream>>>(s, r, 0);
+  select_kernel<<<select_grid(p, n), kSelectThreads, select_smem(k), p->stream>>>(s, r, 0);
   ICEM_CUDA(cudaGetLastError());
   topk_finish_kernel<<<1, kSelectThreads, 0, p->stream>>>(d_send.p, k, d_cost.p, d_idx.p, d_co.p);
   ICEM_CUDA(cudaGetLastError());
@@ -1593,7 +1628,7 @@ int icem_bench_op(icem_planner_t* p, int32_t op, int32_t n, int32_t reps, int32_
     else if (op == 1) launch_rollout_dyn<true, true>(p, a, n);
     else if (op == 3) launch_rollout_dyn<false, true>(p, a, n);
     else {
-      select_kernel<<<select_grid(p, n), kSelectThreads, (size_t)p->k * sizeof(unsigned long long), p->stream>>>(s, r, 1);
+      select_kernel<<<select_grid(p, n), kSelectThreads, select_smem(p->k), p->stream>>>(s, r, 1);
       ICEM_CUDA(cudaGetLastError());
       g_launches.fetch_add(1, std::memory_order_relaxed);
     }

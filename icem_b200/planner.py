@@ -287,6 +287,15 @@ class Planner:
                                                      obs_dim, dptr(out)))
         return out
 
+    def sim_step_batch(self, states, actions):
+        """n independent transitions in one launch: states [n, state_dim], actions [n, d] -> next states."""
+        st, ac = f64(states), f64(actions)
+        if st.ndim != 2 or ac.ndim != 2 or st.shape[0] != ac.shape[0] or ac.shape[1] != self.d:
+            raise ValueError("states must be [n, state_dim] and actions [n, d]")
+        out = np.empty_like(st)
+        check(self._lib.icem_sim_step_batch(self._h, st.shape[0], dptr(st), st.shape[1], dptr(ac), dptr(out)))
+        return out
+
     def observe(self, state, obs_dim):
         st = f64(state).ravel()
         obs = np.empty(obs_dim, dtype=np.float64)

@@ -235,6 +235,10 @@ int icem_get_actions(icem_planner_t* p, int32_t iteration, float* actions_out, i
 /* ---- forward_model.predict / env.step on the device model (controllers/icem.py:186-188) ---------------- */
 int icem_sim_step(icem_planner_t* p, const double* state, int32_t state_dim, const double* action,
                   double* next_state, double* obs_out, int32_t obs_dim, double* reward_out);
+/* n independent transitions in ONE launch (one CTA each): states[n][state_dim], actions[n][act_dim] ->
+ * next_states[n][state_dim].  The env.step of many episodes at once (icem_b200/batched.py). */
+int icem_sim_step_batch(icem_planner_t* p, int32_t n, const double* states, int32_t state_dim, const double* actions,
+                        double* next_states);
 int icem_state_dim(icem_planner_t* p);
 int icem_observe(icem_planner_t* p, const double* state, int32_t state_dim, double* obs_out, int32_t obs_dim);
 

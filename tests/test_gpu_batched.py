@@ -106,3 +106,18 @@ def test_fused_episode_batch_runs_like_the_streamed_one():
         np.testing.assert_array_equal(eps[i]["rewards"], ref[i]["rewards"])
     fused.close()
     streamed.close()
+
+
+def test_batched_transitions_equal_single_transitions():
+    """icem_sim_step_batch: n transitions in one launch == n icem_sim_step calls, bit for bit."""
+    from icem_b200 import workloads
+    from icem_b200.planner import Planner
+    name = "humanoid_standup_gt_n16384"
+    p = Planner(workloads.planner_settings(name, scale_population=1 / 256))
+    rs = np.random.RandomState(0)
+    states = np.stack([workloads.start_state(name, seed=i) for i in range(7)])
+    acts = rs.uniform(-0.4, 0.4, (7, 17))
+    got = p.sim_step_batch(states, acts)
+    for i in range(7):
+        np.testing.assert_array_equal(got[i], p.sim_step(states[i], acts[i])[0])
+    p.close()
