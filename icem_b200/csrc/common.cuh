@@ -38,13 +38,13 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// minimum of a 64-bit key over the warp with two 32-bit REDUX instructions (high words, then the low words of the
+// lanes that hold the minimal high word) instead of a 5-step shuffle tree of 64-bit values
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
-    v = w < v ? w : v;
-  }
-  return v;
+  const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+  const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+  return ((unsigned long long)mh << 32) | ml;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -70,14 +70,69 @@ struct RefitArgs {
 };
 
 // -------------------------------------------------------------------------------------------------
-// k rounds of block arg-min.  KeyFn(i) -> unique 64-bit key of element i (i in [0,count)).
-// out[0..k) ascending (smem or global).  All threads of the CTA must call.  Keys are unique, so
-// "smallest key greater than the last extracted one" needs no marking.
+// The k smallest of `count` unique 64-bit keys, ascending, into out[0..k) (smem or global).  KeyFn(i) -> key of
+// element i.  All threads of the CTA must call.  Keys are unique, so "smallest key greater than the last extracted
+// one" needs no marking.
+//
+// Fast path (count <= 8 keys per thread, i.e. every select_kernel chunk and every merge): each thread reads its keys
+// ONCE into registers, each WARP extracts the k smallest of its 256 keys with shuffles only (the owner of an
+// extracted minimum advances over its own registers), and one warp merges the 8 x k warp candidates the same way:
+// two CTA barriers in total.  The general path below does k block-wide rounds with two barriers each and lets the
+// owner rescan global memory (a chain of L2 latencies per round): ~40 us per launch against ~15.
+constexpr int kSelPerThread = 8;
+constexpr int kSelMaxK = 64;
+
 template <class KeyFn>
 __device__ void block_topk(KeyFn key, int count, int k, unsigned long long* out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = blockDim.x >> 5;
+  if (count <= (int)blockDim.x * kSelPerThread && k <= kSelMaxK && nwarps <= 8) {
+    __shared__ unsigned long long s_cand[8 * kSelMaxK];
+    unsigned long long v[kSelPerThread];
+    unsigned long long mine = kKeyMax;
+#pragma unroll
+    for (int j = 0; j < kSelPerThread; ++j) {
+      const int i = tid + j * (int)blockDim.x;
+      v[j] = i < count ? key(i) : kKeyMax;
+      mine = v[j] < mine ? v[j] : mine;
+    }
+    for (int r = 0; r < k; ++r) {                     // this warp's k smallest
+      const unsigned long long w = warp_min_u64(mine);
+      if (lane == 0) s_cand[warp * k + r] = w;
+      if (mine == w && w != kKeyMax) {
+        unsigned long long nxt = kKeyMax;
+#pragma unroll
+        for (int j = 0; j < kSelPerThread; ++j) nxt = (v[j] > w && v[j] < nxt) ? v[j] : nxt;
+        mine = nxt;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {                                  // merge nwarps * k candidates (<= 512: 16 per lane)
+      const int total = nwarps * k;
+      unsigned long long c[16];
+      unsigned long long m2 = kKeyMax;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int i = lane + 32 * j;
+        c[j] = i < total ? s_cand[i] : kKeyMax;
+        m2 = c[j] < m2 ? c[j] : m2;
+      }
+      for (int r = 0; r < k; ++r) {
+        const unsigned long long w = warp_min_u64(m2);
+        if (lane == 0) out[r] = w;
+        if (m2 == w && w != kKeyMax) {
+          unsigned long long nxt = kKeyMax;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) nxt = (c[j] > w && c[j] < nxt) ? c[j] : nxt;
+          m2 = nxt;
+        }
+      }
+    }
+    __syncthreads();
+    return;
+  }
   __shared__ unsigned long long s_part[kSelectThreads / 32];
   __shared__ unsigned long long s_min;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned long long mine = kKeyMax;
   for (int i = tid; i < count; i += blockDim.x) {
     const unsigned long long v = key(i);
@@ -160,17 +215,18 @@ __device__ void merge_refit(const RefitArgs& r, unsigned long long* s_keys /* [k
 
   const float inv_k = 1.0f / (float)k;
   for (int e = tid; e < hd; e += blockDim.x) {
+    // The elite rows are read-only here (population / previous elites / gathered records; the new elite buffer is the
+    // other half of a double buffer), so they go through the non-coherent path: with plain loads every load had to
+    // wait for the store before it (possible alias), a chain of ~20 L2 latencies per element -- most of the kernel.
     float sum = 0.f;
-    for (int j = 0; j < k; ++j) {
-      const float v = s_src[j][e];
-      r.new_elite_actions[(size_t)j * r.stride + e] = v;
-      sum += v;
-    }
+    for (int j = 0; j < k; ++j) sum += __ldg(s_src[j] + e);
     const float m = sum * inv_k;
     float var = 0.f;
     for (int j = 0; j < k; ++j) {
-      const float dv = s_src[j][e] - m;
+      const float v = __ldg(s_src[j] + e);
+      const float dv = v - m;
       var = fmaf(dv, dv, var);
+      r.new_elite_actions[(size_t)j * r.stride + e] = v;
     }
     const float sd = sqrtf(var * inv_k);                       // ddof = 0 (icem.py:208)
     const float nm = r.one_minus_alpha * m + r.alpha * r.mean[e];   // icem.py:210-211
