@@ -125,9 +125,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar)) : "memory");
 }
 __device__ __forceinline__ float tanh_approx(float x) {
-#if defined(ICEM_MLP_EXP) && ICEM_MLP_EXP == 1        // timing experiment: no MUFU
-  return x * 0.5f;
-#endif
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
