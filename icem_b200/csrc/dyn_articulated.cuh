@@ -90,6 +90,7 @@ struct Articulated {
 #endif
   static constexpr int kMinCtasPerSm = NVMAX <= 24 ? ICEM_ART_MIN_CTAS : 2;   // register cap: 85 / 128 per thread
   static constexpr bool kCtaLockstep = ICEM_ART_LOCKSTEP != 0;
+  static constexpr bool kOutlineRollout = true;
   static constexpr bool kHasHealth = true;      // state_healthy(): usable with ICEM_COST_LOCOMOTION
   static constexpr int kLd = NVMAX + 1;           // row stride of the transposition buffer (odd for NVMAX even)
   struct Params {

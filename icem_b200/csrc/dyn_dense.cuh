@@ -10,6 +10,7 @@ struct DenseTanh {
   static constexpr int kWarpsPerCta = 8;
   static constexpr int kMinCtasPerSm = 2;
   static constexpr bool kCtaLockstep = false;
+  static constexpr bool kOutlineRollout = false;
   static constexpr bool kHasHealth = false;
   struct Params {
     int obs_dim, act_dim;

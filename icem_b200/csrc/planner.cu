@@ -60,6 +60,7 @@ struct NoDyn {
   static constexpr int kMinCtasPerSm = 2;
   static constexpr bool kCtaLockstep = false;
   static constexpr bool kHasHealth = false;
+  static constexpr bool kOutlineRollout = false;
   struct Params { int act_dim; };
   __host__ __device__ static int cta_floats(const Params&) { return 0; }
   __host__ __device__ static int warp_floats(const Params&) { return 0; }

@@ -179,8 +179,8 @@ __device__ __forceinline__ void fill_normals(float* dst, int count, uint32_t gro
 // (sampler pointers, row bookkeeping, TMA state) stays in registers, so the dynamics code gets the whole register
 // budget of 80.  Measured on B200: HumanoidStandup 34.5 -> 31.6 ms per plan step (+9 %), HalfCheetah +3 %.
 template <class Dyn, bool kNextObs>
-__device__ __noinline__ float rollout_one(Dyn& dyn, const CostConst& cc, const float* tile, float* w_stash, int h, int d,
-                                          int barrier_threads) {
+__device__ __forceinline__ float rollout_one_body(Dyn& dyn, const CostConst& cc, const float* tile, float* w_stash, int h,
+                                                  int d, int barrier_threads) {
   const int lane = threadIdx.x & 31;
   float total = (cc.reduce == 1) ? INFINITY : 0.f;
   for (int t = 0; t < h; ++t) {
@@ -204,6 +204,12 @@ __device__ __noinline__ float rollout_one(Dyn& dyn, const CostConst& cc, const f
     }
   }
   return total;
+}
+
+template <class Dyn, bool kNextObs>
+__device__ __noinline__ float rollout_one(Dyn& dyn, const CostConst& cc, const float* tile, float* w_stash, int h, int d,
+                                          int barrier_threads) {
+  return rollout_one_body<Dyn, kNextObs>(dyn, cc, tile, w_stash, h, d, barrier_threads);
 }
 
 // kNextObs: the cost reads next_obs (ICEM_COST_LOCOMOTION).  A template flag, not a runtime branch: the fused kernel's
@@ -396,7 +402,11 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
     if (kRollout) {
       // ---- 4. open-loop rollout from the shared start state, cost on the pre-action observation ----
       dyn.reset(ICEM_P_STATE);
-      const float total = rollout_one<Dyn, kNextObs>(dyn, cc, tile, w_stash, h, d, n_active * 32);
+      // out of line only where the dynamics is big enough to need the registers (Dyn::kOutlineRollout); a cheap model
+      // (dense layer) loses 30 % to the call and the by-reference state
+      float total;
+      if constexpr (Dyn::kOutlineRollout) total = rollout_one<Dyn, kNextObs>(dyn, cc, tile, w_stash, h, d, n_active * 32);
+      else total = rollout_one_body<Dyn, kNextObs>(dyn, cc, tile, w_stash, h, d, n_active * 32);
       if (lane == 0) ICEM_P_COSTS[row] = total;
     }
     __syncwarp();

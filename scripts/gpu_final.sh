@@ -20,5 +20,5 @@ name='dense_tanh_humanoid_n16384'
 w=workloads.get_workload(name); s=workloads.planner_settings(name, scale_population=16)
 p=Planner(s); p.set_dense_model(*workloads.dense_model_weights(*w['dense'])); p.begin_rollout()
 p.bench_op('sample', 262144, reps=1, flush_l2=False)" > /dev/null 2>&1
-timeout 200 compute-sanitizer --tool synccheck --print-limit 5 python scripts/sanitize.py cheetah humanoid mlp > gpurun_out/sanitize_synccheck_$TAG.log 2>&1; grep -E "ok$|ERROR SUMMARY" gpurun_out/sanitize_synccheck_$TAG.log
+timeout 150 compute-sanitizer --tool synccheck --print-limit 5 python scripts/sanitize.py cheetah humanoid mlp > gpurun_out/sanitize_synccheck_$TAG.log 2>&1; grep -E "ok$|ERROR SUMMARY" gpurun_out/sanitize_synccheck_$TAG.log
 ls -la gpurun_out | tail -12
