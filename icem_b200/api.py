@@ -9,9 +9,25 @@ icem/controllers/abstract_controller.py:43-58 (StatefulController), :61-72 (Mode
 from abc import ABC, abstractmethod
 
 
+_REF_TOP_LEVEL = ("controllers", "environments", "misc", "models")
+
+
+def forget_failed_reference_import(before):
+    """The reference uses top-level package names (`environments`, `controllers`, ...).  Trying to import them when
+    the reference is NOT on sys.path can pick up an unrelated namespace package of the same name from site-packages
+    and leave it cached in sys.modules, which would shadow the reference if it is put on sys.path later (launcher,
+    tests).  Drop whatever such an attempt added."""
+    import sys
+    for name in list(sys.modules):
+        if name not in before and name.split(".")[0] in _REF_TOP_LEVEL:
+            del sys.modules[name]
+
+
 def reference_bases():
     """(Controller bases, ForwardModel base, RolloutBuffer, Rollout, AbstractGroundTruthModel) from the reference
     if importable, else None."""
+    import sys
+    before = set(sys.modules)
     try:
         from controllers.abstract_controller import ModelBasedController as RefMBC  # noqa
         from controllers.abstract_controller import StatefulController as RefSC  # noqa
@@ -21,6 +37,7 @@ def reference_bases():
         return dict(mbc=RefMBC, sc=RefSC, rollout=Rollout, buffer=RolloutBuffer, fm=ForwardModelWithDefaults,
                     gt=AbstractGroundTruthModel)
     except ImportError:
+        forget_failed_reference_import(before)
         return None
 
 

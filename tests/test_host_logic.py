@@ -75,3 +75,16 @@ def test_bench_peak_lookup_tolerates_key_spellings(tmp_path, monkeypatch):
     (tmp_path / "MEASURED_PEAKS.json").write_text(json.dumps(
         {"hbm_copy_GBps": 6547.2, "bf16": {"burst_tflops": 1645.3, "sustained_tflops": 1386.1}}))
     assert b.read_peaks()[0] == 6547.2 and b.read_bf16_peak() == 1645.3
+
+
+def test_importing_the_package_does_not_shadow_the_reference():
+    """An unrelated `environments` namespace package exists in this image's site path; importing icem_b200 without
+    the reference on sys.path must not leave it (or any other top-level name the reference uses) cached in
+    sys.modules, or a later import of the reference would resolve to the wrong package."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import icem_b200.envs, icem_b200.models, icem_b200.controller\n"
+            "bad = [m for m in sys.modules if m.split('.')[0] in ('environments', 'controllers', 'misc', 'models')]\n"
+            "assert not bad, bad\n" % ROOT)
+    subprocess.run([sys.executable, "-c", code], check=True)
