@@ -226,3 +226,49 @@ def test_random_oracle_matches_reference_golden(name, golden_dir):
         c = cases.random_config(cases.RANDOM_CASES[name])
         lo, hi = c["action_low"].astype(np.float64), c["action_high"].astype(np.float64)
         np.testing.assert_array_equal((lo + (hi - lo) * u).astype(np.float32), g[f"s{s}_i0_actions"])
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference not present")
+@pytest.mark.parametrize("fuzz_seed", range(24))
+def test_oracle_matches_live_reference_on_random_configurations(fuzz_seed):
+    """Beyond the committed fixtures: seeded random controller settings (population, horizon incl. odd, action dim,
+    iterations, elite count / reuse fraction, all three feature flags, white and coloured noise, decay factor, cost
+    reduction, momentum) run through the imported reference and through oracle/icem_np.py: identical RNG consumption,
+    elite lists, costs and executed actions over 3 closed-loop steps."""
+    import warnings
+    from oracle import ref_harness
+    from oracle.dynamics_np import DenseTanhModel
+    rs = np.random.RandomState(100 + fuzz_seed)
+    d = int(rs.randint(2, 6))
+    sampler = dict(alpha=float(rs.choice([0.0, 0.1, 0.5])), elites_size=int(rs.randint(2, 12)),
+                   fraction_elites_reused=float(rs.choice([0.0, 0.3, 0.5, 1.0])), init_std=float(rs.uniform(0.2, 0.8)),
+                   keep_previous_elites=bool(rs.randint(2)), shift_elites_over_time=bool(rs.randint(2)),
+                   use_mean_actions=bool(rs.randint(2)), opt_iterations=int(rs.randint(1, 5)),
+                   noise_beta=float(rs.choice([0.0, 0.5, 1.0, 3.0])))
+    ctrl = dict(num_simulated_trajectories=int(rs.randint(4, 80)), factor_decrease_num=float(rs.choice([1.0, 1.25, 2.0])),
+                horizon=int(rs.randint(3, 17)), cost_along_trajectory=str(rs.choice(["sum", "best", "final"])),
+                action_sampler_params=sampler, do_visualize_plan=False, verbose=False)
+    a = 0.9 * np.eye(17) + 0.05 * rs.randn(17, 17)
+    b = 0.3 * rs.randn(17, d)
+    model_fn = lambda: DenseTanhModel(a, b, np.zeros(17))
+    lo = -rs.uniform(0.3, 1.5, d)
+    hi = rs.uniform(0.3, 1.5, d)
+    case = dict(model=model_fn, cost="halfcheetah", penalise_flipping=bool(rs.randint(2)), low=lo, high=hi, ctrl=ctrl,
+                start_obs=0.2 * rs.randn(17), seed=int(rs.randint(1000)), steps=3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # "Number of trajectories is too low ... Setting num_elites to 2"
+        steps, next_ref = ref_harness.run_reference_episode(
+            case["model"](), case["cost"], case["ctrl"], case["low"], case["high"], case["start_obs"], case["seed"],
+            case["steps"], case["penalise_flipping"])
+        traces, next_orc = run_oracle_case(case)
+    assert next_ref == next_orc, (ctrl, "RNG consumption differs")
+    for st, tr in zip(steps, traces):
+        np.testing.assert_allclose(tr.action, st["action"], atol=1e-12, err_msg=str(ctrl))
+        np.testing.assert_allclose(tr.mean_after_shift, st["mean_after_shift"], atol=1e-12)
+        assert len(tr.iterations) == len(st["iterations"])
+        for x, y in zip(tr.iterations, st["iterations"]):
+            np.testing.assert_allclose(x.costs, y["costs"], atol=1e-10)
+            if len(np.unique(np.round(y["costs"], 12))) == len(y["costs"]):      # no exact ties: order is defined
+                np.testing.assert_array_equal(x.elite_idx, y["elite_idx"])
+            np.testing.assert_allclose(x.mean, y["mean"], atol=1e-12)
+            np.testing.assert_allclose(x.std, y["std"], atol=1e-12)
