@@ -272,3 +272,54 @@ def test_oracle_matches_live_reference_on_random_configurations(fuzz_seed):
                 np.testing.assert_array_equal(x.elite_idx, y["elite_idx"])
             np.testing.assert_allclose(x.mean, y["mean"], atol=1e-12)
             np.testing.assert_allclose(x.std, y["std"], atol=1e-12)
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference not present")
+@pytest.mark.parametrize("fuzz_seed", range(8))
+def test_cem_std_and_random_oracles_match_live_reference_on_random_configurations(fuzz_seed):
+    """Same live fuzzing for the two baseline controllers (mpc.py::MpcCemStd, mpc.py::MpcRandom)."""
+    from oracle import ref_harness
+    from oracle.dynamics_np import DenseTanhModel
+    rs = np.random.RandomState(300 + fuzz_seed)
+    d = int(rs.randint(2, 6))
+    a = 0.9 * np.eye(17) + 0.05 * rs.randn(17, 17)
+    b = 0.3 * rs.randn(17, d)
+    model_fn = lambda: DenseTanhModel(a, b, np.zeros(17))
+    lo, hi = -rs.uniform(0.3, 1.5, d), rs.uniform(0.3, 1.5, d)
+    base = dict(model=model_fn, cost="halfcheetah", penalise_flipping=bool(rs.randint(2)), low=lo, high=hi,
+                start_obs=0.2 * rs.randn(17), seed=int(rs.randint(1000)), steps=3)
+    h = int(rs.randint(3, 15))
+    n = int(rs.randint(4, 60))
+    reduce = str(rs.choice(["sum", "best", "final"]))
+    # ---- MpcCemStd
+    sampler = dict(alpha=float(rs.choice([0.0, 0.1, 0.4])), elites_size=int(rs.randint(2, 10)),
+                   opt_iterations=int(rs.randint(1, 4)), init_std=float(rs.uniform(0.2, 0.8)),
+                   shift_means=bool(rs.randint(2)), execute_best_elite=bool(rs.randint(2)),
+                   bounds_like_levine=bool(rs.randint(2)))
+    case = dict(base, ctrl=dict(num_simulated_trajectories=n, horizon=h, cost_along_trajectory=reduce,
+                                action_sampler_params=sampler, do_visualize_plan=False, verbose=False))
+    steps, next_ref = ref_harness.run_reference_episode(
+        case["model"](), case["cost"], case["ctrl"], lo, hi, case["start_obs"], case["seed"], 3,
+        case["penalise_flipping"], controller="MpcCemStd")
+    traces, next_orc = _run_cem_std_case(case)
+    assert next_ref == next_orc
+    for st, tr in zip(steps, traces):
+        np.testing.assert_allclose(tr.action, st["action"], atol=1e-10, err_msg=str(sampler))
+        for x, y in zip(tr.iterations, st["iterations"]):
+            np.testing.assert_allclose(x.costs, y["costs"], atol=1e-8)
+            np.testing.assert_allclose(x.mean, y["mean"], atol=1e-10)
+            np.testing.assert_allclose(x.std, y["std"], atol=1e-10)
+    # ---- MpcRandom
+    case = dict(base, ctrl=dict(num_simulated_trajectories=n, horizon=h, cost_along_trajectory=reduce,
+                                action_sampler_params=dict(action_change_frequency=int(rs.randint(0, h))),
+                                do_visualize_plan=False, verbose=False))
+    steps, next_ref = ref_harness.run_reference_episode(
+        case["model"](), case["cost"], case["ctrl"], lo, hi, case["start_obs"], case["seed"], 3,
+        case["penalise_flipping"], controller="MpcRandom")
+    traces, next_orc = _run_random_case(case, record_actions=True)
+    assert next_ref == next_orc
+    for st, tr in zip(steps, traces):
+        np.testing.assert_array_equal(tr.action.astype(np.float32), st["action"].astype(np.float32))
+        np.testing.assert_array_equal(tr.iterations[0].actions.astype(np.float32),
+                                      st["iterations"][0]["actions"].astype(np.float32))
+        np.testing.assert_allclose(tr.iterations[0].costs, st["iterations"][0]["costs"], atol=1e-10)
