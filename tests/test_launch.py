@@ -97,3 +97,27 @@ def test_register_adds_every_plugin_entry():
         "assert issubclass(cls, ModelBasedController)\n" % (ROOT, os.path.join(ROOT, "oracle", "shims")))
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_example_settings_resolve_through_the_reference_loader(tmp_path):
+    """examples/*.json go through the reference's own settings code path (smart_settings load + hierarchy merge) and
+    name only registered plugins."""
+    code = (
+        "import sys, glob, os; sys.path.insert(0, %r)\n"
+        "from icem_b200 import launch\n"
+        "launch.prepare_paths(shims=%r); launch.register()\n"
+        "import controllers, models\n"
+        "from misc.helpers import resolve_params_hierarchy\n"
+        "import smart_settings\n"
+        "files = sorted(glob.glob(os.path.join(%r, 'examples', '*.json')))\n"
+        "assert len(files) >= 2\n"
+        "for f in files:\n"
+        "    sys.argv = ['main.py', f]\n"          # helpers.py:160 reads the settings path from argv
+        "    p = resolve_params_hierarchy(smart_settings.load(f))\n"
+        "    assert p['controller'] in controllers.ControllerFactory.valid_base_controllers, f\n"
+        "    assert p['forward_model'] in models.models_dict, f\n"
+        "    cp = p['controller_params']\n"
+        "    assert cp['horizon'] == 30 and cp['action_sampler_params']['elites_size'] == 10\n"
+        "    assert p['rollout_params']['use_env_states'] is True\n" % (ROOT, os.path.join(ROOT, "oracle", "shims"), ROOT))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
