@@ -79,37 +79,37 @@ class ModelBasedController(Controller, ABC):
         self.use_env_reward_as_cost = use_env_reward_as_cost
 
     def visualize_plan(self, *, obs, state, acts):
-        """Same contract as controllers/abstract_controller.py:93-128: replay a plan in a second env instance;
-        "last" renders the end of the plan, "all" every step (reporting where the replay leaves the plan)."""
+        """Replays a planned trajectory in a second env instance, like the reference hook
+        (controllers/abstract_controller.py:93-128): mode "last" shows where the plan ends, mode "all" re-simulates it
+        from `state` at 25 fps and reports the first step at which the replay leaves the plan by more than 0.01."""
+        mode = self.do_visualize_plan
+        if not mode or not getattr(self.env, "supports_live_rendering", False):
+            return
+        if mode not in ("last", "all"):
+            raise AttributeError("unknown mode for do_visualize_plan: Options: None, 'last','all'")
         import time
 
         import numpy as np
-        if not self.do_visualize_plan:
+        viewer = self.visualize_env
+        if viewer is None:
+            viewer = self.visualize_env = type(self.env)(name=self.env.name, **getattr(self.env, "init_kwargs", {}))
+            viewer.reset()
+        if mode == "last":
+            viewer.set_state_from_observation(obs[-1])
+            viewer.step(acts[-1])
+            viewer.render()
             return
-        env = self.env
-        if not getattr(env, "supports_live_rendering", False):
-            return
-        if self.visualize_env is None:
-            self.visualize_env = type(env)(name=env.name, **getattr(env, "init_kwargs", {}))
-            self.visualize_env.reset()
-        if self.do_visualize_plan == "last":
-            self.visualize_env.set_state_from_observation(obs[-1])
-            self.visualize_env.step(acts[-1])
-            self.visualize_env.render()
-        elif self.do_visualize_plan == "all":
-            self.visualize_env.set_GT_state(state)
-            reported = False
-            for i, a in enumerate(acts):
-                new_obs, *_ = self.visualize_env.step(a)
-                if i < len(obs) - 1 and np.linalg.norm(new_obs - obs[i + 1]) > 0.01 and not reported:
-                    reported = True
-                    print(f"simulation for visualization does not match mental model at {i}: ")
-                    print("orig: ", obs[i + 1])
-                    print("simu: ", new_obs)
-                self.visualize_env.render()
-                time.sleep(1.0 / 25.0)
-        else:
-            raise AttributeError("unknown mode for do_visualize_plan: Options: None, 'last','all'")
+        viewer.set_GT_state(state)
+        mismatch_at = None
+        for t, action in enumerate(acts):
+            replayed = viewer.step(action)[0]
+            if mismatch_at is None and t + 1 < len(obs) and np.linalg.norm(replayed - obs[t + 1]) > 0.01:
+                mismatch_at = t
+                print(f"simulation for visualization does not match mental model at {t}: ")
+                print("orig: ", obs[t + 1])
+                print("simu: ", replayed)
+            viewer.render()
+            time.sleep(1.0 / 25.0)
 
 
 class ForwardModel(ABC):
