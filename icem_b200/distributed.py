@@ -15,7 +15,6 @@ def default_placement():
 
 
 def broadcast_bytes(payload: bytes, src=0) -> bytes:
-    import torch
     import torch.distributed as dist
     if not dist.is_initialized():
         raise RuntimeError("torch.distributed is not initialised (launch with torchrun / call init_process_group)")

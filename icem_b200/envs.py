@@ -14,12 +14,10 @@ import math
 
 import numpy as np
 
-from . import api
-from .planner import Planner, PlannerSettings
-
 import sys as _sys
 
 from .api import forget_failed_reference_import
+from .planner import Planner, PlannerSettings
 
 _before = set(_sys.modules)
 try:   # the reference's env base class when the reference is importable (launcher), else a minimal stand-in

@@ -1,7 +1,7 @@
 """Object wrapper over one `icem_planner_t` handle (include/icem_b200.h).  Host buffers are NumPy."""
 import ctypes as C
-from dataclasses import dataclass, field
-from typing import List, Optional
+from dataclasses import dataclass
+from typing import Optional
 
 import numpy as np
 
