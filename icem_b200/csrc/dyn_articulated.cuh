@@ -33,7 +33,10 @@ constexpr int kArtMaxChildren = 4;
 constexpr int kArtMaxDepth = 8;
 constexpr int kArtMaxLevelParents = 8;
 constexpr int kArtScanRounds = 5;
+#ifndef ICEM_ART_JOINT_TYPES
+#define ICEM_ART_JOINT_TYPES
 enum { kSlide = 0, kHinge = 1, kFreeTrans = 2, kFreeRot = 3 };
+#endif
 
 // POD model tables; built on the host (planner.cu: icem_set_articulated_model), copied to shared memory per CTA.
 struct ArtModel {

@@ -1,0 +1,772 @@
+// Branch-parallel articulated-body engine: a GROUP of G lanes per trajectory, 32/G trajectories per warp.
+//
+// Same physical model and integrator as dyn_articulated.cuh / oracle/articulated_np.py (what the reference reaches
+// through `GroundTruthModel.predict_n_steps` -> `env.step` -> MuJoCo, icem/models/gt_model.py:76-102,
+// icem/environments/mujoco.py:101-131; PARITY WITH MUJOCO IS UNPINNED), different formulation:
+//
+//   dyn_articulated.cuh : one WARP per trajectory, lanes = bodies / dofs / contacts, composite-rigid-body mass matrix
+//                         + dense in-register Cholesky  (~4100 warp instructions per substep per trajectory)
+//   here                : Featherstone's articulated-body algorithm (no mass matrix, no factorisation, O(n)) on a
+//                         robot decomposed into a TRUNK chain plus up to G LIMB chains hanging off trunk bodies.
+//                         Lane g of a group walks the trunk (all lanes redundantly: the values stay bit-identical, no
+//                         exchange needed) and then ITS limb; the only cross-lane traffic per dynamics evaluation is
+//                         the sum of the limbs' articulated inertias / bias forces where they join the trunk
+//                         (27 values, xor-shuffles inside the group).  Everything is expressed in world-aligned
+//                         coordinates about a common origin O (the root position), so that child -> parent
+//                         accumulation is a plain addition.
+//
+// HumanoidStandup: trunk = torso / lwaist / pelvis (9 dofs), limbs = two arms (3 dofs) and two legs (4 dofs, the
+// jointless foot is fused into the shin): G = 4, 8 trajectories per warp, 13 sequential dof steps per lane instead
+// of 23.  HalfCheetah: trunk = torso (3 dofs), limbs = back / front leg: G = 2, 16 trajectories per warp.
+//
+// The code is __host__ __device__ and templated on an execution context (group sum + group barrier): the GPU context
+// uses warp shuffles; tests/chain_host compiles THE SAME SOURCE for the host with one thread per lane, so the engine
+// is checked against the float64 oracle without a GPU (test infrastructure only, never a product path).
+//
+// Per dynamics evaluation (q, qd, ctrl) -> qacc:
+//   pass 1 (root -> leaves): frames through the joints, motion axes S_j, velocity-product terms c_j, rigid inertia
+//                            about O, bias force v x* I v minus floor-contact wrenches; joint-space force and the
+//                            implicit spring/damper diagonal per dof
+//   pass 2 (leaves -> root): U = IA S, D = S.U + diag, u = tau - S.pA, IA -= U U^T / D, pA += IA c + U u / D;
+//                            limbs first (lanes in parallel), group sum at the junctions, then the trunk
+//   pass 3 (root -> leaves): a += c; qacc = (u - U.a) / D; a += S qacc; semi-implicit Euler on the fly
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/icem_b200.h"
+
+#ifndef __CUDACC__
+#define __host__
+#define __device__
+#define __forceinline__ inline
+#endif
+
+namespace icem {
+
+#ifndef ICEM_ART_JOINT_TYPES
+#define ICEM_ART_JOINT_TYPES
+enum { kSlide = 0, kHinge = 1, kFreeTrans = 2, kFreeRot = 3 };
+#endif
+
+constexpr int kChMaxNodes = 16, kChMaxDofs = 32, kChMaxCon = 32;
+constexpr int kChMaxTrunk = 4, kChMaxLimbs = 4, kChMaxLimbNodes = 4;
+// dof record: S(6) c(6) U/D(6) u/D(1) [rhs diag].  A limb's records belong to one lane, which parks (rhs, diag)
+// of pass 1 in the last two slots that pass 2 overwrites.  Trunk records are written by ALL lanes of the group with
+// identical values, so nothing a lane still has to read may be overwritten there: (rhs, diag) get slots of their own.
+constexpr int kChDofRec = 19, kChTrunkDofRec = 21;
+constexpr int kChNodeRec = 16;    // mass, h(3), Io(6), bias force(6)
+constexpr int kChFrame = 18;      // R(9) p(3) v(6) of a trunk body that carries limbs
+constexpr int kChJun = 27;        // articulated inertia (6 + 9 + 6) + bias force (6) summed over the limbs of a junction
+enum { kChEuler = 0, kChRK4 = 1 };
+
+// POD tables of the decomposed robot; built on the host by build_chain_model(), copied to shared memory per CTA.
+// A NODE is a body together with the jointless bodies rigidly attached below it.
+struct ChainModel {
+  int nq, nv, nu, nsub, obs_offset, integrator;
+  int n_nodes, n_trunk, n_limbs, lanes;          // lanes = G (1, 2 or 4)
+  int max_limb_nodes, trunk_dofs, max_limb_dofs, n_junctions;
+  float dt, gravity, ctrl_limit, kc, cc, kv, mu, cdmax;
+  // scratch layout in slots (group-shared region: slot * (32 / G) + group; lane-private region: slot * 32 + lane)
+  int s_state, s_origin, s_dof, s_node, s_frame, s_acc, s_jun, s_rk, s_ctrl, s_end;
+  int p_dof, p_node, p_end;
+  int trunk_node[kChMaxTrunk];
+  int trunk_junction[kChMaxTrunk];               // junction slot of this trunk position, -1 = no limb hangs here
+  int limb_attach[kChMaxLimbs];                  // trunk position the limb hangs off
+  int limb_nnodes[kChMaxLimbs];
+  int limb_node[kChMaxLimbs][kChMaxLimbNodes];
+  int n_dof_start[kChMaxNodes], n_dof_count[kChMaxNodes], n_con_start[kChMaxNodes], n_con_count[kChMaxNodes];
+  float n_pos[kChMaxNodes][3], n_mass[kChMaxNodes], n_com[kChMaxNodes][3], n_inertia[kChMaxNodes][6];
+  int d_type[kChMaxDofs], d_qadr[kChMaxDofs], d_limited[kChMaxDofs], d_act[kChMaxDofs];
+  int d_rec[kChMaxDofs];                         // record slot of the dof inside its region (trunk / own limb)
+  float d_axis[kChMaxDofs][3], d_anchor[kChMaxDofs][3];
+  float d_stiff[kChMaxDofs], d_damp[kChMaxDofs], d_arm[kChMaxDofs], d_lo[kChMaxDofs], d_hi[kChMaxDofs];
+  float d_klim[kChMaxDofs], d_blim[kChMaxDofs], d_gear[kChMaxDofs];
+  float c_pos[kChMaxCon][3], c_radius[kChMaxCon];
+};
+
+// ---- small vector helpers (registers) --------------------------------------------------------------------------
+namespace ch {
+__host__ __device__ __forceinline__ void cross(const float* a, const float* b, float* o) {
+  const float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+__host__ __device__ __forceinline__ void matvec(const float* R, const float* v, float* o) {   // R row-major 3x3
+  const float x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
+  const float y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
+  const float z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+__host__ __device__ __forceinline__ void matmul(const float* A, const float* B, float* C) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) C[r * 3 + c] = A[r * 3] * B[c] + A[r * 3 + 1] * B[3 + c] + A[r * 3 + 2] * B[6 + c];
+}
+__host__ __device__ __forceinline__ float rsqrt_(float x) {
+#ifdef __CUDA_ARCH__
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+__host__ __device__ __forceinline__ void sincos_(float x, float* s, float* c) {
+#ifdef __CUDA_ARCH__
+  sincosf(x, s, c);
+#else
+  *s = sinf(x); *c = cosf(x);
+#endif
+}
+// spatial motion cross product  [w1; v1] xm [w2; v2] = [w1 x w2 ; w1 x v2 + v1 x w2]
+__host__ __device__ __forceinline__ void cross_motion(const float* a, const float* b, float* o) {
+  float c1[3], c2[3], c3[3];
+  cross(a, b, c1);
+  cross(a, b + 3, c2);
+  cross(a + 3, b, c3);
+  o[0] = c1[0]; o[1] = c1[1]; o[2] = c1[2];
+  o[3] = c2[0] + c3[0]; o[4] = c2[1] + c3[1]; o[5] = c2[2] + c3[2];
+}
+}  // namespace ch
+
+// symmetric 6x6 articulated inertia  [[A, B], [B^T, C]]  (A, C symmetric: xx yy zz xy xz yz; B general row-major)
+struct ArtInertia {
+  float A[6], B[9], C[6];
+  __host__ __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { A[i] = 0.f; C[i] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) B[i] = 0.f;
+  }
+  // y = I x,  x = [w; v]
+  __host__ __device__ __forceinline__ void apply(const float* x, float* y) const {
+    const float* w = x;
+    const float* v = x + 3;
+    y[0] = A[0] * w[0] + A[3] * w[1] + A[4] * w[2] + B[0] * v[0] + B[1] * v[1] + B[2] * v[2];
+    y[1] = A[3] * w[0] + A[1] * w[1] + A[5] * w[2] + B[3] * v[0] + B[4] * v[1] + B[5] * v[2];
+    y[2] = A[4] * w[0] + A[5] * w[1] + A[2] * w[2] + B[6] * v[0] + B[7] * v[1] + B[8] * v[2];
+    y[3] = B[0] * w[0] + B[3] * w[1] + B[6] * w[2] + C[0] * v[0] + C[3] * v[1] + C[4] * v[2];
+    y[4] = B[1] * w[0] + B[4] * w[1] + B[7] * w[2] + C[3] * v[0] + C[1] * v[1] + C[5] * v[2];
+    y[5] = B[2] * w[0] + B[5] * w[1] + B[8] * w[2] + C[4] * v[0] + C[5] * v[1] + C[2] * v[2];
+  }
+  // I -= a b^T   with a b^T symmetric by construction (b = a / D)
+  __host__ __device__ __forceinline__ void sub_outer(const float* a, const float* b) {
+    A[0] -= a[0] * b[0]; A[1] -= a[1] * b[1]; A[2] -= a[2] * b[2];
+    A[3] -= a[0] * b[1]; A[4] -= a[0] * b[2]; A[5] -= a[1] * b[2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) B[r * 3 + c] -= a[r] * b[3 + c];
+    C[0] -= a[3] * b[3]; C[1] -= a[4] * b[4]; C[2] -= a[5] * b[5];
+    C[3] -= a[3] * b[4]; C[4] -= a[3] * b[5]; C[5] -= a[4] * b[5];
+  }
+  // rigid body: mass m, first moment h = m c, rotational inertia Io about O
+  __host__ __device__ __forceinline__ void add_rigid(float m, const float* h, const float* Io) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) A[i] += Io[i];
+    B[1] -= h[2]; B[2] += h[1]; B[3] += h[2]; B[5] -= h[0]; B[6] -= h[1]; B[7] += h[0];
+    C[0] += m; C[1] += m; C[2] += m;
+  }
+};
+
+// strided view of a record in shared memory (stride = lanes or groups per warp: conflict-free by construction)
+struct ChRef {
+  float* p;
+  int s;
+  __host__ __device__ __forceinline__ float& operator[](int i) const { return p[i * s]; }
+};
+
+// One lane of a group.  Ctx provides: group_sum(float (&x)[N]) (sum over the G lanes, identical in all of them)
+// and group_sync() (barrier + memory ordering among the lanes of the warp / group).
+template <class Ctx>
+struct ChainLane {
+  const ChainModel* M;
+  float* sh;     // group-shared region, already offset by the group index
+  int shs;       // its stride (groups per warp)
+  float* pr;     // lane-private region, already offset by the lane index
+  int prs;       // its stride (32)
+  int g;         // lane inside the group == limb index
+  Ctx* ctx;
+
+  __host__ __device__ __forceinline__ ChRef shared_rec(int slot) const { return ChRef{sh + slot * shs, shs}; }
+  __host__ __device__ __forceinline__ ChRef private_rec(int slot) const { return ChRef{pr + slot * prs, prs}; }
+  __host__ __device__ __forceinline__ float& state(int i) const { return sh[(M->s_state + i) * shs]; }
+  __host__ __device__ __forceinline__ ChRef dof_rec(bool trunk, int j) const {
+    return trunk ? shared_rec(M->s_dof + kChTrunkDofRec * M->d_rec[j])
+                 : private_rec(M->p_dof + kChDofRec * M->d_rec[j]);
+  }
+  __host__ __device__ __forceinline__ ChRef node_rec(bool trunk, int pos) const {
+    return trunk ? shared_rec(M->s_node + kChNodeRec * pos) : private_rec(M->p_node + kChNodeRec * pos);
+  }
+  // node this lane visits at position i of its sequence (trunk nodes, then its own limb); false = nothing to do
+  __host__ __device__ __forceinline__ bool node_at(int i, int& node, bool& trunk, int& pos) const {
+    const ChainModel& m = *M;
+    trunk = i < m.n_trunk;
+    if (trunk) { node = m.trunk_node[i]; pos = i; return true; }
+    pos = i - m.n_trunk;
+    if (g >= m.n_limbs || pos >= m.limb_nnodes[g]) { node = 0; return false; }
+    node = m.limb_node[g][pos];
+    return true;
+  }
+
+  // ---- pass 1 ----------------------------------------------------------------------------------------------------
+  __host__ __device__ void pass1(const ChRef& q, const ChRef& qd, const ChRef& ctrl) {
+    const ChainModel& m = *M;
+    const float dt = m.dt;
+    float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f}, p[3] = {0.f, 0.f, 0.f};
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float O[3] = {0.f, 0.f, 0.f};
+    const int n_seq = m.n_trunk + m.max_limb_nodes;
+    for (int i = 0; i < n_seq; ++i) {
+      int node, pos;
+      bool trunk;
+      const bool active = node_at(i, node, trunk, pos);
+      if (!active) continue;
+      if (!trunk && pos == 0) {      // the limb starts from the frame and velocity of the trunk body it hangs off
+        const ChRef f = shared_rec(m.s_frame + kChFrame * m.trunk_junction[m.limb_attach[g]]);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = f[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) p[k] = f[9 + k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[k] = f[12 + k];
+      }
+      const bool root = i == 0;
+      if (root) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) O[k] = m.n_pos[node][k];     // p stays 0: everything is relative to O
+      } else {
+        float off[3];
+        ch::matvec(R, m.n_pos[node], off);
+        p[0] += off[0]; p[1] += off[1]; p[2] += off[2];
+      }
+      const int j0 = m.n_dof_start[node], j1 = j0 + m.n_dof_count[node];
+      for (int j = j0; j < j1; ++j) {
+        const int t = m.d_type[j];
+        if (t == kFreeTrans) {       // free joint of the root: 3 world translations + body-frame rotations
+          const int qa = m.d_qadr[j];
+          O[0] = q[qa]; O[1] = q[qa + 1]; O[2] = q[qa + 2];
+          const float qw = q[qa + 3], x = q[qa + 4], y = q[qa + 5], z = q[qa + 6];
+          R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - qw * z); R[2] = 2.f * (x * z + qw * y);
+          R[3] = 2.f * (x * y + qw * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - qw * x);
+          R[6] = 2.f * (x * z - qw * y); R[7] = 2.f * (y * z + qw * x); R[8] = 1.f - 2.f * (x * x + y * y);
+          float qdv[6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) qdv[k] = qd[j + k];
+          // full velocity of the root: the rotation axes are body-fixed, so each moves with all of it
+          v[0] = R[0] * qdv[3] + R[1] * qdv[4] + R[2] * qdv[5];
+          v[1] = R[3] * qdv[3] + R[4] * qdv[4] + R[5] * qdv[5];
+          v[2] = R[6] * qdv[3] + R[7] * qdv[4] + R[8] * qdv[5];
+          v[3] = qdv[0]; v[4] = qdv[1]; v[5] = qdv[2];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const ChRef rt = dof_rec(true, j + k), rr = dof_rec(true, j + 3 + k);
+            float S[6] = {R[k], R[3 + k], R[6 + k], 0.f, 0.f, 0.f}, c[6];
+            ch::cross_motion(v, S, c);
+#pragma unroll
+            for (int e = 0; e < 6; ++e) {
+              rt[e] = (e == 3 + k) ? 1.f : 0.f;
+              rt[6 + e] = 0.f;
+              rr[e] = S[e];
+              rr[6 + e] = c[e] * qdv[3 + k];
+            }
+            rt[19] = -m.d_damp[j + k] * qdv[k];
+            rt[20] = m.d_arm[j + k] + dt * m.d_damp[j + k];
+            rr[19] = -m.d_damp[j + 3 + k] * qdv[3 + k];
+            rr[20] = m.d_arm[j + 3 + k] + dt * m.d_damp[j + 3 + k];
+          }
+          j += 5;
+          continue;
+        }
+        float ax[3], S[6], c[6];
+        ch::matvec(R, m.d_axis[j], ax);
+        const float qj = q[m.d_qadr[j]], qdj = qd[j];
+        if (t == kSlide) {
+          S[0] = S[1] = S[2] = 0.f;
+          S[3] = ax[0]; S[4] = ax[1]; S[5] = ax[2];
+          float* dst = root ? O : p;           // root slides move the origin itself
+          dst[0] += ax[0] * qj; dst[1] += ax[1] * qj; dst[2] += ax[2] * qj;
+        } else {
+          float an[3];
+          ch::matvec(R, m.d_anchor[j], an);
+          an[0] += p[0]; an[1] += p[1]; an[2] += p[2];
+          S[0] = ax[0]; S[1] = ax[1]; S[2] = ax[2];
+          ch::cross(an, ax, S + 3);            // velocity at O of a unit rotation about the anchored axis
+          float sn, cs;
+          ch::sincos_(qj, &sn, &cs);
+          const float C = 1.f - cs;
+          const float Rj[9] = {cs + ax[0] * ax[0] * C, ax[0] * ax[1] * C - ax[2] * sn, ax[0] * ax[2] * C + ax[1] * sn,
+                               ax[1] * ax[0] * C + ax[2] * sn, cs + ax[1] * ax[1] * C, ax[1] * ax[2] * C - ax[0] * sn,
+                               ax[2] * ax[0] * C - ax[1] * sn, ax[2] * ax[1] * C + ax[0] * sn, cs + ax[2] * ax[2] * C};
+          float Rn[9];
+          ch::matmul(Rj, R, Rn);
+#pragma unroll
+          for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+          const float dp[3] = {p[0] - an[0], p[1] - an[1], p[2] - an[2]};
+          float rp[3];
+          ch::matvec(Rj, dp, rp);
+          p[0] = an[0] + rp[0]; p[1] = an[1] + rp[1]; p[2] = an[2] + rp[2];
+        }
+        ch::cross_motion(v, S, c);             // the axis is fixed in the frame moving with v (before this joint)
+        // joint-space force and the implicit spring / damper diagonal (oracle/articulated_np.py:195-229)
+        float tau = 0.f;
+        const int act = m.d_act[j];
+        if (act >= 0) tau = m.d_gear[j] * fminf(fmaxf(ctrl[act], -m.ctrl_limit), m.ctrl_limit);
+        float keff = m.d_stiff[j], beff = m.d_damp[j];
+        tau -= keff * qj;
+        if (m.d_limited[j]) {
+          const bool below = qj < m.d_lo[j], above = qj > m.d_hi[j];
+          if (below) tau += m.d_klim[j] * (m.d_lo[j] - qj);
+          if (above) tau += m.d_klim[j] * (m.d_hi[j] - qj);
+          if (below || above) { keff += m.d_klim[j]; beff += m.d_blim[j]; }
+        }
+        const ChRef r = dof_rec(trunk, j);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) {
+          r[e] = S[e];
+          r[6 + e] = c[e] * qdj;
+          v[e] += S[e] * qdj;
+        }
+        r[trunk ? 19 : 17] = tau - (beff + dt * keff) * qdj;
+        r[trunk ? 20 : 18] = m.d_arm[j] + dt * beff + dt * dt * keff;
+      }
+      if (root) {
+        const ChRef o = shared_rec(m.s_origin);
+        o[0] = O[0]; o[1] = O[1]; o[2] = O[2];
+      }
+      if (trunk && m.trunk_junction[i] >= 0) {
+        const ChRef f = shared_rec(m.s_frame + kChFrame * m.trunk_junction[i]);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) f[k] = R[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) f[9 + k] = p[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) f[12 + k] = v[k];
+      }
+      // ---- rigid inertia about O, bias force, floor contacts ------------------------------------------------------
+      const float mass = m.n_mass[node];
+      float c[3];
+      ch::matvec(R, m.n_com[node], c);
+      c[0] += p[0]; c[1] += p[1]; c[2] += p[2];
+      const float* I6 = m.n_inertia[node];
+      const float Im[9] = {I6[0], I6[3], I6[4], I6[3], I6[1], I6[5], I6[4], I6[5], I6[2]};
+      float T[9];
+      ch::matmul(R, Im, T);
+      float Io[6];
+      const float c2 = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+      Io[0] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2] + mass * (c2 - c[0] * c[0]);
+      Io[1] = T[3] * R[3] + T[4] * R[4] + T[5] * R[5] + mass * (c2 - c[1] * c[1]);
+      Io[2] = T[6] * R[6] + T[7] * R[7] + T[8] * R[8] + mass * (c2 - c[2] * c[2]);
+      Io[3] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5] - mass * c[0] * c[1];
+      Io[4] = T[0] * R[6] + T[1] * R[7] + T[2] * R[8] - mass * c[0] * c[2];
+      Io[5] = T[3] * R[6] + T[4] * R[7] + T[5] * R[8] - mass * c[1] * c[2];
+      const float h[3] = {mass * c[0], mass * c[1], mass * c[2]};
+      // I v = [Io w + h x vl ; m vl - h x w],  bias = v x* (I v) = [w x n + vl x f ; w x f]
+      float hv[3], hw[3], Iv[6], t1[3], t2[3], t3[3], f[6];
+      ch::cross(h, v + 3, hv);
+      ch::cross(h, v, hw);
+      Iv[0] = Io[0] * v[0] + Io[3] * v[1] + Io[4] * v[2] + hv[0];
+      Iv[1] = Io[3] * v[0] + Io[1] * v[1] + Io[5] * v[2] + hv[1];
+      Iv[2] = Io[4] * v[0] + Io[5] * v[1] + Io[2] * v[2] + hv[2];
+      Iv[3] = mass * v[3] - hw[0];
+      Iv[4] = mass * v[4] - hw[1];
+      Iv[5] = mass * v[5] - hw[2];
+      ch::cross(v, Iv, t1);
+      ch::cross(v + 3, Iv + 3, t2);
+      ch::cross(v, Iv + 3, t3);
+      f[0] = t1[0] + t2[0]; f[1] = t1[1] + t2[1]; f[2] = t1[2] + t2[2];
+      f[3] = t3[0]; f[4] = t3[1]; f[5] = t3[2];
+      const int k0 = m.n_con_start[node], k1 = k0 + m.n_con_count[node];
+      for (int k = k0; k < k1; ++k) {
+        float x[3];
+        ch::matvec(R, m.c_pos[k], x);
+        x[0] += p[0]; x[1] += p[1]; x[2] += p[2];
+        const float pen = m.c_radius[k] - (O[2] + x[2]);
+        if (pen > 0.f) {
+          float u[3];
+          ch::cross(v, x, u);
+          u[0] += v[3]; u[1] += v[4]; u[2] += v[5];
+          const float spring = m.kc * pen;
+          const float damp = fminf(spring * m.cc, m.cdmax);
+          const float fn = fminf(fmaxf(spring - damp * u[2], 0.f), 3.f * spring);
+          const float speed = sqrtf(u[0] * u[0] + u[1] * u[1]);
+          const float coef = fminf(m.kv, m.mu * fn / fmaxf(speed, 1e-6f));
+          const float fc[3] = {-coef * u[0], -coef * u[1], fn};
+          float mo[3];
+          ch::cross(x, fc, mo);
+          f[0] -= mo[0]; f[1] -= mo[1]; f[2] -= mo[2];
+          f[3] -= fc[0]; f[4] -= fc[1]; f[5] -= fc[2];
+        }
+      }
+      const ChRef nr = node_rec(trunk, pos);
+      nr[0] = mass; nr[1] = h[0]; nr[2] = h[1]; nr[3] = h[2];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) { nr[4 + e] = Io[e]; nr[10 + e] = f[e]; }
+    }
+  }
+
+  // ---- pass 2 ----------------------------------------------------------------------------------------------------
+  __host__ __device__ void pass2() {
+    const ChainModel& m = *M;
+    ArtInertia IA;
+    float P[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    IA.zero();
+    const int n_seq = m.n_trunk + m.max_limb_nodes;
+    for (int i = n_seq - 1; i >= 0; --i) {
+      if (i == m.n_trunk - 1 && m.n_junctions > 0) {
+        // the limbs are done: sum them where they join the trunk (every lane gets every junction's sum)
+        const int mine = g < m.n_limbs ? m.trunk_junction[m.limb_attach[g]] : -1;
+        for (int js = 0; js < m.n_junctions; ++js) {
+          const bool w = mine == js;
+          float x[kChJun];
+#pragma unroll
+          for (int e = 0; e < 6; ++e) { x[e] = w ? IA.A[e] : 0.f; x[15 + e] = w ? IA.C[e] : 0.f; x[21 + e] = w ? P[e] : 0.f; }
+#pragma unroll
+          for (int e = 0; e < 9; ++e) x[6 + e] = w ? IA.B[e] : 0.f;
+          ctx->group_sum(x);
+          const ChRef jr = shared_rec(m.s_jun + kChJun * js);
+#pragma unroll
+          for (int e = 0; e < kChJun; ++e) jr[e] = x[e];
+        }
+        IA.zero();
+#pragma unroll
+        for (int e = 0; e < 6; ++e) P[e] = 0.f;
+      }
+      int node, pos;
+      bool trunk;
+      if (!node_at(i, node, trunk, pos)) continue;
+      {
+        const ChRef nr = node_rec(trunk, pos);
+        const float h[3] = {nr[1], nr[2], nr[3]};
+        float Io[6];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { Io[e] = nr[4 + e]; P[e] += nr[10 + e]; }
+        IA.add_rigid(nr[0], h, Io);
+      }
+      if (trunk && m.trunk_junction[i] >= 0) {
+        const ChRef jr = shared_rec(m.s_jun + kChJun * m.trunk_junction[i]);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { IA.A[e] += jr[e]; IA.C[e] += jr[15 + e]; P[e] += jr[21 + e]; }
+#pragma unroll
+        for (int e = 0; e < 9; ++e) IA.B[e] += jr[6 + e];
+      }
+      const int j0 = m.n_dof_start[node], j1 = j0 + m.n_dof_count[node];
+      for (int j = j1 - 1; j >= j0; --j) {
+        const ChRef r = dof_rec(trunk, j);
+        float S[6], c[6], U[6], Ud[6];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { S[e] = r[e]; c[e] = r[6 + e]; }
+        IA.apply(S, U);
+        float D = r[trunk ? 20 : 18], u = r[trunk ? 19 : 17];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { D += S[e] * U[e]; u -= S[e] * P[e]; }
+        const float invD = 1.f / D;
+        const float ud = u * invD;
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { Ud[e] = U[e] * invD; r[12 + e] = Ud[e]; }
+        r[18] = ud;
+        IA.sub_outer(U, Ud);
+        float Ic[6];
+        IA.apply(c, Ic);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) P[e] += Ic[e] + U[e] * ud;
+      }
+    }
+  }
+
+  // ---- pass 3: accelerations; qacc_j is handed to `sink(j, type, qacc)` in dof order ------------------------------
+  template <class Sink>
+  __host__ __device__ void pass3(Sink&& sink) {
+    const ChainModel& m = *M;
+    float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, m.gravity};     // gravity as a fictitious base acceleration
+    const int n_seq = m.n_trunk + m.max_limb_nodes;
+    for (int i = 0; i < n_seq; ++i) {
+      int node, pos;
+      bool trunk;
+      if (!node_at(i, node, trunk, pos)) continue;
+      if (!trunk && pos == 0) {
+        const ChRef ar = shared_rec(m.s_acc + 6 * m.trunk_junction[m.limb_attach[g]]);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) a[e] = ar[e];
+      }
+      const int j0 = m.n_dof_start[node], j1 = j0 + m.n_dof_count[node];
+      for (int j = j0; j < j1; ++j) {
+        const ChRef r = dof_rec(trunk, j);
+        float qacc = r[18];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { a[e] += r[6 + e]; qacc -= r[12 + e] * a[e]; }
+#pragma unroll
+        for (int e = 0; e < 6; ++e) a[e] += r[e] * qacc;
+        sink(j, trunk, qacc);
+      }
+      if (trunk && m.trunk_junction[i] >= 0) {
+        const ChRef ar = shared_rec(m.s_acc + 6 * m.trunk_junction[i]);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) ar[e] = a[e];
+      }
+    }
+  }
+
+  // q (+)= dt * qd for one dof; the quaternion of a free joint moves when its last rotation dof comes by.
+  // `qd_new` is where the updated velocities live (the three rotation rates are read back from it).
+  __host__ __device__ __forceinline__ void advance_position(int j, const ChRef& qsrc, const ChRef& qdst,
+                                                            const ChRef& qd_new, float step) const {
+    const ChainModel& m = *M;
+    const int t = m.d_type[j];
+    if (t != kFreeRot) {
+      const int qa = m.d_qadr[j];
+      qdst[qa] = qsrc[qa] + step * qd_new[j];
+      return;
+    }
+    if (j + 1 < m.nv && m.d_type[j + 1] == kFreeRot) return;
+    const int qa = m.d_qadr[j];
+    const float w0 = qd_new[j - 2], w1 = qd_new[j - 1], w2 = qd_new[j];
+    const float n = sqrtf(w0 * w0 + w1 * w1 + w2 * w2);
+    const float half = 0.5f * step * n;
+    float sn, cs;
+    ch::sincos_(half, &sn, &cs);
+    const float s = n > 1e-8f ? sn / n : 0.5f * step;
+    const float bw = cs, bx = w0 * s, by = w1 * s, bz = w2 * s;
+    const float aw = qsrc[qa], ax = qsrc[qa + 1], ay = qsrc[qa + 2], az = qsrc[qa + 3];
+    const float rw = aw * bw - ax * bx - ay * by - az * bz;
+    const float rx = aw * bx + ax * bw + ay * bz - az * by;
+    const float ry = aw * by - ax * bz + ay * bw + az * bx;
+    const float rz = aw * bz + ax * by - ay * bx + az * bw;
+    const float inv = ch::rsqrt_(rw * rw + rx * rx + ry * ry + rz * rz);
+    qdst[qa] = rw * inv; qdst[qa + 1] = rx * inv; qdst[qa + 2] = ry * inv; qdst[qa + 3] = rz * inv;
+  }
+
+  // ---- one substep, semi-implicit Euler (oracle/articulated_np.py:236-255) ---------------------------------------
+  __host__ __device__ void substep_euler(const ChRef& ctrl) {
+    const ChainModel& m = *M;
+    const ChRef q = shared_rec(m.s_state), qd = shared_rec(m.s_state + m.nq);
+    pass1(q, qd, ctrl);
+    pass2();
+    const float dt = m.dt;
+    const int gg = g;
+    const ChainLane* self = this;
+    pass3([&](int j, bool trunk, float qacc) {
+      // trunk dofs are computed by every lane of the group (identical values): lane 0 alone updates the state
+      if (trunk && gg != 0) return;
+      qd[j] = qd[j] + dt * qacc;
+      self->advance_position(j, q, q, qd, dt);
+    });
+    ctx->group_sync();
+  }
+
+  __host__ __device__ void step(const ChRef& ctrl) {
+    for (int s = 0; s < M->nsub; ++s) substep_euler(ctrl);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host side: decompose a body tree (tables as in icem_articulated_model_t) into trunk + limb chains.
+struct ChainSource {
+  int nb, nq, nv, nu, nc, nsub, obs_offset;
+  float dt, gravity, ctrl_limit, kc, cc, cdmax, kv, mu;
+  const int32_t *body_parent, *body_dof_start, *body_dof_count;
+  const float *body_pos, *body_mass, *body_com, *body_inertia;
+  const int32_t *dof_type, *dof_qadr, *dof_limited, *dof_act;
+  const float *dof_axis, *dof_anchor, *dof_stiffness, *dof_damping, *dof_armature, *dof_lo, *dof_hi, *dof_klim,
+      *dof_blim, *dof_gear;
+  const int32_t* con_body;
+  const float *con_pos, *con_radius;
+};
+
+inline ChainSource chain_source(const icem_articulated_model_t& a) {
+  ChainSource s{};
+  s.nb = a.nb; s.nq = a.nq; s.nv = a.nv; s.nu = a.nu; s.nc = a.nc; s.nsub = a.nsub; s.obs_offset = a.obs_offset;
+  s.dt = a.dt; s.gravity = a.gravity; s.ctrl_limit = a.ctrl_limit;
+  s.kc = a.contact_stiffness; s.cc = a.contact_damping; s.cdmax = a.contact_damping_max;
+  s.kv = a.friction_viscous; s.mu = a.friction;
+  s.body_parent = a.body_parent; s.body_dof_start = a.body_dof_start; s.body_dof_count = a.body_dof_count;
+  s.body_pos = a.body_pos; s.body_mass = a.body_mass; s.body_com = a.body_com; s.body_inertia = a.body_inertia;
+  s.dof_type = a.dof_type; s.dof_qadr = a.dof_qadr; s.dof_limited = a.dof_limited; s.dof_act = a.dof_act;
+  s.dof_axis = a.dof_axis; s.dof_anchor = a.dof_anchor; s.dof_stiffness = a.dof_stiffness;
+  s.dof_damping = a.dof_damping; s.dof_armature = a.dof_armature; s.dof_lo = a.dof_lo; s.dof_hi = a.dof_hi;
+  s.dof_klim = a.dof_klim; s.dof_blim = a.dof_blim; s.dof_gear = a.dof_gear;
+  s.con_body = a.con_body; s.con_pos = a.con_pos; s.con_radius = a.con_radius;
+  return s;
+}
+
+// false (with a reason) when the robot is not "one trunk chain + at most 4 limb chains": the caller falls back to the
+// warp-per-trajectory engine of dyn_articulated.cuh.
+inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, const char** why) {
+  static const char* none = "";
+  *why = none;
+  memset(&m, 0, sizeof m);
+  if (a.nb < 1 || a.nb > kChMaxNodes || a.nv > kChMaxDofs || a.nc > kChMaxCon) { *why = "too large"; return false; }
+  if (a.body_dof_count[0] < 1) { *why = "root body without joints"; return false; }
+  // ---- fuse jointless bodies into the node of their parent ---------------------------------------------------------
+  int node_of[kChMaxNodes], n_nodes = 0, primary[kChMaxNodes];
+  double off[kChMaxNodes][3];          // offset of the body frame inside its node's frame
+  for (int b = 0; b < a.nb; ++b) {
+    const int par = a.body_parent[b];
+    if (par >= b || par < -1) { *why = "bodies not parent-before-child"; return false; }
+    if (par >= 0 && a.body_dof_count[b] == 0) {
+      node_of[b] = node_of[par];
+      for (int k = 0; k < 3; ++k) off[b][k] = off[par][k] + a.body_pos[3 * b + k];
+    } else {
+      node_of[b] = n_nodes;
+      primary[n_nodes++] = b;
+      for (int k = 0; k < 3; ++k) off[b][k] = 0.0;
+    }
+  }
+  int node_parent[kChMaxNodes], n_children[kChMaxNodes] = {0};
+  for (int n = 0; n < n_nodes; ++n) {
+    const int b = primary[n], par = a.body_parent[b];
+    node_parent[n] = par < 0 ? -1 : node_of[par];
+    if (n > 0 && par < 0) { *why = "more than one root"; return false; }
+    if (node_parent[n] >= 0) n_children[node_parent[n]]++;
+    for (int k = 0; k < 3; ++k) m.n_pos[n][k] = (float)(a.body_pos[3 * b + k] + (par >= 0 ? off[par][k] : 0.0));
+    m.n_dof_start[n] = a.body_dof_start[b];
+    m.n_dof_count[n] = a.body_dof_count[b];
+  }
+  // mass properties of a node: its bodies combined about the common centre of mass (no relative rotation)
+  int n_con = 0;
+  for (int n = 0; n < n_nodes; ++n) {
+    double mass = 0, mc[3] = {0, 0, 0};
+    for (int b = 0; b < a.nb; ++b)
+      if (node_of[b] == n) {
+        mass += a.body_mass[b];
+        for (int k = 0; k < 3; ++k) mc[k] += a.body_mass[b] * (off[b][k] + a.body_com[3 * b + k]);
+      }
+    double com[3] = {mc[0] / mass, mc[1] / mass, mc[2] / mass};
+    double I[6] = {0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < a.nb; ++b)
+      if (node_of[b] == n) {
+        const double mb = a.body_mass[b];
+        double d[3];
+        for (int k = 0; k < 3; ++k) d[k] = off[b][k] + a.body_com[3 * b + k] - com[k];
+        const double d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        const float* Ib = a.body_inertia + 6 * b;
+        I[0] += Ib[0] + mb * (d2 - d[0] * d[0]);
+        I[1] += Ib[1] + mb * (d2 - d[1] * d[1]);
+        I[2] += Ib[2] + mb * (d2 - d[2] * d[2]);
+        I[3] += Ib[3] - mb * d[0] * d[1];
+        I[4] += Ib[4] - mb * d[0] * d[2];
+        I[5] += Ib[5] - mb * d[1] * d[2];
+      }
+    m.n_mass[n] = (float)mass;
+    for (int k = 0; k < 3; ++k) m.n_com[n][k] = (float)com[k];
+    for (int k = 0; k < 6; ++k) m.n_inertia[n][k] = (float)I[k];
+    m.n_con_start[n] = n_con;
+    for (int c = 0; c < a.nc; ++c) {
+      const int b = a.con_body[c];
+      if (b < 0 || b >= a.nb) { *why = "contact body out of range"; return false; }
+      if (node_of[b] != n) continue;
+      for (int k = 0; k < 3; ++k) m.c_pos[n_con][k] = (float)(off[b][k] + a.con_pos[3 * c + k]);
+      m.c_radius[n_con] = a.con_radius[c];
+      ++n_con;
+    }
+    m.n_con_count[n] = n_con - m.n_con_start[n];
+  }
+  // ---- trunk: follow the one child whose subtree branches; every other child must be a plain chain = a limb ------
+  bool is_chain[kChMaxNodes];
+  for (int n = n_nodes - 1; n >= 0; --n) {
+    is_chain[n] = n_children[n] <= 1;
+    for (int c = n + 1; c < n_nodes; ++c)
+      if (node_parent[c] == n && !is_chain[c]) is_chain[n] = false;
+  }
+  int t = 0;
+  m.n_trunk = 0;
+  m.n_limbs = 0;
+  for (int k = 0; k < kChMaxTrunk; ++k) m.trunk_junction[k] = -1;
+  while (true) {
+    if (m.n_trunk >= kChMaxTrunk) { *why = "trunk longer than 4 bodies"; return false; }
+    const int pos = m.n_trunk;
+    m.trunk_node[m.n_trunk++] = t;
+    int next = -1;
+    for (int c = t + 1; c < n_nodes; ++c) {
+      if (node_parent[c] != t) continue;
+      if (!is_chain[c]) {
+        if (next >= 0) { *why = "two branching subtrees below one body"; return false; }
+        next = c;
+        continue;
+      }
+      if (m.n_limbs >= kChMaxLimbs) { *why = "more than 4 limbs"; return false; }
+      const int l = m.n_limbs++;
+      m.limb_attach[l] = pos;
+      int cur = c, cnt = 0;
+      while (cur >= 0) {
+        if (cnt >= kChMaxLimbNodes) { *why = "limb longer than 4 bodies"; return false; }
+        m.limb_node[l][cnt++] = cur;
+        int nxt = -1;
+        for (int c2 = cur + 1; c2 < n_nodes; ++c2)
+          if (node_parent[c2] == cur) nxt = c2;
+        cur = nxt;
+      }
+      m.limb_nnodes[l] = cnt;
+      if (m.trunk_junction[pos] < 0) m.trunk_junction[pos] = m.n_junctions++;
+    }
+    if (next < 0) break;
+    t = next;
+  }
+  m.lanes = m.n_limbs <= 1 ? 1 : (m.n_limbs <= 2 ? 2 : 4);
+  // ---- dofs -----------------------------------------------------------------------------------------------------
+  for (int j = 0; j < a.nv; ++j) {
+    m.d_type[j] = a.dof_type[j]; m.d_qadr[j] = a.dof_qadr[j]; m.d_limited[j] = a.dof_limited[j];
+    m.d_act[j] = a.dof_act[j];
+    if (m.d_act[j] >= act_dim) { *why = "actuator index out of range"; return false; }
+    for (int k = 0; k < 3; ++k) { m.d_axis[j][k] = a.dof_axis[3 * j + k]; m.d_anchor[j][k] = a.dof_anchor[3 * j + k]; }
+    m.d_stiff[j] = a.dof_stiffness[j]; m.d_damp[j] = a.dof_damping[j]; m.d_arm[j] = a.dof_armature[j];
+    m.d_lo[j] = a.dof_lo[j]; m.d_hi[j] = a.dof_hi[j]; m.d_klim[j] = a.dof_klim[j]; m.d_blim[j] = a.dof_blim[j];
+    m.d_gear[j] = a.dof_gear[j];
+  }
+  m.trunk_dofs = 0;
+  for (int k = 0; k < m.n_trunk; ++k) {
+    const int n = m.trunk_node[k];
+    bool seen_hinge = false;
+    for (int j = m.n_dof_start[n]; j < m.n_dof_start[n] + m.n_dof_count[n]; ++j) {
+      m.d_rec[j] = m.trunk_dofs++;
+      const int ty = m.d_type[j];
+      if ((ty == kFreeTrans || ty == kFreeRot) && k != 0) { *why = "free joint below the root"; return false; }
+      if (k == 0 && ty == kHinge) seen_hinge = true;
+      if (k == 0 && ty == kSlide && seen_hinge) { *why = "root slide after a root hinge"; return false; }
+      if (ty == kFreeTrans && j != m.n_dof_start[n] && m.d_type[j - 1] != kFreeTrans) {
+        *why = "free joint must come first on the root";
+        return false;
+      }
+    }
+  }
+  m.max_limb_nodes = 0;
+  m.max_limb_dofs = 0;
+  for (int l = 0; l < m.n_limbs; ++l) {
+    int cnt = 0;
+    for (int k = 0; k < m.limb_nnodes[l]; ++k) {
+      const int n = m.limb_node[l][k];
+      for (int j = m.n_dof_start[n]; j < m.n_dof_start[n] + m.n_dof_count[n]; ++j) {
+        if (m.d_type[j] != kSlide && m.d_type[j] != kHinge) { *why = "free joint on a limb"; return false; }
+        m.d_rec[j] = cnt++;
+      }
+    }
+    m.max_limb_dofs = cnt > m.max_limb_dofs ? cnt : m.max_limb_dofs;
+    m.max_limb_nodes = m.limb_nnodes[l] > m.max_limb_nodes ? m.limb_nnodes[l] : m.max_limb_nodes;
+  }
+  m.nq = a.nq; m.nv = a.nv; m.nu = a.nu; m.nsub = a.nsub; m.obs_offset = a.obs_offset; m.n_nodes = n_nodes;
+  m.integrator = kChEuler;
+  m.dt = a.dt; m.gravity = a.gravity; m.ctrl_limit = a.ctrl_limit;
+  m.kc = a.kc; m.cc = a.cc; m.kv = a.kv; m.mu = a.mu; m.cdmax = a.cdmax;
+  // ---- scratch layout ---------------------------------------------------------------------------------------------
+  int s = 0;
+  m.s_state = s; s += m.nq + m.nv;
+  m.s_origin = s; s += 3;
+  m.s_ctrl = s; s += 2 * act_dim;                  // the staged actions of the current / next control step
+  m.s_dof = s; s += kChTrunkDofRec * m.trunk_dofs;
+  m.s_node = s; s += kChNodeRec * m.n_trunk;
+  m.s_acc = s; s += 6 * m.n_junctions;
+  m.s_frame = s;                                   // frames are dead once pass 1 is over: the junction sums alias them
+  m.s_jun = s; s += kChJun * m.n_junctions;
+  m.s_rk = s;
+  m.s_end = s;
+  int p = 0;
+  m.p_dof = p; p += kChDofRec * m.max_limb_dofs;
+  m.p_node = p; p += kChNodeRec * m.max_limb_nodes;
+  m.p_end = p;
+  return true;
+}
+
+// floats of scratch one warp needs (group-shared region + lane-private region)
+inline int chain_warp_floats(const ChainModel& m) { return m.s_end * (32 / m.lanes) + m.p_end * 32; }
+
+}  // namespace icem

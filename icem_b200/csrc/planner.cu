@@ -9,7 +9,9 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 #include "../../include/icem_b200.h"
@@ -21,6 +23,7 @@
 #include "mlp_rollout_2cta.cuh"
 #include "sampler.cuh"
 #include "rollout.cuh"
+#include "rollout_chain.cuh"
 #include "select_refit.cuh"
 
 namespace icem {
@@ -133,6 +136,12 @@ struct icem_planner {
   bool model_ready = false;
   Articulated<32>::Params art{};      // Params is layout-identical for every NVMAX instantiation
   DevBuf<ArtModel> art_model;
+  // branch-parallel engine (dyn_chain.cuh): used whenever the robot decomposes into trunk + limb chains
+  bool chain_ok = false;
+  bool force_warp_engine = false;     // ICEM_B200_ENGINE=warp at icem_create: A/B the two engines (tests, profiles)
+  ChainModel chain_host{};
+  DevBuf<ChainModel> chain_model;
+  ChainParams chain{};
   MlpParams mlp{};
   DevBuf<__nv_bfloat16> mlp_w1, mlp_w2, mlp_w3;
   DevBuf<__nv_bfloat16> mlp_half[2][3];  // per-CTA halves of the packed weights for the cta_group::2 kernel
@@ -272,6 +281,20 @@ static typename Articulated<NVMAX>::Params art_params(icem_planner* p) {
   return q;
 }
 
+// function attributes are per device: remember per (kernel, device) what was configured
+template <class K>
+static void ensure_dynamic_smem(K kern, size_t smem, int device) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> configured;
+  if (smem <= 48 * 1024) return;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = configured[{reinterpret_cast<const void*>(kern), device}];
+  if (smem > have) {
+    ICEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    have = smem;
+  }
+}
+
 template <class Dyn, bool kSample, bool kRollout, bool kNextObs = false>
 static void launch_rollout_impl(icem_planner* p, const RolloutArgs& a, const typename Dyn::Params& dp, int rows_max) {
   const SamplerConst sc = sampler_const(p);
@@ -279,11 +302,7 @@ static void launch_rollout_impl(icem_planner* p, const RolloutArgs& a, const typ
   const int warps = Dyn::kWarpsPerCta;
   const size_t smem = rollout_smem_bytes<Dyn, kSample>(sc, dp, a.stride, warps);
   auto kern = rollout_kernel<Dyn, kSample, kRollout, kNextObs>;
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    ICEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  ensure_dynamic_smem(kern, smem, p->cfg.device);
   int occ = 0;
   ICEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
   if (occ < 1) throw InvalidArg("rollout kernel does not fit on an SM (shared memory)");
@@ -318,11 +337,7 @@ static void launch_mlp(icem_planner* p, const RolloutArgs& a, int rows_max) {
   // MUFU work (8.8 k) and the remaining gaps (3-4 k) do not close without a deeper software pipeline.
   if (p->mlp_use_2cta && p->cfg.cost_along_trajectory == ICEM_REDUCE_SUM) {
     const size_t smem = mlp2_smem_bytes(p->mlp.hidden);
-    static thread_local size_t configured2 = 0;
-    if (smem > configured2) {
-      ICEM_CUDA(cudaFuncSetAttribute(mlp_rollout_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured2 = smem;
-    }
+    ensure_dynamic_smem(mlp_rollout_2cta_kernel, smem, p->cfg.device);
     const int super_tiles = (rows_max + kMlp2SuperTile - 1) / kMlp2SuperTile;
     const int clusters = std::max(1, std::min(super_tiles, p->sm_count / 2));
     mlp_rollout_2cta_kernel<<<2 * clusters, kMlpThreads, smem, p->stream>>>(a, sc, cc, p->mlp, p->mlp_halves);
@@ -331,11 +346,7 @@ static void launch_mlp(icem_planner* p, const RolloutArgs& a, int rows_max) {
     return;
   }
   const size_t smem = mlp_smem_bytes(p->mlp.hidden);
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
-    ICEM_CUDA(cudaFuncSetAttribute(mlp_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  ensure_dynamic_smem(mlp_rollout_kernel, smem, p->cfg.device);
   const int tiles = (rows_max + kMlpTile - 1) / kMlpTile;
   const int grid = std::max(1, std::min(tiles, p->sm_count));     // one resident CTA per SM (weights fill smem)
   mlp_rollout_kernel<<<grid, kMlpThreads, smem, p->stream>>>(a, sc, cc, p->mlp);
@@ -355,11 +366,7 @@ static void launch_series_sampler_k(icem_planner* p, const RolloutArgs& a, int r
   const int R = sampler_rows_per_batch(p->d, a.stride);
   const size_t smem = sampler_smem_bytes(p->h, p->d, KPAD, a.stride, R);
   auto kern = colored_sampler_kernel<KPAD>;
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    ICEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  ensure_dynamic_smem(kern, smem, p->cfg.device);
   int occ = 0;
   ICEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSamplerThreads, smem));
   if (occ < 1) throw InvalidArg("sampler kernel does not fit on an SM (shared memory)");
@@ -374,6 +381,49 @@ static void launch_series_sampler(icem_planner* p, const RolloutArgs& a, int row
   if (p->K <= 8) launch_series_sampler_k<8>(p, a, rows_max);
   else if (p->K <= 16) launch_series_sampler_k<16>(p, a, rows_max);
   else launch_series_sampler_k<32>(p, a, rows_max);
+}
+
+constexpr size_t kMaxSmemPerCta = 227 * 1024;
+
+template <int G, bool kSample, bool kRollout, bool kNextObs>
+static void launch_chain_impl(icem_planner* p, const RolloutArgs& a, int rows_max) {
+  const SamplerConst sc = sampler_const(p);
+  const CostConst cc = cost_const(p);
+  ChainParams dp = p->chain;
+  const int nprob = a.prob_actions ? p->B : 1;      // operator launches carry no problem strides
+  const int trips = (rows_max + dp.rows_per_warp - 1) / dp.rows_per_warp;
+  // warps per CTA: as many as shared memory holds (one CTA per SM), but no more than it takes to give every SM work
+  int wmax = 8;
+  while (wmax > 1 && chain_rollout_smem_bytes<kSample>(sc, dp, a.stride, wmax) > kMaxSmemPerCta) --wmax;
+  const int sms = std::max(1, p->sm_count / nprob);
+  const int warps = std::max(1, std::min(wmax, (trips + sms - 1) / sms));
+  const size_t smem = chain_rollout_smem_bytes<kSample>(sc, dp, a.stride, warps);
+  if (smem > kMaxSmemPerCta) throw InvalidArg("chain rollout kernel does not fit on an SM (shared memory)");
+  auto kern = chain_rollout_kernel<G, kSample, kRollout, kNextObs>;
+  ensure_dynamic_smem(kern, chain_rollout_smem_bytes<kSample>(sc, dp, a.stride, wmax), p->cfg.device);
+  const int grid = std::max(1, std::min((trips + warps - 1) / warps, sms));
+  kern<<<dim3(grid, nprob), warps * 32, smem, p->stream>>>(a, sc, cc, dp);
+  ICEM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+template <int G, bool kSample, bool kRollout>
+static void launch_chain_g(icem_planner* p, const RolloutArgs& a, int rows_max) {
+  if (p->cfg.cost == ICEM_COST_LOCOMOTION) {
+    if constexpr (kRollout) launch_chain_impl<G, kSample, true, true>(p, a, rows_max);
+    else launch_chain_impl<G, kSample, false, false>(p, a, rows_max);
+  } else {
+    launch_chain_impl<G, kSample, kRollout, false>(p, a, rows_max);
+  }
+}
+
+template <bool kSample, bool kRollout>
+static void launch_chain(icem_planner* p, const RolloutArgs& a, int rows_max) {
+  switch (p->chain_host.lanes) {
+    case 1: launch_chain_g<1, kSample, kRollout>(p, a, rows_max); break;
+    case 2: launch_chain_g<2, kSample, kRollout>(p, a, rows_max); break;
+    default: launch_chain_g<4, kSample, kRollout>(p, a, rows_max); break;
+  }
 }
 
 template <bool kSample, bool kRollout>
@@ -401,7 +451,9 @@ static void launch_rollout_dyn(icem_planner* p, const RolloutArgs& a, int rows_m
     case ICEM_DYN_HALFCHEETAH:
     case ICEM_DYN_HUMANOID_STANDUP:
     case ICEM_DYN_ARTICULATED:
-      if (Articulated<12>::fits(p->art.nb, p->art.nv, p->art.nc))
+      if (p->chain_ok)
+        launch_chain<kSample, kRollout>(p, a, rows_max);
+      else if (Articulated<12>::fits(p->art.nb, p->art.nv, p->art.nc))
         launch_rollout<Articulated<12>, kSample, kRollout>(p, a, art_params<12>(p), rows_max);
       else if (Articulated<24>::fits(p->art.nb, p->art.nv, p->art.nc))
         launch_rollout<Articulated<24>, kSample, kRollout>(p, a, art_params<24>(p), rows_max);
@@ -580,7 +632,19 @@ static void advance_dyn(icem_planner* p, float* state, const float* action, floa
     case ICEM_DYN_HALFCHEETAH:
     case ICEM_DYN_HUMANOID_STANDUP:
     case ICEM_DYN_ARTICULATED:
-      if (Articulated<12>::fits(p->art.nb, p->art.nv, p->art.nc))
+      if (p->chain_ok) {
+        const size_t smem = ((((sizeof(ChainModel) / 4) + 3) & ~(size_t)3) + p->chain.warp_floats + 4) * sizeof(float);
+        auto launch = [&](auto kern) {
+          ensure_dynamic_smem(kern, smem, p->cfg.device);
+          kern<<<batch, 32, smem, p->stream>>>(p->chain, state, action, next_state, obs_out, obs_dim, ab.state_stride,
+                                               ab.action_stride, ab.obs_stride);
+        };
+        if (p->chain_host.lanes == 1) launch(chain_advance_kernel<1>);
+        else if (p->chain_host.lanes == 2) launch(chain_advance_kernel<2>);
+        else launch(chain_advance_kernel<4>);
+        ICEM_CUDA(cudaGetLastError());
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+      } else if (Articulated<12>::fits(p->art.nb, p->art.nv, p->art.nc))
         launch_advance<Articulated<12>>(p, art_params<12>(p), state, action, next_state, obs_out, obs_dim, batch, ab);
       else if (Articulated<24>::fits(p->art.nb, p->art.nv, p->art.nc))
         launch_advance<Articulated<24>>(p, art_params<24>(p), state, action, next_state, obs_out, obs_dim, batch, ab);
@@ -767,6 +831,7 @@ int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
   p->white = cem_std || rnd || !(cfg->noise_beta > 0);
   { const char* e = getenv("ICEM_B200_WARP_SAMPLER"); p->force_warp_sampler = e && e[0] == '1'; }
   { const char* e = getenv("ICEM_B200_MLP_2CTA"); p->mlp_use_2cta = e && e[0] == '1'; }
+  { const char* e = getenv("ICEM_B200_ENGINE"); p->force_warp_engine = e && strcmp(e, "warp") == 0; }
   p->low.assign(cfg->action_low, cfg->action_low + p->d);
   p->high.assign(cfg->action_high, cfg->action_high + p->d);
   p->cfg.action_low = p->low.data();
@@ -1000,6 +1065,18 @@ int icem_set_articulated_model(icem_planner_t* p, const icem_articulated_model_t
   }
   p->art_model.alloc(1);
   ICEM_CUDA(cudaMemcpy(p->art_model.p, &m, sizeof m, cudaMemcpyHostToDevice));
+  {
+    const char* why = "";
+    p->chain_ok = !p->force_warp_engine && build_chain_model(chain_source(*a), p->d, p->chain_host, &why);
+    if (p->chain_ok) {
+      p->chain_model.alloc(1);
+      ICEM_CUDA(cudaMemcpy(p->chain_model.p, &p->chain_host, sizeof(ChainModel), cudaMemcpyHostToDevice));
+      p->chain.model = p->chain_model.p;
+      p->chain.act_dim = p->d;
+      p->chain.warp_floats = chain_warp_floats(p->chain_host);
+      p->chain.rows_per_warp = 32 / p->chain_host.lanes;
+    }
+  }
   p->art.model = p->art_model.p;
   p->art.act_dim = p->d; p->art.nq = m.nq; p->art.nv = m.nv; p->art.nb = m.nb; p->art.nc = m.nc;
   p->state_dim = m.nq + m.nv;

@@ -175,6 +175,85 @@ __device__ __forceinline__ void fill_normals(float* dst, int count, uint32_t gro
   }
 }
 
+// One trajectory row of the population -> its action tile [h][d] in shared memory (the whole warp works on the row):
+// unit normals (Philox, or the injected parity draws), colored-noise synthesis + affine + clip, mean row, shifted
+// elites; the truncated-normal (MpcCemStd) and uniform (MpcRandom) samplers.  `z` is per-warp scratch of d * (2K + 1)
+// floats (unused for white noise); G / mean / std / low / high are the CTA's shared-memory copies.
+__device__ __forceinline__ void sample_row_tile(const RolloutArgs& a, const SamplerConst& sc, unsigned long long pr,
+                                                int row, float* tile, float* w_z, const float* s_G,
+                                                const float* s_mean, const float* s_std, const float* s_low,
+                                                const float* s_high) {
+  const int lane = threadIdx.x & 31;
+  const int h = sc.h, d = sc.d, hd = h * d;
+  const int K2 = 2 * sc.K, gs = K2 + 1, zs = K2 + 1;
+  const int tile_floats = a.stride;
+  // re-read per row (an L1 hit) rather than held in registers across the rollout loop
+  const uint32_t ss_step = a.ss->step;
+  const bool ss_inject = a.ss->inject != 0;
+  const bool shifted = row >= a.n_fresh_local;
+  // global trajectory index: fresh rows are contiguous per rank, shifted rows follow N_i
+  const uint32_t grow = shifted ? (uint32_t)(a.n_fresh_global + (row - a.n_fresh_local))
+                                : (uint32_t)(a.global_offset + row);
+        // ---- 1. unit normals ----
+        float* zdst = sc.white ? tile : w_z;
+        const int count = sc.white ? hd : d * K2;
+        if (ss_inject) {
+          if (sc.white) {
+            const float* src = a.inj_zr + (size_t)row * hd;
+            for (int i = lane; i < hd; i += 32) tile[i] = src[i];
+          } else {
+            const int dK = d * sc.K;
+            const float* sr = a.inj_zr + (size_t)row * dK;
+            const float* si = a.inj_zi + (size_t)row * dK;
+            for (int i = lane; i < dK; i += 32) {
+              const int dim = (int)__umulhi((uint32_t)i, sc.magic_K), k = i - dim * sc.K;
+              w_z[dim * zs + k] = sr[i];
+              w_z[dim * zs + sc.K + k] = si[i];
+            }
+          }
+        } else if (sc.rnd_freq < 0) {
+          fill_normals(zdst, count, grow, a, (uint32_t)pr, ss_step, K2, zs, sc.white, sc.trunc != 0, sc.magic_K);
+        }
+        __syncwarp();
+        // ---- 2. synthesis + affine + clip (icem.py:73-79), elite shift (icem.py:91-104), mean row ----
+        const bool mean_row = a.inject_mean_row0 && grow == 0u && !shifted;
+        const float* elite = shifted ? (a.prev_elites + pr * (unsigned)a.prob_elites) + (size_t)(row - a.n_fresh_local) * a.stride : nullptr;
+        for (int o = lane; o < hd; o += 32) {
+          const int t = (int)__umulhi((uint32_t)o, sc.magic_d), dim = o - t * d;
+          if (sc.rnd_freq >= 0) {      // MpcRandom: piecewise-constant uniform actions
+            const float u = ss_inject ? tile[o]
+                                      : random_shooting_uniform(a.ss->plans_total, sc.n_global, grow, h, t, dim, sc.rnd_freq,
+                                                                a.seed_lo, a.seed_hi, (uint32_t)pr);
+            tile[o] = fminf(fmaf(s_high[dim] - s_low[dim], u, s_low[dim]), s_high[dim]);   // Box.sample (gym)
+            continue;
+          }
+          if (sc.trunc) {       // MpcCemStd: mean + std * truncnorm.ppf(u; lower, upper), no clip (mpc.py:194-198, 290-301)
+            const float sd = s_std[o], mu = s_mean[o];
+            const float lo_ = sc.levine ? -2.f : (s_low[dim] - mu) / (sd + 1e-8f);
+            const float hi_ = sc.levine ? 2.f : (s_high[dim] - mu) / (sd + 1e-8f);
+            tile[o] = fmaf(sd, truncnorm_ppf(tile[o], lo_, hi_), mu);
+            continue;
+          }
+          float y;
+          if (sc.white) {
+            y = tile[o];
+          } else {
+            const float* g = s_G + t * gs;
+            const float* z = w_z + dim * zs;
+            float acc = 0.f;
+  #pragma unroll 8
+            for (int j = 0; j < K2; ++j) acc = fmaf(g[j], z[j], acc);
+            y = acc;
+          }
+          float v = fminf(fmaxf(fmaf(y, s_std[o], s_mean[o]), s_low[dim]), s_high[dim]);
+          if (mean_row) v = s_mean[o];
+          if (shifted && t < h - 1) v = elite[o + d];
+          tile[o] = v;
+        }
+        for (int o = hd + lane; o < tile_floats; o += 32) tile[o] = 0.f;   // row padding
+        __syncwarp();
+}
+
 // The rollout of ONE trajectory, out of line on purpose: across the call nothing of the kernel's outer loops
 // (sampler pointers, row bookkeeping, TMA state) stays in registers, so the dynamics code gets the whole register
 // budget of 80.  Measured on B200: HumanoidStandup 34.5 -> 31.6 ms per plan step (+9 %), HalfCheetah +3 %.
@@ -311,74 +390,10 @@ rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, typename Dyn::Param
     }
     float* tile = w_tile;
     if (kSample) {
-      // re-read per row (an L1 hit) rather than held in registers across the rollout loop
-      const uint32_t ss_step = a.ss->step;
-      const bool ss_inject = a.ss->inject != 0;
-      const bool shifted = row >= a.n_fresh_local;
-      // global trajectory index: fresh rows are contiguous per rank, shifted rows follow N_i
-      const uint32_t grow = shifted ? (uint32_t)(a.n_fresh_global + (row - a.n_fresh_local))
-                                    : (uint32_t)(a.global_offset + row);
       // the previous trajectory's bulk store must have finished READING the tile
       if (lane == 0) tma_store_wait_read();
       __syncwarp();
-      // ---- 1. unit normals ----
-      float* zdst = sc.white ? tile : w_z;
-      const int count = sc.white ? hd : d * K2;
-      if (ss_inject) {
-        if (sc.white) {
-          const float* src = a.inj_zr + (size_t)row * hd;
-          for (int i = lane; i < hd; i += 32) tile[i] = src[i];
-        } else {
-          const int dK = d * sc.K;
-          const float* sr = a.inj_zr + (size_t)row * dK;
-          const float* si = a.inj_zi + (size_t)row * dK;
-          for (int i = lane; i < dK; i += 32) {
-            const int dim = (int)__umulhi((uint32_t)i, sc.magic_K), k = i - dim * sc.K;
-            w_z[dim * zs + k] = sr[i];
-            w_z[dim * zs + sc.K + k] = si[i];
-          }
-        }
-      } else if (sc.rnd_freq < 0) {
-        fill_normals(zdst, count, grow, a, (uint32_t)pr, ss_step, K2, zs, sc.white, sc.trunc != 0, sc.magic_K);
-      }
-      __syncwarp();
-      // ---- 2. synthesis + affine + clip (icem.py:73-79), elite shift (icem.py:91-104), mean row ----
-      const bool mean_row = a.inject_mean_row0 && grow == 0u && !shifted;
-      const float* elite = shifted ? ICEM_P_ELITES + (size_t)(row - a.n_fresh_local) * a.stride : nullptr;
-      for (int o = lane; o < hd; o += 32) {
-        const int t = (int)__umulhi((uint32_t)o, sc.magic_d), dim = o - t * d;
-        if (sc.rnd_freq >= 0) {      // MpcRandom: piecewise-constant uniform actions
-          const float u = ss_inject ? tile[o]
-                                    : random_shooting_uniform(a.ss->plans_total, sc.n_global, grow, h, t, dim, sc.rnd_freq,
-                                                              a.seed_lo, a.seed_hi, (uint32_t)pr);
-          tile[o] = fminf(fmaf(s_high[dim] - s_low[dim], u, s_low[dim]), s_high[dim]);   // Box.sample (gym)
-          continue;
-        }
-        if (sc.trunc) {       // MpcCemStd: mean + std * truncnorm.ppf(u; lower, upper), no clip (mpc.py:194-198, 290-301)
-          const float sd = s_std[o], mu = s_mean[o];
-          const float lo_ = sc.levine ? -2.f : (s_low[dim] - mu) / (sd + 1e-8f);
-          const float hi_ = sc.levine ? 2.f : (s_high[dim] - mu) / (sd + 1e-8f);
-          tile[o] = fmaf(sd, truncnorm_ppf(tile[o], lo_, hi_), mu);
-          continue;
-        }
-        float y;
-        if (sc.white) {
-          y = tile[o];
-        } else {
-          const float* g = s_G + t * gs;
-          const float* z = w_z + dim * zs;
-          float acc = 0.f;
-#pragma unroll 8
-          for (int j = 0; j < K2; ++j) acc = fmaf(g[j], z[j], acc);
-          y = acc;
-        }
-        float v = fminf(fmaxf(fmaf(y, s_std[o], s_mean[o]), s_low[dim]), s_high[dim]);
-        if (mean_row) v = s_mean[o];
-        if (shifted && t < h - 1) v = elite[o + d];
-        tile[o] = v;
-      }
-      for (int o = hd + lane; o < tile_floats; o += 32) tile[o] = 0.f;   // row padding
-      __syncwarp();
+      sample_row_tile(a, sc, pr, row, tile, w_z, s_G, s_mean, s_std, s_low, s_high);
       // ---- 3. ship the tile: one TMA bulk store, overlapped with the rollout ----
       fence_proxy_async_smem();
       __syncwarp();
