@@ -76,6 +76,7 @@ struct ChainModel {
   int limb_attach[kChMaxLimbs];                  // trunk position the limb hangs off
   int limb_nnodes[kChMaxLimbs];
   int limb_node[kChMaxLimbs][kChMaxLimbNodes];
+  int seq_node[kChMaxLimbs][kChMaxTrunk + kChMaxLimbNodes];   // node lane g visits at position i of its walk, -1 = none
   int n_dof_start[kChMaxNodes], n_dof_count[kChMaxNodes], n_con_start[kChMaxNodes], n_con_count[kChMaxNodes];
   float n_pos[kChMaxNodes][3], n_mass[kChMaxNodes], n_com[kChMaxNodes][3], n_inertia[kChMaxNodes][6];
   int d_type[kChMaxDofs], d_qadr[kChMaxDofs], d_limited[kChMaxDofs], d_act[kChMaxDofs];
@@ -169,28 +170,38 @@ struct ArtInertia {
   }
 };
 
-// strided view of a record in shared memory (stride = lanes or groups per warp: conflict-free by construction)
-struct ChRef {
+// strided view of a record in shared memory; the stride (trajectories per warp on the GPU, 1 on the host) is a
+// compile-time constant so that record fields are immediate offsets of ONE base address
+template <int STRIDE>
+struct ChRefT {
   float* p;
-  int s;
-  __host__ __device__ __forceinline__ float& operator[](int i) const { return p[i * s]; }
+  __host__ __device__ __forceinline__ float& operator[](int i) const { return p[i * STRIDE]; }
 };
+
+__host__ __device__ __forceinline__ float ch_rcp(float x) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
 
 // One lane of a group.  Ctx provides: group_sum(float (&x)[N]) (sum over the G lanes, identical in all of them)
 // and group_sync() (barrier + memory ordering among the lanes of the warp / group).
-template <class Ctx>
+template <class Ctx, int STRIDE>
 struct ChainLane {
+  typedef ChRefT<STRIDE> ChRef;
   const ChainModel* M;
-  float* sh;     // group-shared region, already offset by the group index
-  int shs;       // its stride (groups per warp)
-  float* pr;     // lane-private region, already offset by the lane index
-  int prs;       // its stride (32)
+  float* sh;     // group-shared region, already offset by the group index; slot i lives at sh[i * STRIDE]
+  float* pr;     // lane-private region, already offset for this lane; same stride
   int g;         // lane inside the group == limb index
   Ctx* ctx;
 
-  __host__ __device__ __forceinline__ ChRef shared_rec(int slot) const { return ChRef{sh + slot * shs, shs}; }
-  __host__ __device__ __forceinline__ ChRef private_rec(int slot) const { return ChRef{pr + slot * prs, prs}; }
-  __host__ __device__ __forceinline__ float& state(int i) const { return sh[(M->s_state + i) * shs]; }
+  __host__ __device__ __forceinline__ ChRef shared_rec(int slot) const { return ChRef{sh + slot * STRIDE}; }
+  __host__ __device__ __forceinline__ ChRef private_rec(int slot) const { return ChRef{pr + slot * STRIDE}; }
+  __host__ __device__ __forceinline__ float& state(int i) const { return sh[(M->s_state + i) * STRIDE]; }
   __host__ __device__ __forceinline__ ChRef dof_rec(bool trunk, int j) const {
     return trunk ? shared_rec(M->s_dof + kChTrunkDofRec * M->d_rec[j])
                  : private_rec(M->p_dof + kChDofRec * M->d_rec[j]);
@@ -202,11 +213,9 @@ struct ChainLane {
   __host__ __device__ __forceinline__ bool node_at(int i, int& node, bool& trunk, int& pos) const {
     const ChainModel& m = *M;
     trunk = i < m.n_trunk;
-    if (trunk) { node = m.trunk_node[i]; pos = i; return true; }
-    pos = i - m.n_trunk;
-    if (g >= m.n_limbs || pos >= m.limb_nnodes[g]) { node = 0; return false; }
-    node = m.limb_node[g][pos];
-    return true;
+    pos = trunk ? i : i - m.n_trunk;
+    node = m.seq_node[g][i];
+    return node >= 0;
   }
 
   // ---- pass 1 ----------------------------------------------------------------------------------------------------
@@ -390,7 +399,7 @@ struct ChainLane {
           const float damp = fminf(spring * m.cc, m.cdmax);
           const float fn = fminf(fmaxf(spring - damp * u[2], 0.f), 3.f * spring);
           const float speed = sqrtf(u[0] * u[0] + u[1] * u[1]);
-          const float coef = fminf(m.kv, m.mu * fn / fmaxf(speed, 1e-6f));
+          const float coef = fminf(m.kv, m.mu * fn * ch_rcp(fmaxf(speed, 1e-6f)));
           const float fc[3] = {-coef * u[0], -coef * u[1], fn};
           float mo[3];
           ch::cross(x, fc, mo);
@@ -460,7 +469,7 @@ struct ChainLane {
         float D = r[trunk ? 20 : 18], u = r[trunk ? 19 : 17];
 #pragma unroll
         for (int e = 0; e < 6; ++e) { D += S[e] * U[e]; u -= S[e] * P[e]; }
-        const float invD = 1.f / D;
+        const float invD = ch_rcp(D);
         const float ud = u * invD;
 #pragma unroll
         for (int e = 0; e < 6; ++e) { Ud[e] = U[e] * invD; r[12 + e] = Ud[e]; }
@@ -525,7 +534,7 @@ struct ChainLane {
     const float half = 0.5f * step * n;
     float sn, cs;
     ch::sincos_(half, &sn, &cs);
-    const float s = n > 1e-8f ? sn / n : 0.5f * step;
+    const float s = n > 1e-8f ? sn * ch_rcp(n) : 0.5f * step;
     const float bw = cs, bx = w0 * s, by = w1 * s, bz = w2 * s;
     const float aw = qsrc[qa], ax = qsrc[qa + 1], ay = qsrc[qa + 2], az = qsrc[qa + 3];
     const float rw = aw * bw - ax * bx - ay * by - az * bz;
@@ -703,6 +712,13 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
     t = next;
   }
   m.lanes = m.n_limbs <= 1 ? 1 : (m.n_limbs <= 2 ? 2 : 4);
+  for (int g = 0; g < kChMaxLimbs; ++g)
+    for (int i = 0; i < kChMaxTrunk + kChMaxLimbNodes; ++i) {
+      int node = -1;
+      if (i < m.n_trunk) node = m.trunk_node[i];
+      else if (g < m.n_limbs && i - m.n_trunk < m.limb_nnodes[g]) node = m.limb_node[g][i - m.n_trunk];
+      m.seq_node[g][i] = node;
+    }
   // ---- dofs -----------------------------------------------------------------------------------------------------
   for (int j = 0; j < a.nv; ++j) {
     m.d_type[j] = a.dof_type[j]; m.d_qadr[j] = a.dof_qadr[j]; m.d_limited[j] = a.dof_limited[j];
@@ -766,7 +782,17 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
   return true;
 }
 
-// floats of scratch one warp needs (group-shared region + lane-private region)
-inline int chain_warp_floats(const ChainModel& m) { return m.s_end * (32 / m.lanes) + m.p_end * 32; }
+// Scratch of one warp: the group-shared region ([slot][group]) followed by one lane-private region per lane index g
+// inside the group ([g][slot][group]); each private region is padded so that the G regions start 32 / G banks apart
+// (all 32 lanes of the warp then hit 32 different banks when they touch the same slot).
+__host__ __device__ inline int chain_private_region_floats(int p_end, int lanes) {
+  const int ng = 32 / lanes;
+  int f = p_end * ng;
+  while ((f & 31) != (ng & 31)) ++f;
+  return f;
+}
+inline int chain_warp_floats(const ChainModel& m) {
+  return m.s_end * (32 / m.lanes) + m.lanes * chain_private_region_floats(m.p_end, m.lanes);
+}
 
 }  // namespace icem

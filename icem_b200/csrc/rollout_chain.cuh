@@ -47,8 +47,24 @@ struct ChainParams {
 constexpr int kChainPrefetch = 5;     // controls per lane fetched one step ahead (covers d <= 5 G)
 
 template <int G>
-__device__ __forceinline__ float chain_step_cost_pre(const CostConst& cc, const ChainLane<WarpGroupCtx<G>>& L,
-                                                     const ChRef& act, int d, bool next_obs) {
+using ChainWarpLane = ChainLane<WarpGroupCtx<G>, 32 / G>;
+
+// lane-private scratch of lane g of a group: region g behind the group-shared region (see chain_warp_floats)
+template <int G>
+__device__ __forceinline__ void chain_bind_lane(ChainWarpLane<G>& L, const ChainModel& m, float* w_base, int lane,
+                                                WarpGroupCtx<G>* ctx) {
+  constexpr int NG = 32 / G;
+  const int grp = lane / G;
+  L.M = &m;
+  L.g = lane % G;
+  L.sh = w_base + grp;
+  L.pr = w_base + m.s_end * NG + L.g * chain_private_region_floats(m.p_end, G) + grp;
+  L.ctx = ctx;
+}
+
+template <int G>
+__device__ __forceinline__ float chain_step_cost_pre(const CostConst& cc, const ChainWarpLane<G>& L,
+                                                     const typename ChainWarpLane<G>::ChRef& act, int d, bool next_obs) {
   const ChainModel& m = *L.M;
   float a2 = 0.f;
   for (int k = 0; k < d; ++k) a2 = fmaf(act[k], act[k], a2);
@@ -130,13 +146,10 @@ chain_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, ChainParams d
   const uint32_t tile_bytes = (uint32_t)tile_floats * 4u;
 
   WarpGroupCtx<G> ctx;
-  ChainLane<WarpGroupCtx<G>> L;
+  ChainWarpLane<G> L;
+  typedef typename ChainWarpLane<G>::ChRef ChRef;
   const int grp = lane / G;
-  L.M = &m;
-  L.sh = w_base + grp; L.shs = NG;
-  L.pr = w_base + m.s_end * NG + lane; L.prs = 32;
-  L.g = lane % G;
-  L.ctx = &ctx;
+  chain_bind_lane<G>(L, m, w_base, lane, &ctx);
 
   for (int trip = wg; trip < n_trips; trip += n_wg) {
     const int row0 = trip * rpw;
@@ -177,7 +190,7 @@ chain_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, ChainParams d
     const bool direct = d > kChainPrefetch * G;         // wide action vectors: no register prefetch
     for (int t = 0; t < h; ++t) {
       const int buf = t & 1;
-      const ChRef act{L.sh + (m.s_ctrl + buf * d) * NG, NG};
+      const ChRef act{L.sh + (m.s_ctrl + buf * d) * NG};
       float* nxt = L.sh + (m.s_ctrl + (buf ^ 1) * d) * NG;
       float pre[kChainPrefetch];
       const bool more = t + 1 < h;
@@ -253,18 +266,15 @@ __global__ void chain_advance_kernel(ChainParams dp, float* state, const float* 
   const ChainModel& m = *reinterpret_cast<const ChainModel*>(s_model);
   const int lane = threadIdx.x & 31, grp = lane / G;
   WarpGroupCtx<G> ctx;
-  ChainLane<WarpGroupCtx<G>> L;
-  L.M = &m;
-  L.sh = w_base + grp; L.shs = NG;
-  L.pr = w_base + m.s_end * NG + lane; L.prs = 32;
-  L.g = lane % G;
-  L.ctx = &ctx;
+  ChainWarpLane<G> L;
+  typedef typename ChainWarpLane<G>::ChRef ChRef;
+  chain_bind_lane<G>(L, m, w_base, lane, &ctx);
   const int ns = m.nq + m.nv;
   for (int i = L.g; i < ns; i += G) L.state(i) = state[i];
   if (action)
     for (int k = L.g; k < dp.act_dim; k += G) L.sh[(m.s_ctrl + k) * NG] = action[k];
   __syncwarp();
-  if (action) L.step(ChRef{L.sh + m.s_ctrl * NG, NG});
+  if (action) L.step(ChRef{L.sh + m.s_ctrl * NG});
   __syncwarp();
   if (grp == 0) {
     if (next_state)

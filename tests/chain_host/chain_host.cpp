@@ -82,9 +82,9 @@ int chain_host_rollout(const icem_articulated_model_t* a, int act_dim, int integ
   SpinBarrier bar(G);
   auto lane = [&](int g) {
     HostCtx ctx{&bar, xbuf.data(), g, G};
-    icem::ChainLane<HostCtx> L;
-    L.M = &m; L.sh = shared.data(); L.shs = 1; L.pr = priv[g].data(); L.prs = 1; L.g = g; L.ctx = &ctx;
-    const icem::ChRef ctrl = L.shared_rec(m.s_ctrl);
+    icem::ChainLane<HostCtx, 1> L;
+    L.M = &m; L.sh = shared.data(); L.pr = priv[g].data(); L.g = g; L.ctx = &ctx;
+    const auto ctrl = L.shared_rec(m.s_ctrl);
     for (int r = 0; r < n; ++r) {
       if (g == 0)
         for (int i = 0; i < ns; ++i) shared[m.s_state + i] = (float)start[i];
