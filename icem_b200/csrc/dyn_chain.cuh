@@ -58,6 +58,7 @@ constexpr int kChMaxTrunk = 4, kChMaxLimbs = 4, kChMaxLimbNodes = 4;
 constexpr int kChDofRec = 19, kChTrunkDofRec = 21;
 constexpr int kChNodeRec = 16;    // mass, h(3), Io(6), bias force(6)
 constexpr int kChFrame = 18;      // R(9) p(3) v(6) of a trunk body that carries limbs
+constexpr int kChFreeRec = 24;    // free root: R(9) c_J linear part(3) | root acceleration(6) qacc(6) from pass 2
 constexpr int kChJun = 27;        // articulated inertia (6 + 9 + 6) + bias force (6) summed over the limbs of a junction
 enum { kChEuler = 0, kChRK4 = 1 };
 
@@ -69,7 +70,9 @@ struct ChainModel {
   int max_limb_nodes, trunk_dofs, max_limb_dofs, n_junctions;
   float dt, gravity, ctrl_limit, kc, cc, kv, mu, cdmax;
   // scratch layout in slots (group-shared region: slot * (32 / G) + group; lane-private region: slot * 32 + lane)
-  int s_state, s_origin, s_dof, s_node, s_frame, s_acc, s_jun, s_rk, s_ctrl, s_end;
+  int s_state, s_free, s_dof, s_node, s_frame, s_acc, s_jun, s_rk, s_ctrl, s_end;
+  int root_free;                                 // the root carries a free joint (handled as one 6-dof joint)
+  int seq_last[kChMaxLimbs];                     // position of the last node of lane g's walk
   int p_dof, p_node, p_end;
   int trunk_node[kChMaxTrunk];
   int trunk_junction[kChMaxTrunk];               // junction slot of this trunk position, -1 = no limb hangs here
@@ -188,6 +191,49 @@ __host__ __device__ __forceinline__ float ch_rcp(float x) {
 #endif
 }
 
+// x = M^-1 b for the symmetric positive definite 6x6 matrix M = [[A, B], [B^T, C]] (LDL^T, everything in registers)
+__host__ __device__ __forceinline__ void ch_solve_spd6(const ArtInertia& I, const float* b, float* x) {
+  float L[6][6];
+  L[0][0] = I.A[0]; L[1][0] = I.A[3]; L[1][1] = I.A[1]; L[2][0] = I.A[4]; L[2][1] = I.A[5]; L[2][2] = I.A[2];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) L[3 + r][c] = I.B[c * 3 + r];          // lower-left block = B^T
+  L[3][3] = I.C[0]; L[4][3] = I.C[3]; L[4][4] = I.C[1]; L[5][3] = I.C[4]; L[5][4] = I.C[5]; L[5][5] = I.C[2];
+  float dinv[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    float w[6];                       // w[k] = L[j][k] * d_k
+    float d = L[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) { w[k] = L[j][k]; d -= w[k] * w[k] * dinv[k]; }
+    dinv[j] = ch_rcp(d);
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      float v = L[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v -= L[i][k] * w[k] * dinv[k];
+      L[i][j] = v;                    // unscaled: L[i][j] * d_j
+    }
+  }
+  // (L D^-1) D (L D^-1)^T x = b   with the unscaled columns stored in L
+  float z[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    float v = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) v -= L[i][k] * dinv[k] * z[k];
+    z[i] = v;
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    float v = z[i] * dinv[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) v -= L[k][i] * dinv[i] * x[k];
+    x[i] = v;
+  }
+}
+
 // One lane of a group.  Ctx provides: group_sum(float (&x)[N]) (sum over the G lanes, identical in all of them)
 // and group_sync() (barrier + memory ordering among the lanes of the warp / group).
 template <class Ctx, int STRIDE>
@@ -209,7 +255,7 @@ struct ChainLane {
   __host__ __device__ __forceinline__ ChRef node_rec(bool trunk, int pos) const {
     return trunk ? shared_rec(M->s_node + kChNodeRec * pos) : private_rec(M->p_node + kChNodeRec * pos);
   }
-  // node this lane visits at position i of its sequence (trunk nodes, then its own limb); false = nothing to do
+  // node this lane visits at position i of its walk (trunk nodes, then its own limb); false = nothing to do
   __host__ __device__ __forceinline__ bool node_at(int i, int& node, bool& trunk, int& pos) const {
     const ChainModel& m = *M;
     trunk = i < m.n_trunk;
@@ -219,13 +265,17 @@ struct ChainLane {
   }
 
   // ---- pass 1 ----------------------------------------------------------------------------------------------------
-  __host__ __device__ void pass1(const ChRef& q, const ChRef& qd, const ChRef& ctrl) {
+  // `rec` returns the record (mass, h, Io, bias force) of the LAST node of this lane's walk: pass 2 starts with that
+  // node, so its record never goes through shared memory.  `implicit`: joint springs / dampers enter the system matrix
+  // (semi-implicit Euler); otherwise they are plain forces (RK4 stages).
+  __host__ __device__ void pass1(const ChRef& q, const ChRef& qd, const ChRef& ctrl, bool implicit, float (&rec)[kChNodeRec]) {
     const ChainModel& m = *M;
-    const float dt = m.dt;
+    const float dt = implicit ? m.dt : 0.f;
     float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f}, p[3] = {0.f, 0.f, 0.f};
     float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float O[3] = {0.f, 0.f, 0.f};
     const int n_seq = m.n_trunk + m.max_limb_nodes;
+    const int last = m.seq_last[g];
     for (int i = 0; i < n_seq; ++i) {
       int node, pos;
       bool trunk;
@@ -249,44 +299,33 @@ struct ChainLane {
         ch::matvec(R, m.n_pos[node], off);
         p[0] += off[0]; p[1] += off[1]; p[2] += off[2];
       }
-      const int j0 = m.n_dof_start[node], j1 = j0 + m.n_dof_count[node];
+      int j0 = m.n_dof_start[node];
+      const int j1 = j0 + m.n_dof_count[node];
+      if (root && m.root_free) {
+        // free joint: 3 world translations + 3 body-frame rotation rates, handled as ONE 6-dof joint.  Its motion
+        // subspace spans all of R^6, so pass 2 solves the root acceleration directly (floating base) and no per-dof
+        // record is needed: only R and the velocity-product term  c_J = sum_k (v xm S_k) qd_k = [0; v_lin x w].
+        const int qa = m.d_qadr[j0];
+        O[0] = q[qa]; O[1] = q[qa + 1]; O[2] = q[qa + 2];
+        const float qw = q[qa + 3], x = q[qa + 4], y = q[qa + 5], z = q[qa + 6];
+        R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - qw * z); R[2] = 2.f * (x * z + qw * y);
+        R[3] = 2.f * (x * y + qw * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - qw * x);
+        R[6] = 2.f * (x * z - qw * y); R[7] = 2.f * (y * z + qw * x); R[8] = 1.f - 2.f * (x * x + y * y);
+        const float w0 = qd[j0 + 3], w1 = qd[j0 + 4], w2 = qd[j0 + 5];
+        v[0] = R[0] * w0 + R[1] * w1 + R[2] * w2;
+        v[1] = R[3] * w0 + R[4] * w1 + R[5] * w2;
+        v[2] = R[6] * w0 + R[7] * w1 + R[8] * w2;
+        v[3] = qd[j0]; v[4] = qd[j0 + 1]; v[5] = qd[j0 + 2];
+        const ChRef fr = shared_rec(m.s_free);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) fr[k] = R[k];
+        float cl[3];
+        ch::cross(v + 3, v, cl);
+        fr[9] = cl[0]; fr[10] = cl[1]; fr[11] = cl[2];
+        j0 += 6;
+      }
       for (int j = j0; j < j1; ++j) {
         const int t = m.d_type[j];
-        if (t == kFreeTrans) {       // free joint of the root: 3 world translations + body-frame rotations
-          const int qa = m.d_qadr[j];
-          O[0] = q[qa]; O[1] = q[qa + 1]; O[2] = q[qa + 2];
-          const float qw = q[qa + 3], x = q[qa + 4], y = q[qa + 5], z = q[qa + 6];
-          R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - qw * z); R[2] = 2.f * (x * z + qw * y);
-          R[3] = 2.f * (x * y + qw * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - qw * x);
-          R[6] = 2.f * (x * z - qw * y); R[7] = 2.f * (y * z + qw * x); R[8] = 1.f - 2.f * (x * x + y * y);
-          float qdv[6];
-#pragma unroll
-          for (int k = 0; k < 6; ++k) qdv[k] = qd[j + k];
-          // full velocity of the root: the rotation axes are body-fixed, so each moves with all of it
-          v[0] = R[0] * qdv[3] + R[1] * qdv[4] + R[2] * qdv[5];
-          v[1] = R[3] * qdv[3] + R[4] * qdv[4] + R[5] * qdv[5];
-          v[2] = R[6] * qdv[3] + R[7] * qdv[4] + R[8] * qdv[5];
-          v[3] = qdv[0]; v[4] = qdv[1]; v[5] = qdv[2];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const ChRef rt = dof_rec(true, j + k), rr = dof_rec(true, j + 3 + k);
-            float S[6] = {R[k], R[3 + k], R[6 + k], 0.f, 0.f, 0.f}, c[6];
-            ch::cross_motion(v, S, c);
-#pragma unroll
-            for (int e = 0; e < 6; ++e) {
-              rt[e] = (e == 3 + k) ? 1.f : 0.f;
-              rt[6 + e] = 0.f;
-              rr[e] = S[e];
-              rr[6 + e] = c[e] * qdv[3 + k];
-            }
-            rt[19] = -m.d_damp[j + k] * qdv[k];
-            rt[20] = m.d_arm[j + k] + dt * m.d_damp[j + k];
-            rr[19] = -m.d_damp[j + 3 + k] * qdv[3 + k];
-            rr[20] = m.d_arm[j + 3 + k] + dt * m.d_damp[j + 3 + k];
-          }
-          j += 5;
-          continue;
-        }
         float ax[3], S[6], c[6];
         ch::matvec(R, m.d_axis[j], ax);
         const float qj = q[m.d_qadr[j]], qdj = qd[j];
@@ -338,10 +377,6 @@ struct ChainLane {
         }
         r[trunk ? 19 : 17] = tau - (beff + dt * keff) * qdj;
         r[trunk ? 20 : 18] = m.d_arm[j] + dt * beff + dt * dt * keff;
-      }
-      if (root) {
-        const ChRef o = shared_rec(m.s_origin);
-        o[0] = O[0]; o[1] = O[1]; o[2] = O[2];
       }
       if (trunk && m.trunk_junction[i] >= 0) {
         const ChRef f = shared_rec(m.s_frame + kChFrame * m.trunk_junction[i]);
@@ -407,20 +442,25 @@ struct ChainLane {
           f[3] -= fc[0]; f[4] -= fc[1]; f[5] -= fc[2];
         }
       }
-      const ChRef nr = node_rec(trunk, pos);
-      nr[0] = mass; nr[1] = h[0]; nr[2] = h[1]; nr[3] = h[2];
+      rec[0] = mass; rec[1] = h[0]; rec[2] = h[1]; rec[3] = h[2];
 #pragma unroll
-      for (int e = 0; e < 6; ++e) { nr[4 + e] = Io[e]; nr[10 + e] = f[e]; }
+      for (int e = 0; e < 6; ++e) { rec[4 + e] = Io[e]; rec[10 + e] = f[e]; }
+      if (i != last) {
+        const ChRef nr = node_rec(trunk, pos);
+#pragma unroll
+        for (int e = 0; e < kChNodeRec; ++e) nr[e] = rec[e];
+      }
     }
   }
 
   // ---- pass 2 ----------------------------------------------------------------------------------------------------
-  __host__ __device__ void pass2() {
+  __host__ __device__ void pass2(const float (&rec)[kChNodeRec]) {
     const ChainModel& m = *M;
     ArtInertia IA;
     float P[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     IA.zero();
     const int n_seq = m.n_trunk + m.max_limb_nodes;
+    const int last = m.seq_last[g];
     for (int i = n_seq - 1; i >= 0; --i) {
       if (i == m.n_trunk - 1 && m.n_junctions > 0) {
         // the limbs are done: sum them where they join the trunk (every lane gets every junction's sum)
@@ -444,7 +484,12 @@ struct ChainLane {
       int node, pos;
       bool trunk;
       if (!node_at(i, node, trunk, pos)) continue;
-      {
+      if (i == last) {
+        const float h[3] = {rec[1], rec[2], rec[3]};
+#pragma unroll
+        for (int e = 0; e < 6; ++e) P[e] += rec[10 + e];
+        IA.add_rigid(rec[0], h, rec + 4);
+      } else {
         const ChRef nr = node_rec(trunk, pos);
         const float h[3] = {nr[1], nr[2], nr[3]};
         float Io[6];
@@ -459,7 +504,10 @@ struct ChainLane {
 #pragma unroll
         for (int e = 0; e < 9; ++e) IA.B[e] += jr[6 + e];
       }
-      const int j0 = m.n_dof_start[node], j1 = j0 + m.n_dof_count[node];
+      int j0 = m.n_dof_start[node];
+      const int j1 = j0 + m.n_dof_count[node];
+      const bool free_root = i == 0 && m.root_free;
+      if (free_root) j0 += 6;
       for (int j = j1 - 1; j >= j0; --j) {
         const ChRef r = dof_rec(trunk, j);
         float S[6], c[6], U[6], Ud[6];
@@ -480,10 +528,27 @@ struct ChainLane {
 #pragma unroll
         for (int e = 0; e < 6; ++e) P[e] += Ic[e] + U[e] * ud;
       }
+      if (free_root) {
+        // floating base: no joint force on any of the 6 directions, so  IA a + pA = 0
+        const ChRef fr = shared_rec(m.s_free);
+        float b[6], a[6];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) b[e] = -P[e];
+        ch_solve_spd6(IA, b, a);
+        // a = a_base + c_J + S qacc   with S = [[0, R], [1, 0]]:  qacc_trans = a_lin - g - c_J,  qacc_rot = R^T a_ang
+#pragma unroll
+        for (int e = 0; e < 6; ++e) fr[12 + e] = a[e];
+        fr[18] = a[3] - fr[9];
+        fr[19] = a[4] - fr[10];
+        fr[20] = a[5] - fr[11] - m.gravity;
+        fr[21] = fr[0] * a[0] + fr[3] * a[1] + fr[6] * a[2];
+        fr[22] = fr[1] * a[0] + fr[4] * a[1] + fr[7] * a[2];
+        fr[23] = fr[2] * a[0] + fr[5] * a[1] + fr[8] * a[2];
+      }
     }
   }
 
-  // ---- pass 3: accelerations; qacc_j is handed to `sink(j, type, qacc)` in dof order ------------------------------
+  // ---- pass 3: accelerations; qacc_j is handed to `sink(j, trunk, qacc)` in dof order ------------------------------
   template <class Sink>
   __host__ __device__ void pass3(Sink&& sink) {
     const ChainModel& m = *M;
@@ -498,7 +563,16 @@ struct ChainLane {
 #pragma unroll
         for (int e = 0; e < 6; ++e) a[e] = ar[e];
       }
-      const int j0 = m.n_dof_start[node], j1 = j0 + m.n_dof_count[node];
+      int j0 = m.n_dof_start[node];
+      const int j1 = j0 + m.n_dof_count[node];
+      if (i == 0 && m.root_free) {
+        const ChRef fr = shared_rec(m.s_free);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) a[e] = fr[12 + e];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) sink(j0 + e, true, fr[18 + e]);
+        j0 += 6;
+      }
       for (int j = j0; j < j1; ++j) {
         const ChRef r = dof_rec(trunk, j);
         float qacc = r[18];
@@ -516,8 +590,8 @@ struct ChainLane {
     }
   }
 
-  // q (+)= dt * qd for one dof; the quaternion of a free joint moves when its last rotation dof comes by.
-  // `qd_new` is where the updated velocities live (the three rotation rates are read back from it).
+  // q (+)= step * qd for one dof; the quaternion of a free joint moves when its last rotation dof comes by.
+  // `qd_new` is where the velocities to integrate live (the three rotation rates are read back from it).
   __host__ __device__ __forceinline__ void advance_position(int j, const ChRef& qsrc, const ChRef& qdst,
                                                             const ChRef& qd_new, float step) const {
     const ChainModel& m = *M;
@@ -549,8 +623,10 @@ struct ChainLane {
   __host__ __device__ void substep_euler(const ChRef& ctrl) {
     const ChainModel& m = *M;
     const ChRef q = shared_rec(m.s_state), qd = shared_rec(m.s_state + m.nq);
-    pass1(q, qd, ctrl);
-    pass2();
+    float rec[kChNodeRec];
+    pass1(q, qd, ctrl, true, rec);
+    pass2(rec);
+    ctx->group_sync();       // the junction accelerations of pass 3 overwrite the junction sums pass 2 was reading
     const float dt = m.dt;
     const int gg = g;
     const ChainLane* self = this;
@@ -718,6 +794,7 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
       if (i < m.n_trunk) node = m.trunk_node[i];
       else if (g < m.n_limbs && i - m.n_trunk < m.limb_nnodes[g]) node = m.limb_node[g][i - m.n_trunk];
       m.seq_node[g][i] = node;
+      if (node >= 0) m.seq_last[g] = i;
     }
   // ---- dofs -----------------------------------------------------------------------------------------------------
   for (int j = 0; j < a.nv; ++j) {
@@ -734,14 +811,29 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
     const int n = m.trunk_node[k];
     bool seen_hinge = false;
     for (int j = m.n_dof_start[n]; j < m.n_dof_start[n] + m.n_dof_count[n]; ++j) {
-      m.d_rec[j] = m.trunk_dofs++;
       const int ty = m.d_type[j];
+      if (ty == kFreeTrans || ty == kFreeRot) {
+        // the free root is solved as a floating base: nothing may act on its six dofs
+        if (m.d_arm[j] != 0.f || m.d_damp[j] != 0.f || m.d_stiff[j] != 0.f || m.d_act[j] >= 0 || m.d_limited[j]) {
+          *why = "free joint with armature / damping / actuator";
+          return false;
+        }
+        m.root_free = 1;
+        m.d_rec[j] = 0;
+      } else {
+        m.d_rec[j] = m.trunk_dofs++;
+      }
       if ((ty == kFreeTrans || ty == kFreeRot) && k != 0) { *why = "free joint below the root"; return false; }
       if (k == 0 && ty == kHinge) seen_hinge = true;
       if (k == 0 && ty == kSlide && seen_hinge) { *why = "root slide after a root hinge"; return false; }
       if (ty == kFreeTrans && j != m.n_dof_start[n] && m.d_type[j - 1] != kFreeTrans) {
         *why = "free joint must come first on the root";
         return false;
+      }
+      if (ty == kFreeTrans && j == m.n_dof_start[n]) {
+        if (j + 5 >= m.n_dof_start[n] + m.n_dof_count[n]) { *why = "incomplete free joint"; return false; }
+        for (int e = 0; e < 6; ++e)
+          if (m.d_type[j + e] != (e < 3 ? kFreeTrans : kFreeRot)) { *why = "malformed free joint"; return false; }
       }
     }
   }
@@ -766,18 +858,20 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
   // ---- scratch layout ---------------------------------------------------------------------------------------------
   int s = 0;
   m.s_state = s; s += m.nq + m.nv;
-  m.s_origin = s; s += 3;
-  m.s_ctrl = s; s += 2 * act_dim;                  // the staged actions of the current / next control step
+  m.s_ctrl = s; s += act_dim;                      // the controls of the current control step
+  m.s_free = s; s += m.root_free ? kChFreeRec : 0;
   m.s_dof = s; s += kChTrunkDofRec * m.trunk_dofs;
   m.s_node = s; s += kChNodeRec * m.n_trunk;
-  m.s_acc = s; s += 6 * m.n_junctions;
-  m.s_frame = s;                                   // frames are dead once pass 1 is over: the junction sums alias them
-  m.s_jun = s; s += kChJun * m.n_junctions;
+  // one region, three tenants in turn: junction frames (pass 1) -> junction sums (pass 2) -> junction accelerations
+  // (pass 3); the lanes are synchronised between the tenants (group sum / group_sync)
+  m.s_frame = s; m.s_jun = s; m.s_acc = s;
+  s += kChJun * m.n_junctions;
   m.s_rk = s;
   m.s_end = s;
   int p = 0;
   m.p_dof = p; p += kChDofRec * m.max_limb_dofs;
-  m.p_node = p; p += kChNodeRec * m.max_limb_nodes;
+  // the last node of a walk keeps its record in registers (pass 1 -> pass 2)
+  m.p_node = p; p += kChNodeRec * (m.max_limb_nodes > 0 ? m.max_limb_nodes - 1 : 0);
   m.p_end = p;
   return true;
 }

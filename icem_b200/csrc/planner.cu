@@ -393,7 +393,7 @@ static void launch_chain_impl(icem_planner* p, const RolloutArgs& a, int rows_ma
   const int nprob = a.prob_actions ? p->B : 1;      // operator launches carry no problem strides
   const int trips = (rows_max + dp.rows_per_warp - 1) / dp.rows_per_warp;
   // warps per CTA: as many as shared memory holds (one CTA per SM), but no more than it takes to give every SM work
-  int wmax = 8;
+  int wmax = kChainMaxWarps;
   while (wmax > 1 && chain_rollout_smem_bytes<kSample>(sc, dp, a.stride, wmax) > kMaxSmemPerCta) --wmax;
   const int sms = std::max(1, p->sm_count / nprob);
   const int warps = std::max(1, std::min(wmax, (trips + sms - 1) / sms));

@@ -95,8 +95,10 @@ __device__ __forceinline__ float chain_step_cost_pre(const CostConst& cc, const 
   return -L.state(cc.idx_a + oo) + 0.1f * a2;   // environments/mujoco.py:259-277
 }
 
+constexpr int kChainMaxWarps = 12;    // per CTA (one CTA per SM): 384 threads x 170 registers fill the register file
+
 template <int G, bool kSample, bool kRollout, bool kNextObs>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kChainMaxWarps * 32, 1)
 chain_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, ChainParams dp) {
   extern __shared__ __align__(128) float smem[];
   constexpr int NG = 32 / G;
@@ -189,12 +191,10 @@ chain_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, ChainParams d
     float total = (cc.reduce == 1) ? INFINITY : 0.f;
     const bool direct = d > kChainPrefetch * G;         // wide action vectors: no register prefetch
     for (int t = 0; t < h; ++t) {
-      const int buf = t & 1;
-      const ChRef act{L.sh + (m.s_ctrl + buf * d) * NG};
-      float* nxt = L.sh + (m.s_ctrl + (buf ^ 1) * d) * NG;
+      const ChRef act{L.sh + m.s_ctrl * NG};
       float pre[kChainPrefetch];
       const bool more = t + 1 < h;
-      if (more && !direct) {
+      if (more && !direct) {          // the next step's controls travel from L2 while this step's substeps run
 #pragma unroll
         for (int u = 0; u < kChainPrefetch; ++u) {
           const int k = L.g + u * G;
@@ -215,15 +215,15 @@ chain_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, ChainParams d
         else if (cc.reduce == 1) total = fminf(total, cf);
         else total = cf;
       }
-      if (more) {
+      if (more) {                     // every lane is past its last read of this step's controls (group_sync in step)
         if (!direct) {
 #pragma unroll
           for (int u = 0; u < kChainPrefetch; ++u) {
             const int k = L.g + u * G;
-            if (k < d) nxt[k * NG] = pre[u];
+            if (k < d) L.sh[(m.s_ctrl + k) * NG] = pre[u];
           }
         } else {
-          for (int k = L.g; k < d; k += G) nxt[k * NG] = __ldcg(arow + (t + 1) * d + k);
+          for (int k = L.g; k < d; k += G) L.sh[(m.s_ctrl + k) * NG] = __ldcg(arow + (t + 1) * d + k);
         }
       }
       __syncwarp();
