@@ -197,7 +197,7 @@ def build_controller(name, world, rank, device):
                                    weights=wts)
         model = CudaDenseTanhModel(env=env, **dict(zip(("w_obs", "w_act", "bias"), wts)))
     else:
-        env = envs.make_env(w["env"], device=device)
+        env = envs.make_env(w["env"], device=device, **w.get("env_kwargs", {}))
         model = CudaGroundTruthModel(env=env)
     ctrl = MpcICemB200(env=env, forward_model=model, horizon=st["horizon"],
                        num_simulated_trajectories=st["num_simulated_trajectories"],

@@ -7,7 +7,8 @@ import numpy as np
 LIB_PATH = os.environ.get("ICEM_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
                                                            "libicem_b200.so")
 
-ICEM_ABI_VERSION = 6
+ICEM_ABI_VERSION = 7
+INTEGRATOR = {"euler": 0, "rk4": 1}
 DYN = {"dense_tanh": 0, "halfcheetah": 1, "humanoid_standup": 2, "mlp": 3, "articulated": 4}
 COST = {"halfcheetah": 0, "humanoid_standup": 1, "locomotion": 2}
 REDUCE = {"sum": 0, "best": 1, "final": 2}
@@ -49,6 +50,7 @@ class IcemArticulatedModel(C.Structure):
         + [(n, C.POINTER(C.c_float)) for n in ("dof_axis", "dof_anchor", "dof_stiffness", "dof_damping",
                                                "dof_armature", "dof_lo", "dof_hi", "dof_klim", "dof_blim", "dof_gear")]
         + [("con_body", C.POINTER(C.c_int32)), ("con_pos", C.POINTER(C.c_float)), ("con_radius", C.POINTER(C.c_float))]
+        + [("integrator", C.c_int32)]
     )
 
 

@@ -590,26 +590,26 @@ struct ChainLane {
     }
   }
 
-  // q (+)= step * qd for one dof; the quaternion of a free joint moves when its last rotation dof comes by.
-  // `qd_new` is where the velocities to integrate live (the three rotation rates are read back from it).
-  __host__ __device__ __forceinline__ void advance_position(int j, const ChRef& qsrc, const ChRef& qdst,
-                                                            const ChRef& qd_new, float step) const {
+  // q (+)= step * rate for one dof.  The quaternion of a free joint moves when its last rotation dof comes by:
+  // the caller collects the three body-frame rates in `w` (dof order) on the way.
+  __host__ __device__ __forceinline__ void advance_position(int j, const ChRef& qsrc, const ChRef& qdst, float rate,
+                                                            float (&w)[3], float step) const {
     const ChainModel& m = *M;
     const int t = m.d_type[j];
     if (t != kFreeRot) {
       const int qa = m.d_qadr[j];
-      qdst[qa] = qsrc[qa] + step * qd_new[j];
+      qdst[qa] = qsrc[qa] + step * rate;
       return;
     }
+    w[0] = w[1]; w[1] = w[2]; w[2] = rate;
     if (j + 1 < m.nv && m.d_type[j + 1] == kFreeRot) return;
     const int qa = m.d_qadr[j];
-    const float w0 = qd_new[j - 2], w1 = qd_new[j - 1], w2 = qd_new[j];
-    const float n = sqrtf(w0 * w0 + w1 * w1 + w2 * w2);
+    const float n = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
     const float half = 0.5f * step * n;
     float sn, cs;
     ch::sincos_(half, &sn, &cs);
     const float s = n > 1e-8f ? sn * ch_rcp(n) : 0.5f * step;
-    const float bw = cs, bx = w0 * s, by = w1 * s, bz = w2 * s;
+    const float bw = cs, bx = w[0] * s, by = w[1] * s, bz = w[2] * s;
     const float aw = qsrc[qa], ax = qsrc[qa + 1], ay = qsrc[qa + 2], az = qsrc[qa + 3];
     const float rw = aw * bw - ax * bx - ay * by - az * bz;
     const float rx = aw * bx + ax * bw + ay * bz - az * by;
@@ -619,7 +619,7 @@ struct ChainLane {
     qdst[qa] = rw * inv; qdst[qa + 1] = rx * inv; qdst[qa + 2] = ry * inv; qdst[qa + 3] = rz * inv;
   }
 
-  // ---- one substep, semi-implicit Euler (oracle/articulated_np.py:236-255) ---------------------------------------
+  // ---- one substep, semi-implicit Euler (oracle/articulated_np.py: integrate) -------------------------------------
   __host__ __device__ void substep_euler(const ChRef& ctrl) {
     const ChainModel& m = *M;
     const ChRef q = shared_rec(m.s_state), qd = shared_rec(m.s_state + m.nq);
@@ -630,24 +630,69 @@ struct ChainLane {
     const float dt = m.dt;
     const int gg = g;
     const ChainLane* self = this;
+    float w[3] = {0.f, 0.f, 0.f};
     pass3([&](int j, bool trunk, float qacc) {
       // trunk dofs are computed by every lane of the group (identical values): lane 0 alone updates the state
       if (trunk && gg != 0) return;
-      qd[j] = qd[j] + dt * qacc;
-      self->advance_position(j, q, q, qd, dt);
+      const float v = qd[j] + dt * qacc;
+      qd[j] = v;
+      self->advance_position(j, q, q, v, w, dt);
     });
     ctx->group_sync();
   }
 
+  // ---- one substep, four-stage Runge-Kutta like mj_RungeKutta (oracle/articulated_np.py: rk4_substep) -------------
+  // The substep's start state stays in the state slots; the stage state and the weighted sums of the stage
+  // velocities / accelerations live in the s_rk slots: qs(nq) vs(nv) vsum(nv) asum(nv).
+  __host__ __device__ void substep_rk4(const ChRef& ctrl) {
+    const ChainModel& m = *M;
+    const ChRef q0 = shared_rec(m.s_state), v0 = shared_rec(m.s_state + m.nq);
+    const ChRef qs = shared_rec(m.s_rk), vs = shared_rec(m.s_rk + m.nq);
+    const ChRef vsum = shared_rec(m.s_rk + m.nq + m.nv), asum = shared_rec(m.s_rk + m.nq + 2 * m.nv);
+    const float dt = m.dt;
+    const int gg = g;
+    const ChainLane* self = this;
+    for (int stage = 0; stage < 4; ++stage) {
+      float rec[kChNodeRec];
+      // every stage evaluates the damped acceleration field of the Euler step (implicit joint springs / dampers)
+      pass1(stage == 0 ? q0 : qs, stage == 0 ? v0 : vs, ctrl, true, rec);
+      pass2(rec);
+      ctx->group_sync();
+      const float b = (stage == 0 || stage == 3) ? (1.f / 6.f) : (1.f / 3.f);
+      const float nxt = dt * (stage == 2 ? 1.f : 0.5f);
+      float w[3] = {0.f, 0.f, 0.f};
+      pass3([&](int j, bool trunk, float qacc) {
+        if (trunk && gg != 0) return;
+        const float vcur = stage == 0 ? v0[j] : vs[j];
+        const float vw = (stage == 0 ? 0.f : vsum[j]) + b * vcur;
+        const float aw = (stage == 0 ? 0.f : asum[j]) + b * qacc;
+        if (stage < 3) {
+          vsum[j] = vw;
+          asum[j] = aw;
+          self->advance_position(j, q0, qs, vcur, w, nxt);      // stage positions start from the substep's q0
+          vs[j] = v0[j] + nxt * qacc;
+        } else {
+          self->advance_position(j, q0, q0, vw, w, dt);
+          v0[j] = v0[j] + dt * aw;
+        }
+      });
+      ctx->group_sync();
+    }
+  }
+
   __host__ __device__ void step(const ChRef& ctrl) {
-    for (int s = 0; s < M->nsub; ++s) substep_euler(ctrl);
+    if (M->integrator == kChRK4) {
+      for (int s = 0; s < M->nsub; ++s) substep_rk4(ctrl);
+    } else {
+      for (int s = 0; s < M->nsub; ++s) substep_euler(ctrl);
+    }
   }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
 // Host side: decompose a body tree (tables as in icem_articulated_model_t) into trunk + limb chains.
 struct ChainSource {
-  int nb, nq, nv, nu, nc, nsub, obs_offset;
+  int nb, nq, nv, nu, nc, nsub, obs_offset, integrator;
   float dt, gravity, ctrl_limit, kc, cc, cdmax, kv, mu;
   const int32_t *body_parent, *body_dof_start, *body_dof_count;
   const float *body_pos, *body_mass, *body_com, *body_inertia;
@@ -661,6 +706,7 @@ struct ChainSource {
 inline ChainSource chain_source(const icem_articulated_model_t& a) {
   ChainSource s{};
   s.nb = a.nb; s.nq = a.nq; s.nv = a.nv; s.nu = a.nu; s.nc = a.nc; s.nsub = a.nsub; s.obs_offset = a.obs_offset;
+  s.integrator = a.integrator;
   s.dt = a.dt; s.gravity = a.gravity; s.ctrl_limit = a.ctrl_limit;
   s.kc = a.contact_stiffness; s.cc = a.contact_damping; s.cdmax = a.contact_damping_max;
   s.kv = a.friction_viscous; s.mu = a.friction;
@@ -852,7 +898,8 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
     m.max_limb_nodes = m.limb_nnodes[l] > m.max_limb_nodes ? m.limb_nnodes[l] : m.max_limb_nodes;
   }
   m.nq = a.nq; m.nv = a.nv; m.nu = a.nu; m.nsub = a.nsub; m.obs_offset = a.obs_offset; m.n_nodes = n_nodes;
-  m.integrator = kChEuler;
+  if (a.integrator != kChEuler && a.integrator != kChRK4) { *why = "unknown integrator"; return false; }
+  m.integrator = a.integrator;
   m.dt = a.dt; m.gravity = a.gravity; m.ctrl_limit = a.ctrl_limit;
   m.kc = a.kc; m.cc = a.cc; m.kv = a.kv; m.mu = a.mu; m.cdmax = a.cdmax;
   // ---- scratch layout ---------------------------------------------------------------------------------------------
@@ -866,7 +913,7 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
   // (pass 3); the lanes are synchronised between the tenants (group sum / group_sync)
   m.s_frame = s; m.s_jun = s; m.s_acc = s;
   s += kChJun * m.n_junctions;
-  m.s_rk = s;
+  m.s_rk = s; s += m.integrator == kChRK4 ? m.nq + 3 * m.nv : 0;
   m.s_end = s;
   int p = 0;
   m.p_dof = p; p += kChDofRec * m.max_limb_dofs;

@@ -396,7 +396,13 @@ static void launch_chain_impl(icem_planner* p, const RolloutArgs& a, int rows_ma
   int wmax = kChainMaxWarps;
   while (wmax > 1 && chain_rollout_smem_bytes<kSample>(sc, dp, a.stride, wmax) > kMaxSmemPerCta) --wmax;
   const int sms = std::max(1, p->sm_count / nprob);
-  const int warps = std::max(1, std::min(wmax, (trips + sms - 1) / sms));
+  // Every warp makes `rounds` trips of equal length (all trajectories cost the same), so the launch takes
+  // rounds x (time of one trip) whatever the fill of the last round: spread the trips evenly over the rounds and
+  // keep only the warps that needs -- fewer resident warps contend less for the issue slots.
+  const int per_sm = (trips + sms - 1) / sms;
+  const int rounds = std::max(1, (per_sm + wmax - 1) / wmax);
+  int warps = std::max(1, std::min(wmax, (per_sm + rounds - 1) / rounds));
+  { const char* e = getenv("ICEM_B200_CHAIN_WARPS"); if (e && atoi(e) > 0) warps = std::min(wmax, atoi(e)); }
   const size_t smem = chain_rollout_smem_bytes<kSample>(sc, dp, a.stride, warps);
   if (smem > kMaxSmemPerCta) throw InvalidArg("chain rollout kernel does not fit on an SM (shared memory)");
   auto kern = chain_rollout_kernel<G, kSample, kRollout, kNextObs>;
@@ -1075,6 +1081,9 @@ int icem_set_articulated_model(icem_planner_t* p, const icem_articulated_model_t
       p->chain.act_dim = p->d;
       p->chain.warp_floats = chain_warp_floats(p->chain_host);
       p->chain.rows_per_warp = 32 / p->chain_host.lanes;
+    } else if (a->integrator != ICEM_INTEGRATOR_EULER) {
+      throw Unsupported(std::string("the Runge-Kutta integrator needs the branch-parallel engine, which cannot run "
+                                    "this robot: ") + why);
     }
   }
   p->art.model = p->art_model.p;

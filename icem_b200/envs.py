@@ -179,11 +179,13 @@ class _DeviceSimEnv(_EnvBase):
     kind = None
     reward_is_negative_cost = True     # step() returns -cost_fn(obs, action): use_env_reward_as_cost == cost path
 
-    def __init__(self, *, name, device=0, **kwargs):
+    def __init__(self, *, name, device=0, integrator="euler", **kwargs):
         super().__init__(name=name, **kwargs)
         spec = _ARTICULATED[self.kind]
         self.spec = spec
         self.device = device
+        # env_params "integrator": "rk4" = the four-stage Runge-Kutta substep gym's XML files select (robots.get_model)
+        self.integrator = integrator
         self.cuda_dynamics = spec["dynamics"]
         b = spec["bound"]
         self.action_space = Box(-b * np.ones(spec["act_dim"]), b * np.ones(spec["act_dim"]))
@@ -200,16 +202,17 @@ class _DeviceSimEnv(_EnvBase):
                 horizon=2, num_simulated_trajectories=2, action_low=self.action_space.low,
                 action_high=self.action_space.high, dynamics=self.cuda_dynamics, cost=spec[0],
                 cost_params=spec[2] if len(spec) > 2 else None, articulated_model=self.cuda_articulated_model(),
+                integrator=self.integrator,
                 obs_offset=0 if self.cuda_dynamics == "articulated" else None,
                 obs_dim=self.observation_space.shape[0], device=self.device))
         return self._sim
 
     def cuda_articulated_model(self):
         """robots.CompiledModel for dynamics="articulated" (None: the built-in tables of the dynamics id)."""
-        if self.cuda_dynamics != "articulated":
-            return None
         from .robots import get_model
-        return get_model(self.spec["robot"])
+        if self.cuda_dynamics != "articulated":
+            return None if self.integrator == "euler" else get_model(self.cuda_dynamics, integrator=self.integrator)
+        return get_model(self.spec["robot"], integrator=self.integrator)
 
     def __getstate__(self):
         d = dict(self.__dict__)

@@ -9,6 +9,28 @@ from . import _lib
 from ._lib import IcemError, check, dptr, f32, f64, fptr, iptr  # noqa: F401
 
 
+def articulated_model_struct(m, obs_offset=0):
+    """robots.CompiledModel -> (icem_articulated_model_t, arrays that must outlive the call)."""
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    keep = dict(
+        body_parent=i32(m.body_parent), body_dof_start=i32(m.body_dof_start), body_dof_count=i32(m.body_dof_count),
+        body_pos=f32(m.body_pos), body_mass=f32(m.body_mass), body_com=f32(m.body_com),
+        body_inertia=f32(m.body_inertia), dof_body=i32(m.dof_body), dof_type=i32(m.dof_type),
+        dof_qadr=i32(m.dof_qadr), dof_parent=i32(m.dof_parent), dof_limited=i32(m.dof_limited),
+        dof_act=i32(m.dof_act), dof_axis=f32(m.dof_axis), dof_anchor=f32(m.dof_anchor),
+        dof_stiffness=f32(m.dof_stiffness), dof_damping=f32(m.dof_damping), dof_armature=f32(m.dof_armature),
+        dof_lo=f32(m.dof_lo), dof_hi=f32(m.dof_hi), dof_klim=f32(m.dof_klim), dof_blim=f32(m.dof_blim),
+        dof_gear=f32(m.dof_gear), con_body=i32(m.con_body), con_pos=f32(m.con_pos), con_radius=f32(m.con_radius))
+    st = _lib.IcemArticulatedModel(
+        nb=m.nb, nq=m.nq, nv=m.nv, nu=m.nu, nc=m.nc, nsub=m.nsub, obs_offset=int(obs_offset), dt=m.dt,
+        gravity=m.gravity, ctrl_limit=m.ctrl_limit, contact_stiffness=m.contact_stiffness,
+        contact_damping=m.contact_damping, contact_damping_max=m.contact_damping_max,
+        friction_viscous=m.friction_viscous, friction=m.friction,
+        integrator=_lib.INTEGRATOR[getattr(m, "integrator", "euler")],
+        **{k: (iptr(v) if v.dtype == np.int32 else fptr(v)) for k, v in keep.items()})
+    return st, keep
+
+
 @dataclass
 class PlannerSettings:
     """Flattened keyword surface of MpcICem (reference: controllers/icem.py:22,213-233;
@@ -37,6 +59,7 @@ class PlannerSettings:
     world_size: int = 1
     rank: int = 0
     colorednoise_v2: bool = False
+    integrator: Optional[str] = None     # articulated ground-truth models: "euler" | "rk4"; None = the model's own
     keep_iteration_actions: bool = False
     planner: str = "icem"                # "icem" (MpcICem) | "cem_std" (MpcCemStd) | "random" (MpcRandom)
     action_change_frequency: int = 0     # random only (controllers/mpc.py:91)
@@ -103,6 +126,11 @@ class Planner:
             if s.dynamics == "articulated" and s.articulated_model is None:
                 raise ValueError('dynamics="articulated" needs settings.articulated_model (robots.get_model(...))')
             model = s.articulated_model if s.articulated_model is not None else robots.get_model(s.dynamics)
+            if s.integrator is not None and s.integrator != model.integrator:
+                import dataclasses
+                if s.integrator not in _lib.INTEGRATOR:
+                    raise ValueError(f"unknown integrator {s.integrator!r}; choose from {sorted(_lib.INTEGRATOR)}")
+                model = dataclasses.replace(model, integrator=s.integrator)
             obs_offset = s.obs_offset
             if obs_offset is None:     # HalfCheetah's 17-wide observation drops qpos[0] (environments/mujoco.py:80-82)
                 obs_offset = 1 if (s.dynamics == "halfcheetah" and s.obs_dim != 18) else 0
@@ -144,22 +172,7 @@ class Planner:
 
     def set_articulated_model(self, m, obs_offset=0):
         """Upload robots.CompiledModel tables (icem_set_articulated_model)."""
-        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
-        keep = dict(
-            body_parent=i32(m.body_parent), body_dof_start=i32(m.body_dof_start), body_dof_count=i32(m.body_dof_count),
-            body_pos=f32(m.body_pos), body_mass=f32(m.body_mass), body_com=f32(m.body_com),
-            body_inertia=f32(m.body_inertia), dof_body=i32(m.dof_body), dof_type=i32(m.dof_type),
-            dof_qadr=i32(m.dof_qadr), dof_parent=i32(m.dof_parent), dof_limited=i32(m.dof_limited),
-            dof_act=i32(m.dof_act), dof_axis=f32(m.dof_axis), dof_anchor=f32(m.dof_anchor),
-            dof_stiffness=f32(m.dof_stiffness), dof_damping=f32(m.dof_damping), dof_armature=f32(m.dof_armature),
-            dof_lo=f32(m.dof_lo), dof_hi=f32(m.dof_hi), dof_klim=f32(m.dof_klim), dof_blim=f32(m.dof_blim),
-            dof_gear=f32(m.dof_gear), con_body=i32(m.con_body), con_pos=f32(m.con_pos), con_radius=f32(m.con_radius))
-        st = _lib.IcemArticulatedModel(
-            nb=m.nb, nq=m.nq, nv=m.nv, nu=m.nu, nc=m.nc, nsub=m.nsub, obs_offset=int(obs_offset), dt=m.dt,
-            gravity=m.gravity, ctrl_limit=m.ctrl_limit, contact_stiffness=m.contact_stiffness,
-            contact_damping=m.contact_damping, contact_damping_max=m.contact_damping_max,
-            friction_viscous=m.friction_viscous, friction=m.friction,
-            **{k: (iptr(v) if v.dtype == np.int32 else fptr(v)) for k, v in keep.items()})
+        st, _keep = articulated_model_struct(m, obs_offset)
         check(self._lib.icem_set_articulated_model(self._h, C.byref(st)))
         self.articulated = m
 

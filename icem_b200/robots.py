@@ -336,6 +336,7 @@ class CompiledModel:
     con_pos: np.ndarray           # [nc,3]
     con_radius: np.ndarray        # [nc]
     qpos0: np.ndarray             # [nq]
+    integrator: str = "euler"     # "euler" (semi-implicit, springs / dampers implicit) | "rk4" (mj_RungeKutta, N = 4)
 
     @property
     def max_depth(self):
@@ -493,7 +494,11 @@ def _limit_gains(m: CompiledModel, timeconst):
 _CACHE = {}
 
 
-def get_model(name) -> CompiledModel:
-    if name not in _CACHE:
-        _CACHE[name] = compile_model(ROBOTS[name]())
-    return _CACHE[name]
+def get_model(name, integrator="euler") -> CompiledModel:
+    """`integrator="rk4"`: the Runge-Kutta substep gym's XML files ask of MuJoCo."""
+    key = (name, integrator)
+    if key not in _CACHE:
+        import dataclasses
+        m = compile_model(ROBOTS[name]())
+        _CACHE[key] = dataclasses.replace(m, integrator=integrator)
+    return _CACHE[key]

@@ -44,6 +44,17 @@ WORKLOADS = {
         settings=dict(_BLITZ, num_simulated_trajectories=16384, opt_iterations=3, noise_beta=2.0,
                       dynamics="humanoid_standup", cost="humanoid_standup", obs_dim=47),
         act_dim=17, bound=0.4, env="HumanoidStandup"),
+    # the same two with the four-stage Runge-Kutta substep gym's XML files ask of MuJoCo (4 dynamics evaluations per
+    # substep instead of 1; robots.get_model(..., integrator="rk4"))
+    "halfcheetah_gt_n4096_rk4": dict(
+        settings=dict(_BLITZ, num_simulated_trajectories=4096, opt_iterations=5, noise_beta=0.25,
+                      dynamics="halfcheetah", cost="halfcheetah", obs_dim=17, penalise_flipping=True,
+                      integrator="rk4"),
+        act_dim=6, bound=1.0, env="HalfCheetah", env_kwargs=dict(integrator="rk4")),
+    "humanoid_standup_gt_n16384_rk4": dict(
+        settings=dict(_BLITZ, num_simulated_trajectories=16384, opt_iterations=3, noise_beta=2.0,
+                      dynamics="humanoid_standup", cost="humanoid_standup", obs_dim=47, integrator="rk4"),
+        act_dim=17, bound=0.4, env="HumanoidStandup", env_kwargs=dict(integrator="rk4")),
     # one shard of BASELINE configs[4] (N=262144 over 8 GPUs): 32768 trajectories per GPU
     "humanoid_standup_gt_shard32768": dict(
         settings=dict(_BLITZ, num_simulated_trajectories=32768, opt_iterations=3, noise_beta=2.0,

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define ICEM_ABI_VERSION 6
+#define ICEM_ABI_VERSION 7
 
 /* status codes */
 enum { ICEM_OK = 0, ICEM_ERR_INVALID = 1, ICEM_ERR_CUDA = 2, ICEM_ERR_STATE = 3, ICEM_ERR_UNSUPPORTED = 4,
@@ -134,6 +134,12 @@ int icem_set_dense_model(icem_planner_t* p, int32_t obs_dim, const float* w_obs,
 int icem_set_mlp_model(icem_planner_t* p, int32_t n_layers, const int32_t* layer_dims /* n_layers+1 */,
                        const float* const* weights, const float* const* biases);
 
+/* Integrator of the articulated ground-truth models (MuJoCo's <option integrator=...>, reached by the reference through
+ * environments/mujoco.py:101-131 `do_simulation`): semi-implicit Euler with joint springs / dampers in the system
+ * matrix, or the four-stage Runge-Kutta of mj_RungeKutta that gym's half_cheetah.xml / humanoidstandup.xml select
+ * (4 dynamics evaluations per substep, all forces explicit). */
+enum { ICEM_INTEGRATOR_EULER = 0, ICEM_INTEGRATOR_RK4 = 1 };
+
 /* ICEM_DYN_HALFCHEETAH / ICEM_DYN_HUMANOID_STANDUP: tables of the articulated-body model the kernels simulate
  * (the role of the MuJoCo model the reference's GroundTruthModel owns, models/gt_model.py:24-57).  All arrays are
  * HOST pointers, copied by the call.  Bodies are listed parent-before-child, dofs in body order, contact spheres
@@ -167,6 +173,7 @@ typedef struct icem_articulated_model {
   const int32_t* con_body;        /* [nc] */
   const float* con_pos;           /* [nc*3] body frame */
   const float* con_radius;        /* [nc] */
+  int32_t integrator;             /* ICEM_INTEGRATOR_*: how a substep advances (q, qvel) */
 } icem_articulated_model_t;
 int icem_set_articulated_model(icem_planner_t* p, const icem_articulated_model_t* model);
 

@@ -22,6 +22,14 @@ Model, per substep of length dt (frame_skip substeps per control step, control h
              B = joint damping (+ limit damper while violated): springs and dampers implicit (MuJoCo's Euler is
              implicit in joint damping the same way), contacts explicit
   qd <- qd + dt qacc ;  q <- q (+) dt qd                         (semi-implicit Euler; unit quaternion for the root)
+
+`integrator="rk4"` (what gym's half_cheetah.xml / humanoidstandup.xml ask of MuJoCo): the classic
+four-stage Runge-Kutta step laid out like mj_RungeKutta -- FOUR dynamics evaluations per substep, stage positions
+integrated from the substep's start position (quaternion-aware), the final step from the weighted stage velocities /
+accelerations (1/6, 1/3, 1/3, 1/6).  Every stage evaluates the SAME damped acceleration field as the Euler step,
+(M + dt B + dt^2 K)^-1 (tau - (B + dt K) qd - bias): MuJoCo keeps its stiff limit / contact terms stable inside the
+constraint solver; this soft-constraint model needs the implicit joint diagonal for that (with purely explicit
+springs and dampers the limit spring-dampers of HumanoidStandup blow up within a few control steps).
 """
 import numpy as np
 
@@ -77,8 +85,10 @@ def quat_mul(a, b):
 class ArticulatedModel:
     """`rollout(start_state, actions[p,h,d]) -> observations[p,h,obs_dim]` like oracle/dynamics_np.py models."""
 
-    def __init__(self, m: CompiledModel, obs_skip=0):
+    def __init__(self, m: CompiledModel, obs_skip=0, integrator=None):
         self.m = m
+        self.integrator = integrator or getattr(m, "integrator", "euler")
+        assert self.integrator in ("euler", "rk4")
         self.obs_skip = obs_skip             # HalfCheetah observation drops qpos[0] (exclude_current_positions)
         self.state_dim = m.nq + m.nv
         self.obs_dim = self.state_dim - obs_skip
@@ -160,7 +170,7 @@ class ArticulatedModel:
         return Rb, pb, aw, xw
 
     # ---- one dynamics evaluation ---------------------------------------------------------------------------
-    def qacc(self, q, qd, ctrl, return_parts=False):
+    def qacc(self, q, qd, ctrl, return_parts=False, implicit=True):
         m = self.m
         P = q.shape[0]
         Rb, pb, aw, xw = self.kinematics(q)
@@ -224,14 +234,53 @@ class ArticulatedModel:
         fc = np.stack([-coef * uc[..., 0], -coef * uc[..., 1], fn], axis=-1)
         tau_c = np.einsum("pcja,pca->pj", Jc, fc)
 
-        rhs = tau + tau_c - (Beff + m.dt * Keff) * qd - bias
+        hdt = m.dt if implicit else 0.0
+        rhs = tau + tau_c - (Beff + hdt * Keff) * qd - bias
         A = M.copy()
-        A[:, np.arange(m.nv), np.arange(m.nv)] += m.dt * Beff + m.dt * m.dt * Keff
+        A[:, np.arange(m.nv), np.arange(m.nv)] += hdt * Beff + hdt * hdt * Keff
         acc = np.linalg.solve(A, rhs[..., None])[..., 0]
         if return_parts:
             return dict(qacc=acc, M=M, bias=bias, tau=tau, tau_contact=tau_c, Rb=Rb, pb=pb, cb=cb, wb=wb, vcb=vcb,
                         Iw=Iw, fn=fn, xc=xc)
         return acc
+
+    def integrate_pos(self, q, qd, dt):
+        """q (+) dt * qd (unit quaternion for the rotation part of a free joint)."""
+        m = self.m
+        qn = q.copy()
+        for j in range(m.nv):
+            t = m.dof_type[j]
+            if t in (SLIDE, HINGE, FREE_TRANS):
+                qn[:, m.dof_qadr[j]] = q[:, m.dof_qadr[j]] + dt * qd[:, j]
+        for j in range(m.nv):
+            if m.dof_type[j] == FREE_ROT and (j == 0 or m.dof_type[j - 1] != FREE_ROT):
+                qa = m.dof_qadr[j]
+                w = qd[:, j:j + 3]
+                n = np.linalg.norm(w, axis=-1)
+                half = 0.5 * dt * n
+                s = np.where(n > 1e-8, np.sin(half) / np.maximum(n, 1e-30), 0.5 * dt)
+                dq = np.concatenate([np.cos(half)[:, None], w * s[:, None]], axis=-1)
+                qq = quat_mul(q[:, qa:qa + 4], dq)
+                qn[:, qa:qa + 4] = qq / np.linalg.norm(qq, axis=-1, keepdims=True)
+        return qn
+
+    def rk4_substep(self, q0, v0, ctrl):
+        """mj_RungeKutta(N = 4): A = diag(1/2, 1/2, 1), B = (1/6, 1/3, 1/3, 1/6)."""
+        dt = self.m.dt
+        b = (1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0)
+        nxt = (0.5, 0.5, 1.0)
+        q, v = q0, v0
+        vsum = np.zeros_like(v0)
+        asum = np.zeros_like(v0)
+        for i in range(4):
+            a = self.qacc(q, v, ctrl, implicit=True)
+            vsum = vsum + b[i] * v
+            asum = asum + b[i] * a
+            if i < 3:
+                q_next = self.integrate_pos(q0, v, dt * nxt[i])
+                v = v0 + dt * nxt[i] * a
+                q = q_next
+        return self.integrate_pos(q0, vsum, dt), v0 + dt * asum
 
     def integrate(self, q, qd, acc):
         m = self.m
@@ -260,8 +309,11 @@ class ArticulatedModel:
         m = self.m
         q, qd = state[:, :m.nq].copy(), state[:, m.nq:].copy()
         for _ in range(m.nsub):
-            acc = self.qacc(q, qd, action)
-            q, qd = self.integrate(q, qd, acc)
+            if self.integrator == "rk4":
+                q, qd = self.rk4_substep(q, qd, action)
+            else:
+                acc = self.qacc(q, qd, action)
+                q, qd = self.integrate(q, qd, acc)
         return np.concatenate([q, qd], axis=-1)
 
     def observe(self, state):
@@ -298,7 +350,7 @@ class ArticulatedModel:
         return kin, pot
 
 
-def make_model(name, obs_skip=None) -> ArticulatedModel:
+def make_model(name, obs_skip=None, integrator=None) -> ArticulatedModel:
     if obs_skip is None:      # HalfCheetah's 17-wide observation drops qpos[0]; every other env keeps the full state
         obs_skip = 1 if name == "halfcheetah" else 0
-    return ArticulatedModel(get_model(name), obs_skip=obs_skip)
+    return ArticulatedModel(get_model(name), obs_skip=obs_skip, integrator=integrator)

@@ -74,8 +74,9 @@ int chain_host_rollout(const icem_articulated_model_t* a, int act_dim, int integ
                        const double* start, const float* actions, double* states_out) {
   icem::ChainModel m;
   const char* w = "";
-  if (!icem::build_chain_model(icem::chain_source(*a), act_dim, m, &w)) return 1;
-  m.integrator = integrator;
+  icem::ChainSource src = icem::chain_source(*a);
+  src.integrator = integrator;
+  if (!icem::build_chain_model(src, act_dim, m, &w)) return 1;
   const int G = m.lanes, ns = m.nq + m.nv;
   std::vector<float> shared(m.s_end + 8, 0.f), xbuf(4 * 32, 0.f);
   std::vector<std::vector<float>> priv(G, std::vector<float>(m.p_end + 8, 0.f));

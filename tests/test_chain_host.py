@@ -1,0 +1,86 @@
+"""CPU parity of the branch-parallel articulated engine: icem_b200/csrc/dyn_chain.cuh -- the source the CUDA kernels
+run -- is compiled for the HOST (tests/chain_host/chain_host.cpp, one thread per lane of a group, float32) and compared
+with the independent float64 oracle (oracle/articulated_np.py) on the same tables.  Test infrastructure only: the
+product package never loads this library.
+
+Tolerances (float32 articulated-body algorithm vs float64 Jacobian formulation + LAPACK solve):
+  one env step from the same state   |d state| <= 2e-4   (HalfCheetah / Hopper / Humanoid*: measured <= 8e-5)
+                                     Ant: <= 5e-4 (soft contacts on a 0.4 kg torso sphere amplify rounding)
+  free-running h-step rollouts       stay within 5e-3 of the oracle for the first 10 control steps
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from icem_b200 import robots
+from icem_b200._lib import fptr
+from icem_b200.planner import articulated_model_struct
+from oracle.articulated_np import make_model
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "chain_host", "chain_host.cpp")
+OUT = os.path.join(ROOT, "build", "libchain_host.so")
+DEPS = [SRC, os.path.join(ROOT, "icem_b200", "csrc", "dyn_chain.cuh"), os.path.join(ROOT, "include", "icem_b200.h")]
+
+
+@pytest.fixture(scope="module")
+def host_lib():
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(d) for d in DEPS):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", SRC, "-o", OUT], check=True)
+    lib = C.CDLL(OUT)
+    lib.chain_host_describe.restype = C.c_int
+    lib.chain_host_rollout.restype = C.c_int
+    return lib
+
+
+def _describe(lib, name):
+    m = robots.get_model(name)
+    st, keep = articulated_model_struct(m)
+    out = (C.c_int * 8)()
+    why = C.create_string_buffer(128)
+    rc = lib.chain_host_describe(C.byref(st), m.nu, out, why, 128)
+    return rc, list(out), why.value.decode()
+
+
+def test_decomposition_of_the_reference_robots(host_lib):
+    """trunk + limb chains: lanes per trajectory, trunk bodies, limbs, nodes after fusing jointless bodies."""
+    want = {"halfcheetah": (2, 1, 2, 7), "humanoid_standup": (4, 3, 4, 11), "hopper": (1, 1, 1, 4),
+            "ant": (4, 1, 4, 9), "humanoid": (4, 3, 4, 11)}
+    for name, (lanes, trunk, limbs, nodes) in want.items():
+        rc, out, why = _describe(host_lib, name)
+        assert rc == 0, (name, why)
+        assert tuple(out[:4]) == (lanes, trunk, limbs, nodes), (name, out)
+        assert out[6] * 4 <= 32 * 1024, "scratch per warp must stay small enough for >= 6 warps per SM"
+
+
+@pytest.mark.parametrize("integrator", ["euler", "rk4"])
+@pytest.mark.parametrize("name,tol", [("halfcheetah", 2e-4), ("humanoid_standup", 2e-4), ("hopper", 2e-4),
+                                      ("ant", 5e-4), ("humanoid", 2e-4)])
+def test_host_compiled_engine_matches_float64_oracle(host_lib, name, tol, integrator):
+    m = robots.get_model(name, integrator=integrator)
+    st, keep = articulated_model_struct(m)
+    mod = make_model(name, obs_skip=0, integrator=integrator)
+    rs = np.random.RandomState(5)
+    n, h = 12, 10
+    start = np.concatenate([m.qpos0, 0.1 * rs.randn(m.nv)])
+    acts = rs.uniform(-1.3 * m.ctrl_limit, 1.3 * m.ctrl_limit, (n, h, m.nu)).astype(np.float32)   # also beyond the clip
+    states = np.zeros((n, h + 1, m.nq + m.nv))
+    rc = host_lib.chain_host_rollout(C.byref(st), m.nu, {"euler": 0, "rk4": 1}[integrator], n, h, start.ctypes.data_as(C.POINTER(C.c_double)),
+                                     fptr(acts), states.ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc == 0
+    np.testing.assert_allclose(states[:, 0], np.broadcast_to(start.astype(np.float32), (n, start.size)), atol=0)
+    # teacher forcing: one oracle step from every state the engine visited
+    worst = 0.0
+    for t in range(h):
+        ref = mod.step_state(states[:, t], acts[:, t].astype(np.float64))
+        worst = max(worst, float(np.abs(ref - states[:, t + 1]).max()))
+    assert worst <= tol, worst
+    # free running
+    s = np.broadcast_to(start.astype(np.float32).astype(np.float64), (n, start.size)).copy()
+    for t in range(h):
+        s = mod.step_state(s, acts[:, t].astype(np.float64))
+    assert np.abs(s - states[:, h]).max() <= (5e-2 if name == "ant" else 5e-3)

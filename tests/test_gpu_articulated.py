@@ -1,7 +1,8 @@
-"""GPU parity of the articulated ground-truth path (csrc/dyn_articulated.cuh through the C ABI) against the
-independent float64 oracle (oracle/articulated_np.py) on the same tables.
+"""GPU parity of the articulated ground-truth path (csrc/dyn_chain.cuh -- or csrc/dyn_articulated.cuh with
+ICEM_B200_ENGINE=warp -- through the C ABI) against the independent float64 oracle (oracle/articulated_np.py) on the
+same tables, for both integrators (semi-implicit Euler, four-stage Runge-Kutta).
 
-Tolerances (fp32 spatial-vector RNEA/CRBA + in-register Cholesky vs float64 Jacobian formulation + LAPACK):
+Tolerances (fp32 articulated-body algorithm / RNEA+CRBA+Cholesky vs float64 Jacobian formulation + LAPACK):
   one env step from the same state     |d state| <= 2e-4        (measured: median 1e-5, max 5e-5)
   h=30 trajectory cost                 median |d| <= 1e-4, 95 % of the population within 5e-3, elite set exact;
                                        contact make/break events amplify fp32 rounding over 150 substeps, so a
@@ -34,24 +35,28 @@ def _cost_fn(name):
     return costs_np.humanoid_standup_cost
 
 
-def _planner(name, n=64, iters=3, **over):
+INTEGRATORS = ["euler", "rk4"]
+
+
+def _planner(name, n=64, iters=3, integrator="euler", **over):
     from icem_b200.planner import Planner, PlannerSettings
     from icem_b200.robots import get_model
-    m = get_model(name)
+    m = get_model(name, integrator=integrator)
     sp = SPECS[name]
     lim = m.ctrl_limit
     kw = dict(horizon=30, num_simulated_trajectories=n, action_low=-lim * np.ones(m.nu, np.float32),
               action_high=lim * np.ones(m.nu, np.float32), dynamics=name, cost=sp["cost"], obs_dim=sp["obs_dim"],
               penalise_flipping=True, factor_decrease_num=1.25, opt_iterations=iters, noise_beta=sp["beta"],
-              keep_iteration_actions=True)
+              keep_iteration_actions=True, integrator=integrator)
     kw.update(over)
     return Planner(PlannerSettings(**kw)), m
 
 
+@pytest.mark.parametrize("integrator", INTEGRATORS)
 @pytest.mark.parametrize("name", sorted(SPECS))
-def test_env_step_matches_oracle(name):
-    p, m = _planner(name)
-    mod = make_model(name)
+def test_env_step_matches_oracle(name, integrator):
+    p, m = _planner(name, integrator=integrator)
+    mod = make_model(name, integrator=integrator)
     rs = np.random.RandomState(0)
     st = np.concatenate([m.qpos0, 0.1 * rs.randn(m.nv)])
     for t in range(40):
@@ -61,6 +66,9 @@ def test_env_step_matches_oracle(name):
         assert np.abs(got - ref).max() <= 2e-4, (t, np.abs(got - ref).max())
         np.testing.assert_allclose(obs, mod.observe(got), atol=1e-6)
         st = ref
+    if integrator != "euler":
+        p.close()
+        return
     # golden fixture of the oracle (tests/golden/articulated_<name>.npz): first transitions from its start state
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"articulated_{name}.npz"))
     st = g["start"]
@@ -71,10 +79,11 @@ def test_env_step_matches_oracle(name):
     p.close()
 
 
+@pytest.mark.parametrize("integrator", INTEGRATORS)
 @pytest.mark.parametrize("name", sorted(SPECS))
-def test_rollout_costs_match_oracle(name):
-    p, m = _planner(name)
-    mod = make_model(name)
+def test_rollout_costs_match_oracle(name, integrator):
+    p, m = _planner(name, integrator=integrator)
+    mod = make_model(name, integrator=integrator)
     rs = np.random.RandomState(3)
     n = 96
     lim = m.ctrl_limit
