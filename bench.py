@@ -206,6 +206,69 @@ def build_controller(name, world, rank, device):
     return ctrl, env
 
 
+def strong_and_digest(world, rank, local, steps):
+    """What the weak-scaling line cannot show (BASELINE configs[4]):
+
+    strong       plan-step time at a FIXED global population of 262144 HumanoidStandup trajectories sharded over the
+                 ranks (131072 / 65536 / 32768 per GPU at 2 / 4 / 8), device-timed, max over ranks;
+    plan_digest  sha256 over the executed actions and the last iteration's elite index lists of 3 closed-loop plan
+                 steps at a fixed global N = 16384: identical digests at 1, 2, 4, 8 GPUs = the sharded plan is
+                 bit-identical to the single-GPU plan (global trajectory indices key the Philox draws, the merge is
+                 a total order on (cost, global index));
+    exchange_us  one elite all-gather + merge/refit kernel (the only data-path collective), CUDA events."""
+    import hashlib
+    from icem_b200 import workloads
+    from icem_b200.planner import Planner
+    name = DEFAULT_WORKLOAD
+    out = {}
+    # ---- digest ----
+    s = workloads.planner_settings(name, world_size=world, rank=rank, device=local, seed=0)
+    p = Planner(s)
+    if world > 1:
+        from icem_b200.distributed import init_planner_comm
+        init_planner_comm(p)
+    p.begin_rollout()
+    state = workloads.start_state(name, seed=0)
+    h = hashlib.sha256()
+    for _ in range(3):
+        act = p.plan(state)
+        rec = p.iteration_record(s.opt_iterations - 1)
+        h.update(np.asarray(act, np.float32).tobytes())
+        h.update(np.asarray(rec["elite_idx"], np.int32).tobytes())
+        state, _, _ = p.sim_step(state, act)
+    out["plan_digest"] = {"sha256": h.hexdigest(), "global_population": s.num_simulated_trajectories,
+                          "closed_loop_steps": 3, "what": "executed actions (f32) + last-iteration elite indices (i32)"}
+    if world > 1:
+        ms = p.bench_op("exchange", 0, reps=50, flush_l2=False)
+        out["exchange_us"] = {"value": 1e3 * max_over_ranks(ms, world), "what": "ncclAllGather of k elite records per "
+                              "rank + merge_refit_kernel, per CEM iteration, CUDA events, max over ranks",
+                              "bytes_per_rank": 8 * p.k + 4 * p.k * ((s.horizon * p.d + 3) // 4 * 4)}
+    p.close()
+    # ---- strong scaling at global N = 262144 ----
+    n_global = 262144
+    s2 = workloads.planner_settings(name, world_size=world, rank=rank, device=local, seed=0,
+                                    scale_population=n_global // s.num_simulated_trajectories)
+    p2 = Planner(s2)
+    if world > 1:
+        from icem_b200.distributed import init_planner_comm
+        init_planner_comm(p2)
+    p2.begin_rollout()
+    p2.plan(workloads.start_state(name, seed=0))
+    barrier(world)
+    k_steps = max(2, min(int(steps), 5))
+    total_ms, _, _ = p2.bench_device(k_steps, 3, flush_l2=True)
+    barrier(world)
+    total_ms = max_over_ranks(total_ms, world)
+    traj = workloads.trajectories_per_step(s2, first_step=False)
+    out["strong"] = {"workload": "humanoid_standup_gt global N=262144 (BASELINE configs[4])", "scaling": "strong",
+                     "global_population": n_global, "per_gpu_population": -(-n_global // world), "n_gpus": world,
+                     "steps": k_steps, "warmup": 3, "ms_per_step": total_ms / k_steps,
+                     "value": k_steps * traj / (total_ms * 1e-3), "unit": UNIT,
+                     "populations_global": workloads.populations(s2)}
+    p2.close()
+    return out
+
+
 def run_ours(args):
     rank, world, local = dist_setup(args.gpus)
     import torch  # noqa: F401  (device memory / streams / torch.distributed are plumbing here)
@@ -268,7 +331,9 @@ def run_ours(args):
         except Exception:
             compute = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "rollout_kernel<sample,rollout> (fused)",
+                "traffic": traffic, "peak_source": peak_src,
+                "kernel": ("chain_rollout_kernel<sample,rollout> (fused sample->rollout->cost, branch-parallel "
+                           "articulated engine)") if w.get("env") else "rollout_kernel<sample,rollout> (fused)",
                 "kernel_ms_avg": avg_kernel_ms, "kernel_share_of_step": rollout_ms / max(total_ms, 1e-9)
                 if world == 1 else None,
                 "algorithmic_bytes_per_trajectory": bytes_per_traj,
@@ -337,11 +402,15 @@ def run_ours(args):
                "call": "icem_plan on every rank (host state in, action out)"}
         planner2.close()
 
+    # ---- configs[4]: strong scaling at global N = 262144 + bit-identity digest (default workload only) ----
+    extra = {}
+    if name == DEFAULT_WORKLOAD and not args.no_strong:
+        extra = strong_and_digest(world, rank, local, args.steps)
+
     # ---- CPU baseline beside it (rank 0, single GPU run only) -------------------------------------------
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
-        from oracle import cpu_bench
-        cpu = cpu_bench.run(name, cores=os.cpu_count() or 1, budget_s=15.0)
+        cpu = cpu_baseline(name, budget_s=15.0, steps=2)
 
     if rank == 0:
         line = {
@@ -352,33 +421,59 @@ def run_ours(args):
                        "num_simulated_trajectories_global": s.num_simulated_trajectories,
                        "populations_global": workloads.populations(s), "opt_iterations": s.opt_iterations,
                        "noise_beta": s.noise_beta, "trajectories_per_step": traj_step,
+                       "integrator": (s.integrator or "euler") if w.get("env") else None,
                        "sharding": f"num_sim_traj over {world} rank(s), one NCCL all-gather of elites per CEM iteration"
                        if world > 1 else "single GPU",
                        "l2": "256 MiB memset between timed steps (L2 flush)"},
             "clocks": clk, "e2e": e2e, "gpu_launches": launches_timed, "roofline": roofline,
             "cpu_baseline": cpu,
         }
+        line.update(extra)
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
 
 
+def cpu_baseline(name, budget_s, steps):
+    """The reference's CPU path on this box's host cores: the UNMODIFIED reference `MpcICem` when its sources are
+    present (kind "reference": /root/reference in the build container, baseline/_ref/icem staged on a GPU box by
+    scripts/stage_reference.sh), else the NumPy oracle port of the same plan step (kind "port")."""
+    import contextlib
+    from oracle import cpu_bench, ref_loader
+    from icem_b200 import workloads
+    cores = os.cpu_count() or 1
+    with contextlib.redirect_stdout(sys.stderr):          # the reference prints; stdout carries the ONE JSON line
+        if ref_loader.reference_available() and workloads.get_workload(name).get("env"):
+            try:
+                return cpu_bench.run_reference(name, cores=cores, budget_s=budget_s, steps=steps)
+            except Exception as e:                            # never lose the bench line over the baseline leg
+                sys.stderr.write(f"reference arm failed ({e!r}); falling back to the oracle port\n")
+        return cpu_bench.run(name, cores=cores, budget_s=budget_s, steps=steps, warmup=0)
+
+
 def run_reference(args):
-    """The reference's own CPU implementation of the path, all host cores (oracle/_ref is not applicable: the
-    reference is pure Python).  Rank 0 only."""
+    """`--impl reference`: the reference's own CPU implementation of the path with all host cores (see cpu_baseline).
+    Rank 0 only.  The reference is pure Python, so there is no oracle/_ref to compile; it is imported from its sources.
+    `steps` / `warmup` in the line are what was actually run (a CPU plan step at the full population takes minutes:
+    each step is a bounded sample, population stated in `config`)."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    from oracle import cpu_bench
     name = args.workload or (DEFAULT_WORKLOAD if world == 1 else DEFAULT_SHARD_WORKLOAD)
-    cores = os.cpu_count() or 1
-    res = cpu_bench.run(name, cores=cores, budget_s=25.0, steps=max(1, min(args.steps, 3)), warmup=0)
+    steps = max(1, min(args.steps, 2))
+    res = cpu_baseline(name, budget_s=25.0, steps=steps)
+    from icem_b200 import workloads
+    s = workloads.planner_settings(name)
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "sample": res["sample"]},
+            "steps": steps, "warmup": 0, "steps_requested": args.steps, "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "horizon": s.horizon, "act_dim": len(s.action_low),
+                       "opt_iterations": s.opt_iterations, "noise_beta": s.noise_beta,
+                       "population": res.get("population"), "population_scaled_from": s.num_simulated_trajectories,
+                       "same_population_as_gpu_arm": res.get("population") == s.num_simulated_trajectories,
+                       "sample": res["sample"]},
             "cpu_baseline": res,
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -392,6 +487,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling / digest legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

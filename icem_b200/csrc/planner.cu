@@ -1680,9 +1680,36 @@ int icem_bench_device(icem_planner_t* p, int32_t steps, int32_t warmup, int32_t 
 int icem_bench_op(icem_planner_t* p, int32_t op, int32_t n, int32_t reps, int32_t flush_l2, float* ms_avg) {
   ICEM_API_BEGIN
   if (!p || !ms_avg) throw InvalidArg("null argument");
-  if (n < p->k || reps < 1 || op < 0 || op > 3) throw InvalidArg("bad n / reps / op");
+  if (reps < 1 || op < 0 || op > 4 || (op != 4 && n < p->k)) throw InvalidArg("bad n / reps / op");
   require_model(p);
   ICEM_CUDA(cudaSetDevice(p->cfg.device));
+  if (op == 4) {
+    // the exchange step of a sharded plan step alone: all-gather of the per-rank elite records + the deterministic
+    // merge / refit every rank then runs (latency bound -- report microseconds, not GB/s)
+    if (p->cfg.world_size < 2 || !p->comm.ready()) throw StateError("op 4 needs a sharded planner (icem_comm_init)");
+    if (!p->was_reset) throw StateError("beginning_of_rollout() needs to be called before");
+    write_step_in(p, nullptr);
+    ICEM_CUDA(cudaMemcpyAsync(p->step_in.p, p->h_in, sizeof(StepState), cudaMemcpyHostToDevice, p->stream));
+    enqueue_iterations(p, false);            // fills the send records with real elites
+    const RefitArgs r0 = refit_args(p, 0);
+    double tot4 = 0;
+    for (int it = 0; it < reps + 3; ++it) {
+      ICEM_CUDA(cudaEventRecord(p->ev_a, p->stream));
+      p->comm.all_gather(p->send_rec.p, p->recv_rec.p, p->rec_bytes, p->stream);
+      merge_refit_kernel<<<1, kSelectThreads, select_smem(p->k), p->stream>>>(r0);
+      ICEM_CUDA(cudaGetLastError());
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      ICEM_CUDA(cudaEventRecord(p->ev_b, p->stream));
+      ICEM_CUDA(cudaStreamSynchronize(p->stream));
+      float ms = 0;
+      ICEM_CUDA(cudaEventElapsedTime(&ms, p->ev_a, p->ev_b));
+      if (it >= 3) tot4 += ms;
+    }
+    *ms_avg = (float)(tot4 / reps);
+    reset_distribution(p);
+    ICEM_CUDA(cudaStreamSynchronize(p->stream));
+    return ICEM_OK;
+  }
   DevBuf<float> d_act, d_cost;
   d_act.alloc((size_t)n * p->stride);
   d_cost.alloc(n);

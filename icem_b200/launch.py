@@ -26,7 +26,18 @@ import os
 import sys
 import types
 
-DEFAULT_REFERENCE = os.environ.get("ICEM_REFERENCE_ROOT", "/root/reference/icem")
+def _default_reference():
+    env = os.environ.get("ICEM_REFERENCE_ROOT")
+    if env:
+        return env
+    staged = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "icem")
+    for cand in ("/root/reference/icem", staged):
+        if os.path.isfile(os.path.join(cand, "main.py")):
+            return cand
+    return "/root/reference/icem"
+
+
+DEFAULT_REFERENCE = _default_reference()
 
 
 def prepare_paths(reference_root=DEFAULT_REFERENCE, shims=None):

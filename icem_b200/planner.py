@@ -355,7 +355,7 @@ class Planner:
     def bench_op(self, op, n, reps=20, flush_l2=True):
         """Average launch duration (ms) of one kernel in isolation: op 0 sampler, 1 fused rollout, 2 select+refit."""
         ms = C.c_float()
-        check(self._lib.icem_bench_op(self._h, {"sample": 0, "fused": 1, "select": 2, "rollout": 3}.get(op, op), int(n), int(reps),
+        check(self._lib.icem_bench_op(self._h, {"sample": 0, "fused": 1, "select": 2, "rollout": 3, "exchange": 4}.get(op, op), int(n), int(reps),
                                       int(bool(flush_l2)), C.byref(ms)))
         return ms.value
 

@@ -285,6 +285,8 @@ int icem_bench_device(icem_planner_t* p, int32_t steps, int32_t warmup, int32_t 
  *   op 1: fused sample -> rollout -> cost (one CEM iteration's dominant kernel)
  *   op 2: elite selection + refit on n costs (controllers/icem.py:194-211)
  *   op 3: rollout + cost of GIVEN action tiles (the tensor-core kernel for ICEM_DYN_MLP)
+ *   op 4: sharded planners only (every rank must call it): one NCCL all-gather of the per-rank elite records + the
+ *         merge / refit kernel, i.e. the exchange step of a CEM iteration; n is ignored
  * flush_l2 != 0 writes a 256 MiB buffer between launches. */
 int icem_bench_op(icem_planner_t* p, int32_t op, int32_t n, int32_t reps, int32_t flush_l2, float* ms_avg);
 

@@ -10,7 +10,20 @@ import collections.abc
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("ICEM_REFERENCE_ROOT", "/root/reference/icem")
+def _find_reference():
+    """ICEM_REFERENCE_ROOT, else the read-only checkout of this container, else the copy staged for the GPU box
+    (scripts/stage_reference.sh -> baseline/_ref/icem: git-ignored, shipped by gpurun, never committed)."""
+    env = os.environ.get("ICEM_REFERENCE_ROOT")
+    if env:
+        return env
+    staged = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "icem")
+    for cand in ("/root/reference/icem", staged):
+        if os.path.isfile(os.path.join(cand, "controllers", "icem.py")):
+            return cand
+    return "/root/reference/icem"
+
+
+REFERENCE_ROOT = _find_reference()
 SHIM_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
 
 

@@ -54,3 +54,61 @@ def test_plan_step_is_self_consistent_at_full_size(name):
     assert not np.array_equal(r.plan(start), a1)
     for x in (p, q, r):
         x.close()
+
+
+@pytest.mark.parametrize("name,robot", [("halfcheetah_gt_n4096", "halfcheetah"),
+                                        ("humanoid_standup_gt_n16384", "humanoid_standup")])
+def test_full_size_population_rescored_by_the_float64_oracle(name, robot):
+    """The float64 oracle (oracle/articulated_np.py) scores trajectories OF THE FULL-SIZE POPULATIONS (N = 4096 x 5,
+    16384 x 3 iterations): after a plan step, the device's 32 cheapest fresh rows of the last iteration plus 256 random
+    rows of it are rolled out again on the CPU.
+
+      * median |device cost - oracle cost| <= 1e-4 over those ~288 trajectories (95 % within 5e-3: contact make / break
+        events amplify fp32 rounding over 150 substeps);
+      * the device's 10 cheapest rows == the oracle's 10 cheapest of the re-scored union, whenever the oracle's gap
+        between rank 10 and 11 exceeds 4x the error measured on those candidates (else the sets must still agree up
+        to rows inside that gap)."""
+    from icem_b200 import workloads
+    from icem_b200.planner import Planner
+    from oracle import costs_np
+    from oracle.articulated_np import make_model
+    from oracle.icem_np import reduce_costs
+    s = dataclasses.replace(workloads.planner_settings(name, seed=5), keep_iteration_actions=True)
+    p = Planner(s)
+    start = workloads.start_state(name, seed=2)
+    p.begin_rollout()
+    p.plan(start)
+    last = s.opt_iterations - 1
+    n_last = p.population_size(last, first_step=True)[1]
+    acts = p.actions(last, n_last)
+    costs = p.costs(last, n_last)
+    p.close()
+    order_dev = np.argsort(costs, kind="stable")
+    rs = np.random.RandomState(0)
+    rows = np.unique(np.concatenate([order_dev[:32], rs.choice(n_last, 256, replace=False)]))
+    mod = make_model(robot)
+    start32 = np.asarray(start, np.float32).astype(np.float64)        # the device holds the start state in fp32
+    obs = mod.rollout(start32, acts[rows].astype(np.float64))
+    if robot == "halfcheetah":
+        per_step = costs_np.halfcheetah_cost(obs, acts[rows].astype(np.float64), True)
+    else:
+        per_step = costs_np.humanoid_standup_cost(obs, acts[rows].astype(np.float64))
+    ref = reduce_costs(per_step, "sum")
+    d = np.abs(costs[rows] - ref)
+    assert np.median(d) <= 1e-4, np.median(d)
+    assert np.mean(d <= 5e-3) >= 0.95, np.sort(d)[-8:]
+    k = 10
+    order_ref = rows[np.argsort(ref, kind="stable")]
+    ref_sorted = np.sort(ref, kind="stable")
+    cand = np.isin(rows, np.concatenate([order_ref[: k + 2], order_dev[: k + 2]]))
+    err = float(d[cand].max())
+    gap = float(ref_sorted[k] - ref_sorted[k - 1])
+    dev_top = [r for r in order_dev if r in set(rows.tolist())][:k]
+    if gap > 4 * err:
+        assert set(dev_top) == set(order_ref[:k].tolist()), (gap, err)
+    else:
+        # near-tie at the elite boundary: every disagreement must lie inside the error band around the k-th cost
+        band = ref_sorted[k - 1] + 4 * err
+        diff = set(dev_top) ^ set(order_ref[:k].tolist())
+        lut = dict(zip(rows.tolist(), ref.tolist()))
+        assert all(abs(lut[r] - ref_sorted[k - 1]) <= 4 * err + 1e-12 or lut[r] <= band for r in diff), (gap, err, diff)

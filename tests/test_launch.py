@@ -5,7 +5,11 @@
   (b) through icem_b200.launch with controller "mpc-icem-b200" + forward model "CudaGroundTruthModel": every layer up
       to the C ABI is exercised and, because this container has no GPU, icem_create must fail LOUDLY (no CPU fallback).
 
-Both need /root/reference (absent on the GPU box -> skipped there)."""
+  (c) on a GPU (marker `gpu`): the same launcher run finishes -- the unchanged main.py drives MpcICemB200 for a few env
+      steps, checkpoints are written -- and `elite_samples` is the reference's own RolloutBuffer.
+
+All need the reference sources: /root/reference in the build container, or the copy staged for GPU boxes by
+scripts/stage_reference.sh (baseline/_ref/icem, found by oracle/ref_loader.py); skipped when neither exists."""
 import json
 import os
 import subprocess
@@ -121,3 +125,58 @@ def test_example_settings_resolve_through_the_reference_loader(tmp_path):
         "    assert p['rollout_params']['use_env_states'] is True\n" % (ROOT, os.path.join(ROOT, "oracle", "shims"), ROOT))
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_unchanged_main_drives_the_b200_controller_on_the_gpu(tmp_path):
+    """(c) T7 on the device: icem/main.py (unchanged) -> ControllerFactory -> MpcICemB200 -> C ABI -> CUDA kernels,
+    3 env steps, checkpoint written (reference: icem/main.py:82-243, misc/rollout_utils.py:155-227)."""
+    path = _settings(tmp_path, controller="mpc-icem-b200", forward_model="CudaGroundTruthModel",
+                     forward_model_params={"num_parallel": 8})
+    cfg = json.load(open(path))
+    cfg["controller_params"]["num_simulated_trajectories"] = 64
+    cfg["controller_params"]["action_sampler_params"]["elites_size"] = 10
+    cfg["rollout_params"]["task_horizon"] = 3
+    json.dump(cfg, open(path, "w"))
+    res = subprocess.run([sys.executable, "-m", "icem_b200.launch", path, "--reference", ref_loader.REFERENCE_ROOT,
+                          "--shims", os.path.join(ROOT, "oracle", "shims")], cwd=str(tmp_path), capture_output=True,
+                         text=True, timeout=900, env=dict(os.environ, PYTHONPATH=ROOT))
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert "iCEM using" in res.stdout                                   # banner of MpcICemB200 (controllers/icem.py:42-43)
+    out = tmp_path / "results"
+    assert (out / "settings.json").exists() and (out / "checkpoints_latest").exists()
+
+
+@pytest.mark.gpu
+def test_elite_samples_are_the_reference_rolloutbuffer_on_the_gpu(tmp_path):
+    """With the reference importable the controller's `elite_samples` must be the reference's own RolloutBuffer of
+    Rollout objects (misc/rolloutbuffer.py:10-54,125-281), not the stand-in of icem_b200.api."""
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from icem_b200 import launch\n"
+        "launch.prepare_paths(%r, shims=%r); launch.register()\n"
+        "from environments import env_from_string\n"
+        "from controllers import controller_from_string\n"
+        "from models import forward_model_from_string\n"
+        "env = env_from_string('HalfCheetah', penalise_flipping=True, exclude_current_positions_from_observation=True)\n"
+        "fm = forward_model_from_string('CudaGroundTruthModel')(env=env)\n"
+        "cls = controller_from_string('mpc-icem-b200')\n"
+        "ctrl = cls(env=env, forward_model=fm, horizon=30, num_simulated_trajectories=64, factor_decrease_num=1.25,\n"
+        "           cost_along_trajectory='sum', action_sampler_params=dict(alpha=0.1, elites_size=10,\n"
+        "           opt_iterations=3, init_std=0.5, use_mean_actions=True, keep_previous_elites=True,\n"
+        "           shift_elites_over_time=True, fraction_elites_reused=0.3, noise_beta=0.25), seed=1)\n"
+        "obs = env.reset(); st = env.get_GT_state()\n"
+        "ctrl.beginning_of_rollout(observation=obs, state=st, mode='train')\n"
+        "a = ctrl.get_action(obs, state=st, mode='train')\n"
+        "es = ctrl.elite_samples\n"
+        "from misc.rolloutbuffer import RolloutBuffer, Rollout\n"
+        "assert type(es) is RolloutBuffer, type(es)\n"
+        "assert len(es) == 10 and isinstance(es[0], Rollout)\n"
+        "acts = es.as_array('actions'); obs_ = es.as_array('observations')\n"
+        "assert acts.shape == (10, 30, 6) and obs_.shape == (10, 30, 17), (acts.shape, obs_.shape)\n"
+        "np.testing.assert_allclose(acts[0, 0], a, atol=1e-6)\n"
+        "print('reference RolloutBuffer OK')\n" % (ROOT, ref_loader.REFERENCE_ROOT, os.path.join(ROOT, "oracle", "shims")))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert "reference RolloutBuffer OK" in res.stdout
