@@ -213,7 +213,11 @@ struct Articulated {
         if (t == kFreeTrans) {                 // free joint (root): 3 translations + ball, S directly in world
           const int qa = m.d_qadr[j];
           p[0] = q[qa]; p[1] = q[qa + 1]; p[2] = q[qa + 2];
-          const float qw = q[qa + 3], x = q[qa + 4], y = q[qa + 5], z = q[qa + 6];
+          float qw = q[qa + 3], x = q[qa + 4], y = q[qa + 5], z = q[qa + 6];
+          {   // rotation of the NORMALISED quaternion (a start state may carry reset noise on it)
+            const float qn = rsqrtf(qw * qw + x * x + y * y + z * z);
+            qw *= qn; x *= qn; y *= qn; z *= qn;
+          }
           R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - qw * z); R[2] = 2.f * (x * z + qw * y);
           R[3] = 2.f * (x * y + qw * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - qw * x);
           R[6] = 2.f * (x * z - qw * y); R[7] = 2.f * (y * z + qw * x); R[8] = 1.f - 2.f * (x * x + y * y);

@@ -122,6 +122,7 @@ def start_state(name, seed=0):
     if w["env"] == "HumanoidStandup":
         from .envs import humanoid_standup_qpos0
         qpos = humanoid_standup_qpos0() + rs.uniform(-0.01, 0.01, 24)
+        qpos[3:7] /= np.linalg.norm(qpos[3:7])          # a valid orientation (MuJoCo normalises the quaternion)
         qvel = rs.uniform(-0.01, 0.01, 23)
         return np.concatenate([qpos, qvel])
     obs_dim = w["dense"][0] if w.get("dense") else w["mlp"][0]

@@ -59,6 +59,9 @@ def _rodrigues(axis, angle):
 
 
 def quat_to_mat(q):
+    """Rotation matrix of the NORMALISED quaternion (MuJoCo normalises quaternions before using them, so a state
+    with gym's reset noise on qpos[3:7] is still a valid orientation)."""
+    q = q / np.linalg.norm(q, axis=-1, keepdims=True)
     w, x, y, z = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
     R = np.empty(q.shape[:-1] + (3, 3))
     R[..., 0, 0] = 1 - 2 * (y * y + z * z)
