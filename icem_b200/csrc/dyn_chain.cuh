@@ -59,7 +59,7 @@ constexpr int kChMaxTrunk = 4, kChMaxLimbs = 4, kChMaxLimbNodes = 4;
 // identical values, so nothing a lane still has to read may be overwritten there: (rhs, diag) get slots of their own.
 constexpr int kChDofRec = 19, kChTrunkDofRec = 21;
 constexpr int kChNodeRec = 16;    // mass, h(3), Io(6), bias force(6)
-constexpr int kChFrame = 18;      // R(9) p(3) v(6) of a trunk body that carries limbs
+constexpr int kChFrame = 18;      // R(9) p(3) v(6) of a trunk body
 constexpr int kChFreeRec = 24;    // free root: R(9) c_J linear part(3) | root acceleration(6) qacc(6) from pass 2
 constexpr int kChJun = 27;        // articulated inertia (6 + 9 + 6) + bias force (6) summed over the limbs of a junction
 enum { kChEuler = 0, kChRK4 = 1 };
@@ -267,195 +267,226 @@ struct ChainLane {
   }
 
   // ---- pass 1 ----------------------------------------------------------------------------------------------------
-  // `rec` returns the record (mass, h, Io, bias force) of the LAST node of this lane's walk: pass 2 starts with that
-  // node, so its record never goes through shared memory.  `implicit`: joint springs / dampers enter the system matrix
-  // (semi-implicit Euler); otherwise they are plain forces (RK4 stages).
+  // Joints of one node: frame (R, p) through the joints, motion axes S_j, velocity-product terms c_j, the joint-space
+  // force and the implicit spring / damper diagonal -> dof records; v becomes the node's velocity.
+  __host__ __device__ __forceinline__ void walk_joints(int node, bool root, bool trunk, float (&R)[9], float (&p)[3],
+                                                       float (&v)[6], float (&O)[3], const ChRef& q, const ChRef& qd,
+                                                       const ChRef& ctrl, float dt) {
+    const ChainModel& m = *M;
+    if (root) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) O[k] = m.n_pos[node][k];     // p stays 0: everything is relative to O
+    } else {
+      float off[3];
+      ch::matvec(R, m.n_pos[node], off);
+      p[0] += off[0]; p[1] += off[1]; p[2] += off[2];
+    }
+    int j0 = m.n_dof_start[node];
+    const int j1 = j0 + m.n_dof_count[node];
+    if (root && m.root_free) {
+      // free joint: 3 world translations + 3 body-frame rotation rates, handled as ONE 6-dof joint.  Its motion
+      // subspace spans all of R^6, so pass 2 solves the root acceleration directly (floating base) and no per-dof
+      // record is needed: only R and the velocity-product term  c_J = sum_k (v xm S_k) qd_k = [0; v_lin x w].
+      const int qa = m.d_qadr[j0];
+      O[0] = q[qa]; O[1] = q[qa + 1]; O[2] = q[qa + 2];
+      float qw = q[qa + 3], x = q[qa + 4], y = q[qa + 5], z = q[qa + 6];
+      {   // rotation of the NORMALISED quaternion (a start state may carry reset noise on it): R must be orthonormal,
+          // pass 2 turns the root's angular acceleration into rotation rates with R^T
+        const float qn = ch::rsqrt_(qw * qw + x * x + y * y + z * z);
+        qw *= qn; x *= qn; y *= qn; z *= qn;
+      }
+      R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - qw * z); R[2] = 2.f * (x * z + qw * y);
+      R[3] = 2.f * (x * y + qw * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - qw * x);
+      R[6] = 2.f * (x * z - qw * y); R[7] = 2.f * (y * z + qw * x); R[8] = 1.f - 2.f * (x * x + y * y);
+      const float w0 = qd[j0 + 3], w1 = qd[j0 + 4], w2 = qd[j0 + 5];
+      v[0] = R[0] * w0 + R[1] * w1 + R[2] * w2;
+      v[1] = R[3] * w0 + R[4] * w1 + R[5] * w2;
+      v[2] = R[6] * w0 + R[7] * w1 + R[8] * w2;
+      v[3] = qd[j0]; v[4] = qd[j0 + 1]; v[5] = qd[j0 + 2];
+      const ChRef fr = shared_rec(m.s_free);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) fr[k] = R[k];
+      float cl[3];
+      ch::cross(v + 3, v, cl);
+      fr[9] = cl[0]; fr[10] = cl[1]; fr[11] = cl[2];
+      j0 += 6;
+    }
+    for (int j = j0; j < j1; ++j) {
+      const int t = m.d_type[j];
+      float ax[3], S[6], c[6];
+      ch::matvec(R, m.d_axis[j], ax);
+      const float qj = q[m.d_qadr[j]], qdj = qd[j];
+      if (t == kSlide) {
+        S[0] = S[1] = S[2] = 0.f;
+        S[3] = ax[0]; S[4] = ax[1]; S[5] = ax[2];
+        float* dst = root ? O : p;           // root slides move the origin itself
+        dst[0] += ax[0] * qj; dst[1] += ax[1] * qj; dst[2] += ax[2] * qj;
+      } else {
+        float an[3];
+        ch::matvec(R, m.d_anchor[j], an);
+        an[0] += p[0]; an[1] += p[1]; an[2] += p[2];
+        S[0] = ax[0]; S[1] = ax[1]; S[2] = ax[2];
+        ch::cross(an, ax, S + 3);            // velocity at O of a unit rotation about the anchored axis
+        float sn, cs;
+        ch::sincos_(qj, &sn, &cs);
+        const float C = 1.f - cs;
+        const float Rj[9] = {cs + ax[0] * ax[0] * C, ax[0] * ax[1] * C - ax[2] * sn, ax[0] * ax[2] * C + ax[1] * sn,
+                             ax[1] * ax[0] * C + ax[2] * sn, cs + ax[1] * ax[1] * C, ax[1] * ax[2] * C - ax[0] * sn,
+                             ax[2] * ax[0] * C - ax[1] * sn, ax[2] * ax[1] * C + ax[0] * sn, cs + ax[2] * ax[2] * C};
+        float Rn[9];
+        ch::matmul(Rj, R, Rn);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+        const float dp[3] = {p[0] - an[0], p[1] - an[1], p[2] - an[2]};
+        float rp[3];
+        ch::matvec(Rj, dp, rp);
+        p[0] = an[0] + rp[0]; p[1] = an[1] + rp[1]; p[2] = an[2] + rp[2];
+      }
+      ch::cross_motion(v, S, c);             // the axis is fixed in the frame moving with v (before this joint)
+      // joint-space force and the implicit spring / damper diagonal (oracle/articulated_np.py:195-229)
+      float tau = 0.f;
+      const int act = m.d_act[j];
+      if (act >= 0) tau = m.d_gear[j] * fminf(fmaxf(ctrl[act], -m.ctrl_limit), m.ctrl_limit);
+      float keff = m.d_stiff[j], beff = m.d_damp[j];
+      tau -= keff * qj;
+      if (m.d_limited[j]) {
+        const bool below = qj < m.d_lo[j], above = qj > m.d_hi[j];
+        if (below) tau += m.d_klim[j] * (m.d_lo[j] - qj);
+        if (above) tau += m.d_klim[j] * (m.d_hi[j] - qj);
+        if (below || above) { keff += m.d_klim[j]; beff += m.d_blim[j]; }
+      }
+      const ChRef r = dof_rec(trunk, j);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) {
+        r[e] = S[e];
+        r[6 + e] = c[e] * qdj;
+        v[e] += S[e] * qdj;
+      }
+      r[trunk ? 19 : 17] = tau - (beff + dt * keff) * qdj;
+      r[trunk ? 20 : 18] = m.d_arm[j] + dt * beff + dt * dt * keff;
+    }
+  }
+
+  // Body-level work of one node given its frame and velocity: rigid inertia about O, bias force v x* I v minus the
+  // floor-contact wrenches -> rec = (mass, h, Io, bias force).
+  __host__ __device__ __forceinline__ void node_work(int node, const float (&R)[9], const float (&p)[3],
+                                                     const float (&v)[6], float Oz, float (&rec)[kChNodeRec]) const {
+    const ChainModel& m = *M;
+    const float mass = m.n_mass[node];
+    float c[3];
+    ch::matvec(R, m.n_com[node], c);
+    c[0] += p[0]; c[1] += p[1]; c[2] += p[2];
+    const float* I6 = m.n_inertia[node];
+    const float Im[9] = {I6[0], I6[3], I6[4], I6[3], I6[1], I6[5], I6[4], I6[5], I6[2]};
+    float T[9];
+    ch::matmul(R, Im, T);
+    float Io[6];
+    const float c2 = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+    Io[0] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2] + mass * (c2 - c[0] * c[0]);
+    Io[1] = T[3] * R[3] + T[4] * R[4] + T[5] * R[5] + mass * (c2 - c[1] * c[1]);
+    Io[2] = T[6] * R[6] + T[7] * R[7] + T[8] * R[8] + mass * (c2 - c[2] * c[2]);
+    Io[3] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5] - mass * c[0] * c[1];
+    Io[4] = T[0] * R[6] + T[1] * R[7] + T[2] * R[8] - mass * c[0] * c[2];
+    Io[5] = T[3] * R[6] + T[4] * R[7] + T[5] * R[8] - mass * c[1] * c[2];
+    const float h[3] = {mass * c[0], mass * c[1], mass * c[2]};
+    // I v = [Io w + h x vl ; m vl - h x w],  bias = v x* (I v) = [w x n + vl x f ; w x f]
+    float hv[3], hw[3], Iv[6], t1[3], t2[3], t3[3], f[6];
+    ch::cross(h, v + 3, hv);
+    ch::cross(h, v, hw);
+    Iv[0] = Io[0] * v[0] + Io[3] * v[1] + Io[4] * v[2] + hv[0];
+    Iv[1] = Io[3] * v[0] + Io[1] * v[1] + Io[5] * v[2] + hv[1];
+    Iv[2] = Io[4] * v[0] + Io[5] * v[1] + Io[2] * v[2] + hv[2];
+    Iv[3] = mass * v[3] - hw[0];
+    Iv[4] = mass * v[4] - hw[1];
+    Iv[5] = mass * v[5] - hw[2];
+    ch::cross(v, Iv, t1);
+    ch::cross(v + 3, Iv + 3, t2);
+    ch::cross(v, Iv + 3, t3);
+    f[0] = t1[0] + t2[0]; f[1] = t1[1] + t2[1]; f[2] = t1[2] + t2[2];
+    f[3] = t3[0]; f[4] = t3[1]; f[5] = t3[2];
+    const int k0 = m.n_con_start[node], k1 = k0 + m.n_con_count[node];
+    for (int k = k0; k < k1; ++k) {
+      // height first: most spheres are above the floor most of the time
+      const float xz = R[6] * m.c_pos[k][0] + R[7] * m.c_pos[k][1] + R[8] * m.c_pos[k][2] + p[2];
+      const float pen = m.c_radius[k] - (Oz + xz);
+      if (pen > 0.f) {
+        float x[3], u[3];
+        x[0] = R[0] * m.c_pos[k][0] + R[1] * m.c_pos[k][1] + R[2] * m.c_pos[k][2] + p[0];
+        x[1] = R[3] * m.c_pos[k][0] + R[4] * m.c_pos[k][1] + R[5] * m.c_pos[k][2] + p[1];
+        x[2] = xz;
+        ch::cross(v, x, u);
+        u[0] += v[3]; u[1] += v[4]; u[2] += v[5];
+        const float spring = m.kc * pen;
+        const float damp = fminf(spring * m.cc, m.cdmax);
+        const float fn = fminf(fmaxf(spring - damp * u[2], 0.f), 3.f * spring);
+        const float speed = sqrtf(u[0] * u[0] + u[1] * u[1]);
+        const float coef = fminf(m.kv, m.mu * fn * ch_rcp(fmaxf(speed, 1e-6f)));
+        const float fc[3] = {-coef * u[0], -coef * u[1], fn};
+        float mo[3];
+        ch::cross(x, fc, mo);
+        f[0] -= mo[0]; f[1] -= mo[1]; f[2] -= mo[2];
+        f[3] -= fc[0]; f[4] -= fc[1]; f[5] -= fc[2];
+      }
+    }
+    rec[0] = mass; rec[1] = h[0]; rec[2] = h[1]; rec[3] = h[2];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) { rec[4 + e] = Io[e]; rec[10 + e] = f[e]; }
+  }
+
+  // `rec` returns the record of the LAST node of this lane's limb: pass 2 starts with that node, so its record never
+  // goes through shared memory.  `implicit`: joint springs / dampers enter the system matrix (dt > 0 in the diagonal).
+  //   1. every lane walks the trunk's joints (identical values in all lanes; frames -> shared memory);
+  //   2. the trunk's BODY-level work (inertia, bias force, contacts) is dealt out: lane g takes trunk node g, g + G, ...
+  //      -- the lanes work on different nodes at the same time instead of all repeating all of them;
+  //   3. every lane walks its own limb (joints + body-level work).
   __host__ __device__ void pass1(const ChRef& q, const ChRef& qd, const ChRef& ctrl, bool implicit, float (&rec)[kChNodeRec]) {
     const ChainModel& m = *M;
     const float dt = implicit ? m.dt : 0.f;
     float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f}, p[3] = {0.f, 0.f, 0.f};
     float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float O[3] = {0.f, 0.f, 0.f};
-    const int n_seq = m.n_trunk + m.max_limb_nodes;
-    const int last = m.seq_last[g];
-    for (int i = 0; i < n_seq; ++i) {
-      int node, pos;
-      bool trunk;
-      const bool active = node_at(i, node, trunk, pos);
-      if (!active) continue;
-      if (!trunk && pos == 0) {      // the limb starts from the frame and velocity of the trunk body it hangs off
-        const ChRef f = shared_rec(m.s_frame + kChFrame * m.trunk_junction[m.limb_attach[g]]);
+    for (int t = 0; t < m.n_trunk; ++t) {
+      walk_joints(m.trunk_node[t], t == 0, true, R, p, v, O, q, qd, ctrl, dt);
+      const ChRef f = shared_rec(m.s_frame + kChFrame * t);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) R[k] = f[k];
+      for (int k = 0; k < 9; ++k) f[k] = R[k];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) p[k] = f[9 + k];
+      for (int k = 0; k < 3; ++k) f[9 + k] = p[k];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) v[k] = f[12 + k];
-      }
-      const bool root = i == 0;
-      if (root) {
+      for (int k = 0; k < 6; ++k) f[12 + k] = v[k];
+    }
+    const float Oz = O[2];
+    for (int t = g; t < m.n_trunk; t += m.lanes) {
+      const ChRef f = shared_rec(m.s_frame + kChFrame * t);     // written by this very lane a moment ago
 #pragma unroll
-        for (int k = 0; k < 3; ++k) O[k] = m.n_pos[node][k];     // p stays 0: everything is relative to O
-      } else {
-        float off[3];
-        ch::matvec(R, m.n_pos[node], off);
-        p[0] += off[0]; p[1] += off[1]; p[2] += off[2];
-      }
-      int j0 = m.n_dof_start[node];
-      const int j1 = j0 + m.n_dof_count[node];
-      if (root && m.root_free) {
-        // free joint: 3 world translations + 3 body-frame rotation rates, handled as ONE 6-dof joint.  Its motion
-        // subspace spans all of R^6, so pass 2 solves the root acceleration directly (floating base) and no per-dof
-        // record is needed: only R and the velocity-product term  c_J = sum_k (v xm S_k) qd_k = [0; v_lin x w].
-        const int qa = m.d_qadr[j0];
-        O[0] = q[qa]; O[1] = q[qa + 1]; O[2] = q[qa + 2];
-        float qw = q[qa + 3], x = q[qa + 4], y = q[qa + 5], z = q[qa + 6];
-        {   // rotation of the NORMALISED quaternion (a start state may carry reset noise on it): R must be orthonormal,
-            // pass 2 turns the root's angular acceleration into rotation rates with R^T
-          const float qn = ch::rsqrt_(qw * qw + x * x + y * y + z * z);
-          qw *= qn; x *= qn; y *= qn; z *= qn;
+      for (int k = 0; k < 9; ++k) R[k] = f[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) p[k] = f[9 + k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v[k] = f[12 + k];
+      node_work(m.trunk_node[t], R, p, v, Oz, rec);
+      const ChRef nr = shared_rec(m.s_node + kChNodeRec * t);
+#pragma unroll
+      for (int e = 0; e < kChNodeRec; ++e) nr[e] = rec[e];
+    }
+    if (g < m.n_limbs) {
+      const ChRef f = shared_rec(m.s_frame + kChFrame * m.limb_attach[g]);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) R[k] = f[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) p[k] = f[9 + k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v[k] = f[12 + k];
+      const int nn = m.limb_nnodes[g];
+      for (int i = 0; i < nn; ++i) {
+        const int node = m.limb_node[g][i];
+        walk_joints(node, false, false, R, p, v, O, q, qd, ctrl, dt);
+        node_work(node, R, p, v, Oz, rec);
+        if (i != nn - 1) {
+          const ChRef nr = private_rec(m.p_node + kChNodeRec * i);
+#pragma unroll
+          for (int e = 0; e < kChNodeRec; ++e) nr[e] = rec[e];
         }
-        R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - qw * z); R[2] = 2.f * (x * z + qw * y);
-        R[3] = 2.f * (x * y + qw * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - qw * x);
-        R[6] = 2.f * (x * z - qw * y); R[7] = 2.f * (y * z + qw * x); R[8] = 1.f - 2.f * (x * x + y * y);
-        const float w0 = qd[j0 + 3], w1 = qd[j0 + 4], w2 = qd[j0 + 5];
-        v[0] = R[0] * w0 + R[1] * w1 + R[2] * w2;
-        v[1] = R[3] * w0 + R[4] * w1 + R[5] * w2;
-        v[2] = R[6] * w0 + R[7] * w1 + R[8] * w2;
-        v[3] = qd[j0]; v[4] = qd[j0 + 1]; v[5] = qd[j0 + 2];
-        const ChRef fr = shared_rec(m.s_free);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) fr[k] = R[k];
-        float cl[3];
-        ch::cross(v + 3, v, cl);
-        fr[9] = cl[0]; fr[10] = cl[1]; fr[11] = cl[2];
-        j0 += 6;
-      }
-      for (int j = j0; j < j1; ++j) {
-        const int t = m.d_type[j];
-        float ax[3], S[6], c[6];
-        ch::matvec(R, m.d_axis[j], ax);
-        const float qj = q[m.d_qadr[j]], qdj = qd[j];
-        if (t == kSlide) {
-          S[0] = S[1] = S[2] = 0.f;
-          S[3] = ax[0]; S[4] = ax[1]; S[5] = ax[2];
-          float* dst = root ? O : p;           // root slides move the origin itself
-          dst[0] += ax[0] * qj; dst[1] += ax[1] * qj; dst[2] += ax[2] * qj;
-        } else {
-          float an[3];
-          ch::matvec(R, m.d_anchor[j], an);
-          an[0] += p[0]; an[1] += p[1]; an[2] += p[2];
-          S[0] = ax[0]; S[1] = ax[1]; S[2] = ax[2];
-          ch::cross(an, ax, S + 3);            // velocity at O of a unit rotation about the anchored axis
-          float sn, cs;
-          ch::sincos_(qj, &sn, &cs);
-          const float C = 1.f - cs;
-          const float Rj[9] = {cs + ax[0] * ax[0] * C, ax[0] * ax[1] * C - ax[2] * sn, ax[0] * ax[2] * C + ax[1] * sn,
-                               ax[1] * ax[0] * C + ax[2] * sn, cs + ax[1] * ax[1] * C, ax[1] * ax[2] * C - ax[0] * sn,
-                               ax[2] * ax[0] * C - ax[1] * sn, ax[2] * ax[1] * C + ax[0] * sn, cs + ax[2] * ax[2] * C};
-          float Rn[9];
-          ch::matmul(Rj, R, Rn);
-#pragma unroll
-          for (int k = 0; k < 9; ++k) R[k] = Rn[k];
-          const float dp[3] = {p[0] - an[0], p[1] - an[1], p[2] - an[2]};
-          float rp[3];
-          ch::matvec(Rj, dp, rp);
-          p[0] = an[0] + rp[0]; p[1] = an[1] + rp[1]; p[2] = an[2] + rp[2];
-        }
-        ch::cross_motion(v, S, c);             // the axis is fixed in the frame moving with v (before this joint)
-        // joint-space force and the implicit spring / damper diagonal (oracle/articulated_np.py:195-229)
-        float tau = 0.f;
-        const int act = m.d_act[j];
-        if (act >= 0) tau = m.d_gear[j] * fminf(fmaxf(ctrl[act], -m.ctrl_limit), m.ctrl_limit);
-        float keff = m.d_stiff[j], beff = m.d_damp[j];
-        tau -= keff * qj;
-        if (m.d_limited[j]) {
-          const bool below = qj < m.d_lo[j], above = qj > m.d_hi[j];
-          if (below) tau += m.d_klim[j] * (m.d_lo[j] - qj);
-          if (above) tau += m.d_klim[j] * (m.d_hi[j] - qj);
-          if (below || above) { keff += m.d_klim[j]; beff += m.d_blim[j]; }
-        }
-        const ChRef r = dof_rec(trunk, j);
-#pragma unroll
-        for (int e = 0; e < 6; ++e) {
-          r[e] = S[e];
-          r[6 + e] = c[e] * qdj;
-          v[e] += S[e] * qdj;
-        }
-        r[trunk ? 19 : 17] = tau - (beff + dt * keff) * qdj;
-        r[trunk ? 20 : 18] = m.d_arm[j] + dt * beff + dt * dt * keff;
-      }
-      if (trunk && m.trunk_junction[i] >= 0) {
-        const ChRef f = shared_rec(m.s_frame + kChFrame * m.trunk_junction[i]);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) f[k] = R[k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) f[9 + k] = p[k];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) f[12 + k] = v[k];
-      }
-      // ---- rigid inertia about O, bias force, floor contacts ------------------------------------------------------
-      const float mass = m.n_mass[node];
-      float c[3];
-      ch::matvec(R, m.n_com[node], c);
-      c[0] += p[0]; c[1] += p[1]; c[2] += p[2];
-      const float* I6 = m.n_inertia[node];
-      const float Im[9] = {I6[0], I6[3], I6[4], I6[3], I6[1], I6[5], I6[4], I6[5], I6[2]};
-      float T[9];
-      ch::matmul(R, Im, T);
-      float Io[6];
-      const float c2 = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
-      Io[0] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2] + mass * (c2 - c[0] * c[0]);
-      Io[1] = T[3] * R[3] + T[4] * R[4] + T[5] * R[5] + mass * (c2 - c[1] * c[1]);
-      Io[2] = T[6] * R[6] + T[7] * R[7] + T[8] * R[8] + mass * (c2 - c[2] * c[2]);
-      Io[3] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5] - mass * c[0] * c[1];
-      Io[4] = T[0] * R[6] + T[1] * R[7] + T[2] * R[8] - mass * c[0] * c[2];
-      Io[5] = T[3] * R[6] + T[4] * R[7] + T[5] * R[8] - mass * c[1] * c[2];
-      const float h[3] = {mass * c[0], mass * c[1], mass * c[2]};
-      // I v = [Io w + h x vl ; m vl - h x w],  bias = v x* (I v) = [w x n + vl x f ; w x f]
-      float hv[3], hw[3], Iv[6], t1[3], t2[3], t3[3], f[6];
-      ch::cross(h, v + 3, hv);
-      ch::cross(h, v, hw);
-      Iv[0] = Io[0] * v[0] + Io[3] * v[1] + Io[4] * v[2] + hv[0];
-      Iv[1] = Io[3] * v[0] + Io[1] * v[1] + Io[5] * v[2] + hv[1];
-      Iv[2] = Io[4] * v[0] + Io[5] * v[1] + Io[2] * v[2] + hv[2];
-      Iv[3] = mass * v[3] - hw[0];
-      Iv[4] = mass * v[4] - hw[1];
-      Iv[5] = mass * v[5] - hw[2];
-      ch::cross(v, Iv, t1);
-      ch::cross(v + 3, Iv + 3, t2);
-      ch::cross(v, Iv + 3, t3);
-      f[0] = t1[0] + t2[0]; f[1] = t1[1] + t2[1]; f[2] = t1[2] + t2[2];
-      f[3] = t3[0]; f[4] = t3[1]; f[5] = t3[2];
-      const int k0 = m.n_con_start[node], k1 = k0 + m.n_con_count[node];
-      for (int k = k0; k < k1; ++k) {
-        float x[3];
-        ch::matvec(R, m.c_pos[k], x);
-        x[0] += p[0]; x[1] += p[1]; x[2] += p[2];
-        const float pen = m.c_radius[k] - (O[2] + x[2]);
-        if (pen > 0.f) {
-          float u[3];
-          ch::cross(v, x, u);
-          u[0] += v[3]; u[1] += v[4]; u[2] += v[5];
-          const float spring = m.kc * pen;
-          const float damp = fminf(spring * m.cc, m.cdmax);
-          const float fn = fminf(fmaxf(spring - damp * u[2], 0.f), 3.f * spring);
-          const float speed = sqrtf(u[0] * u[0] + u[1] * u[1]);
-          const float coef = fminf(m.kv, m.mu * fn * ch_rcp(fmaxf(speed, 1e-6f)));
-          const float fc[3] = {-coef * u[0], -coef * u[1], fn};
-          float mo[3];
-          ch::cross(x, fc, mo);
-          f[0] -= mo[0]; f[1] -= mo[1]; f[2] -= mo[2];
-          f[3] -= fc[0]; f[4] -= fc[1]; f[5] -= fc[2];
-        }
-      }
-      rec[0] = mass; rec[1] = h[0]; rec[2] = h[1]; rec[3] = h[2];
-#pragma unroll
-      for (int e = 0; e < 6; ++e) { rec[4 + e] = Io[e]; rec[10 + e] = f[e]; }
-      if (i != last) {
-        const ChRef nr = node_rec(trunk, pos);
-#pragma unroll
-        for (int e = 0; e < kChNodeRec; ++e) nr[e] = rec[e];
       }
     }
   }
@@ -488,6 +519,7 @@ struct ChainLane {
 #pragma unroll
         for (int e = 0; e < 6; ++e) P[e] = 0.f;
       }
+      if (i == m.n_trunk - 1) ctx->group_sync();      // the trunk's node records were written by different lanes
       int node, pos;
       bool trunk;
       if (!node_at(i, node, trunk, pos)) continue;
@@ -841,13 +873,14 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
     t = next;
   }
   m.lanes = m.n_limbs <= 1 ? 1 : (m.n_limbs <= 2 ? 2 : 4);
+  for (int g = 0; g < kChMaxLimbs; ++g) m.seq_last[g] = -1;
   for (int g = 0; g < kChMaxLimbs; ++g)
     for (int i = 0; i < kChMaxTrunk + kChMaxLimbNodes; ++i) {
       int node = -1;
       if (i < m.n_trunk) node = m.trunk_node[i];
       else if (g < m.n_limbs && i - m.n_trunk < m.limb_nnodes[g]) node = m.limb_node[g][i - m.n_trunk];
       m.seq_node[g][i] = node;
-      if (node >= 0) m.seq_last[g] = i;
+      if (node >= 0 && i >= m.n_trunk) m.seq_last[g] = i;      // a trunk node never is "last": its record is shared
     }
   // ---- dofs -----------------------------------------------------------------------------------------------------
   for (int j = 0; j < a.nv; ++j) {
@@ -919,7 +952,7 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
   // one region, three tenants in turn: junction frames (pass 1) -> junction sums (pass 2) -> junction accelerations
   // (pass 3); the lanes are synchronised between the tenants (group sum / group_sync)
   m.s_frame = s; m.s_jun = s; m.s_acc = s;
-  s += kChJun * m.n_junctions;
+  s += kChJun * m.n_junctions > kChFrame * m.n_trunk ? kChJun * m.n_junctions : kChFrame * m.n_trunk;
   m.s_rk = s; s += m.integrator == kChRK4 ? m.nq + 3 * m.nv : 0;
   m.s_end = s;
   int p = 0;
