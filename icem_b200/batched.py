@@ -99,7 +99,7 @@ class FusedEpisodeBatch(EpisodeBatch):
     def plan(self, mode="train"):
         fm = self.controller.forward_model
         states = np.stack([fm.start_state(ob, env.get_GT_state()) for env, ob in zip(self.envs, self.obs)])
-        return self.controller._planner.plan_batch(states)
+        return self.controller.plan_batch(states, obs_dim=int(np.asarray(self.obs[0]).shape[-1]))
 
     def step(self, mode="train"):
         """Plan all episodes (one graph launch) and step all envs (one launch of B transitions, icem_sim_step_batch)

@@ -38,6 +38,7 @@ class MpcICemB200(*_Bases):
         if num_simulated_trajectories < 2:
             raise ValueError("At least two trajectories needed!")
         self.verbose = verbose
+        self.model_dir = None                 # controllers/mpc.py:34
         self.forward_model_state = None
         self._parse_action_sampler_params(**action_sampler_params)
         self._check_validity_parameters()
@@ -64,6 +65,10 @@ class MpcICemB200(*_Bases):
             rank = rk_ if rank is None else rank
         if seed is None:
             seed = int(np.random.randint(0, 2 ** 31 - 1))   # follows np.random.seed(Seeding.SEED), misc/seeding.py:18
+        if world_size > 1:
+            from .distributed import agree_on_seed
+            seed = agree_on_seed(seed)                       # one Philox stream for all shards: rank 0's
+        self._world_size = world_size
         self._planner = Planner(PlannerSettings(
             horizon=horizon, num_simulated_trajectories=num_simulated_trajectories,
             action_low=self.env.action_space.low, action_high=self.env.action_space.high,
@@ -169,12 +174,33 @@ class MpcICemB200(*_Bases):
         self._last_start = np.array(start, dtype=np.float64)
         self._obs_dim = int(np.asarray(obs).shape[-1])
         self._pending = (obs, state, self._steps_since_reset == 0)
+        if self._world_size > 1 and self._steps_since_reset == 0:
+            from .distributed import assert_same_on_all_ranks
+            assert_same_on_all_ranks(self._last_start)       # every shard must roll out from the same state
         try:
             self._planner.plan_async(start)
         except IcemError as e:
             if "beginning_of_rollout" in str(e):
                 raise AttributeError(str(e))
             raise
+
+    def plan_batch(self, start_states, obs_dim=None):
+        """One plan step of EVERY problem of a controller built with num_problems = B (icem_plan_batch): the same
+        bookkeeping as get_action -- step counter, elite cache, expected cost of the active problem."""
+        if not self.was_reset:
+            raise AttributeError("beginning_of_rollout() needs to be called before")
+        start_states = np.asarray(start_states, np.float64)
+        actions = self._planner.plan_batch(start_states)
+        self._last_start = np.array(start_states[self._planner.active_problem], dtype=np.float64)
+        if obs_dim is not None:
+            self._obs_dim = int(obs_dim)
+        self._steps_since_reset += 1
+        self._elite_cache = None
+        if self.logger is not None:
+            rec = self._planner.iteration_record(self.opt_iter - 1)
+            self.expected_cost = float(rec["elite_costs"][0])
+            self.logger.log(self._logged_cost(self.expected_cost), key="Expected_trajectory_cost")
+        return actions
 
     def finish_get_action(self):
         obs, state, first = self._pending
@@ -187,7 +213,7 @@ class MpcICemB200(*_Bases):
         if rec is not None:
             self.expected_cost = float(rec["elite_costs"][0])
             if self.logger is not None:
-                self.logger.log(self.expected_cost, key="Expected_trajectory_cost")   # icem.py:177
+                self.logger.log(self._logged_cost(self.expected_cost), key="Expected_trajectory_cost")   # icem.py:177
         if self.do_visualize_plan:      # icem.py:179-183: the best trajectory of the last iteration = elite 0
             best = self.elite_samples[0]
             self.visualize_plan(obs=best["observations"], state=self.forward_model_state, acts=best["actions"])
@@ -197,6 +223,9 @@ class MpcICemB200(*_Bases):
             _, self.forward_model_state, _ = self.forward_model.predict(
                 observations=obs, states=self.forward_model_state, actions=executed_action)
         return executed_action
+
+    def _logged_cost(self, cost):
+        return cost          # MpcICem logs min(costs) as it is (icem.py:177)
 
     def _print_iterations(self, first):
         p = self._planner
@@ -288,6 +317,9 @@ class MpcCemStdB200(MpcICemB200):
 
     def _evals_per_timestep(self):      # controllers/mpc.py:172
         return self.num_sim_traj * self.opt_iter * self.horizon
+
+    def _logged_cost(self, cost):       # MpcCemStd logs display_cost(min(costs)): per step for "sum" (mpc.py:217-218,251)
+        return cost / self.horizon if self.cost_along_trajectory == "sum" else cost
 
 
 class MpcRandomB200(MpcICemB200):

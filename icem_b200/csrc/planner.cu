@@ -44,8 +44,16 @@ struct DevBuf {
     n = count;
     if (count) {
       ICEM_CUDA(cudaMalloc(&p, count * sizeof(T)));
+      // A device memset is asynchronous to the host and runs on the legacy default stream, which does NOT order
+      // against the planner's non-blocking stream: wait for it, so that work enqueued on any stream afterwards
+      // sees the zeros and never races them.
       ICEM_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+      ICEM_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
     }
+  }
+  // grow-only scratch: reuse across calls (no cudaMalloc / cudaFree, hence no device synchronisation, per call)
+  void reserve(size_t count) {
+    if (count > n) alloc(count);
   }
   void release() {
     if (p) cudaFree(p);
@@ -119,6 +127,7 @@ struct icem_planner {
   DevBuf<unsigned int> ticket;
   DevBuf<float> w_obs, w_act, bias;      // dense model
   DevBuf<unsigned char> flush;           // L2 flush buffer (bench)
+  DevBuf<float> step_scratch;            // icem_sim_step / _batch / icem_op_rollout_observations staging (grow-only)
   std::vector<DevBuf<float>> inj_zr, inj_zi;
   std::vector<int> inj_rows;
   // multi-rank
@@ -1426,9 +1435,9 @@ int icem_sim_step(icem_planner_t* p, const double* state, int32_t state_dim, con
   if (state_dim != p->state_dim) throw InvalidArg("state_dim does not match the forward model");
   if (obs_dim < 0 || obs_dim > 512) throw InvalidArg("obs_dim out of range");
   ICEM_CUDA(cudaSetDevice(p->cfg.device));
-  DevBuf<float> buf;
+  DevBuf<float>& buf = p->step_scratch;
   const int sd = p->state_dim;
-  buf.alloc((size_t)2 * sd + p->d + std::max(obs_dim, 1));
+  buf.reserve((size_t)2 * sd + p->d + std::max(obs_dim, 1));
   std::vector<float> h((size_t)sd + p->d);
   for (int i = 0; i < sd; ++i) h[i] = (float)state[i];
   if (action)
@@ -1459,8 +1468,8 @@ int icem_sim_step_batch(icem_planner_t* p, int32_t n, const double* states, int3
   if (state_dim != p->state_dim) throw InvalidArg("state_dim does not match the forward model");
   ICEM_CUDA(cudaSetDevice(p->cfg.device));
   const int sd = p->state_dim, d = p->d;
-  DevBuf<float> buf;
-  buf.alloc((size_t)n * (2 * sd + d));
+  DevBuf<float>& buf = p->step_scratch;
+  buf.reserve((size_t)n * (2 * sd + d));
   std::vector<float> h((size_t)n * (sd + d));
   for (size_t i = 0; i < (size_t)n * sd; ++i) h[i] = (float)states[i];
   for (size_t i = 0; i < (size_t)n * d; ++i) h[(size_t)n * sd + i] = (float)actions[i];
@@ -1562,23 +1571,24 @@ int icem_op_rollout_observations(icem_planner_t* p, int32_t n, const double* sta
   if (obs_dim < 1 || obs_dim > 512) throw InvalidArg("obs_dim out of range");
   ICEM_CUDA(cudaSetDevice(p->cfg.device));
   const int sd = p->state_dim, h = p->h, d = p->d;
-  DevBuf<float> d_state, d_act, d_obs;
-  d_state.alloc((size_t)2 * sd);                       // start state, running state
-  d_act.alloc((size_t)n * h * d);
-  d_obs.alloc((size_t)n * (h + 1) * obs_dim);
+  const size_t n_state = (size_t)2 * sd, n_act = (size_t)n * h * d, n_obs = (size_t)n * (h + 1) * obs_dim;
+  p->step_scratch.reserve(n_state + n_act + n_obs);
+  float* d_state = p->step_scratch.p;                  // start state, running state
+  float* d_act = d_state + n_state;
+  float* d_obs = d_act + n_act;
   std::vector<float> hs(sd);
   for (int i = 0; i < sd; ++i) hs[i] = (float)state[i];
-  ICEM_CUDA(cudaMemcpyAsync(d_state.p, hs.data(), sd * sizeof(float), cudaMemcpyHostToDevice, p->stream));
-  ICEM_CUDA(cudaMemcpyAsync(d_act.p, actions, (size_t)n * h * d * sizeof(float), cudaMemcpyHostToDevice, p->stream));
-  float* run = d_state.p + sd;
+  ICEM_CUDA(cudaMemcpyAsync(d_state, hs.data(), sd * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+  ICEM_CUDA(cudaMemcpyAsync(d_act, actions, n_act * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+  float* run = d_state + sd;
   for (int r = 0; r < n; ++r) {
-    float* obs_r = d_obs.p + (size_t)r * (h + 1) * obs_dim;
-    advance_dyn(p, d_state.p, nullptr, run, obs_r, obs_dim);                     // entry 0: the start observation
+    float* obs_r = d_obs + (size_t)r * (h + 1) * obs_dim;
+    advance_dyn(p, d_state, nullptr, run, obs_r, obs_dim);                       // entry 0: the start observation
     for (int t = 0; t < h; ++t)
-      advance_dyn(p, run, d_act.p + ((size_t)r * h + t) * d, run, obs_r + (size_t)(t + 1) * obs_dim, obs_dim);
+      advance_dyn(p, run, d_act + ((size_t)r * h + t) * d, run, obs_r + (size_t)(t + 1) * obs_dim, obs_dim);
   }
-  std::vector<float> ho((size_t)n * (h + 1) * obs_dim);
-  ICEM_CUDA(cudaMemcpyAsync(ho.data(), d_obs.p, ho.size() * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+  std::vector<float> ho(n_obs);
+  ICEM_CUDA(cudaMemcpyAsync(ho.data(), d_obs, ho.size() * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
   ICEM_CUDA(cudaStreamSynchronize(p->stream));
   for (size_t i = 0; i < ho.size(); ++i) obs_out[i] = ho[i];
   ICEM_API_END

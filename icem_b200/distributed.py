@@ -37,3 +37,26 @@ def shard_bounds(n_global: int, world_size: int, rank: int):
     lo = min(n_global, rank * chunk)
     hi = min(n_global, lo + chunk)
     return lo, hi
+
+
+def agree_on_seed(seed):
+    """All ranks of a sharded plan must draw the same Philox stream (the population is split by GLOBAL trajectory
+    index): rank 0's seed wins."""
+    import struct
+    payload = broadcast_bytes(struct.pack("<q", int(seed)), src=0)
+    return struct.unpack("<q", payload)[0]
+
+
+def assert_same_on_all_ranks(array, what="start state"):
+    """The ranks refit on elites gathered from all of them, which is only meaningful when every rank rolled out
+    from the same start state: compare a checksum across ranks (one tiny all-gather)."""
+    import hashlib
+
+    import torch.distributed as dist
+    import numpy as np
+    digest = hashlib.sha256(np.ascontiguousarray(array, dtype=np.float64).tobytes()).hexdigest()
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, digest)
+    if len(set(out)) != 1:
+        raise RuntimeError(f"sharded planner: the {what} differs between ranks (rank 0 {out[0][:12]}..., "
+                           f"rank {dist.get_rank()} {digest[:12]}...)")

@@ -253,6 +253,15 @@ class _DeviceSimEnv(_EnvBase):
         obs, r, _, _ = self.step(action)
         return obs, self.get_GT_state(), r
 
+    def simulate_state(self, state, action):
+        """(next_obs, next GT state, reward) of one transition from `state` = [time, qpos, qvel] on the device model;
+        the env itself (its own state, time, RNG) is left untouched."""
+        saved = (self._state.copy(), self._t)
+        try:
+            return self.simulate(state, action)
+        finally:
+            self._state, self._t = saved
+
     def close(self):
         if self._sim is not None:
             self._sim.close()

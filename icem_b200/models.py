@@ -121,7 +121,13 @@ class CudaGroundTruthModel(_GTBase):
         raise NotImplementedError
 
     def get_state(self, observation):
-        return self.env.state_from_observation(observation)
+        # The reference's GroundTruthModel (models/gt_model.py:45-55) rebuilds the simulator state from an observation
+        # through env.set_state_from_observation; the device-simulated stand-ins cannot (HalfCheetah's observation
+        # drops the x position, HumanoidStandup's is a function of the state, not the state).
+        if hasattr(self.env, "state_from_observation"):
+            return self.env.state_from_observation(observation)
+        raise ValueError("CudaGroundTruthModel needs the env state (rollout_params.use_env_states: true): this env "
+                         "cannot rebuild its state from an observation")
 
     def reset(self, observation):
         return self.get_state(observation)
@@ -131,6 +137,10 @@ class CudaGroundTruthModel(_GTBase):
         return self.reset(observation) if env_state is None else env_state
 
     def predict(self, *, observations, states, actions):
+        # one transition on the device model WITHOUT touching the live env (the reference keeps a separate
+        # simulated_env for this, models/gt_model.py:28-33): the stand-in's stateless `simulate_state`
+        if hasattr(self.env, "simulate_state"):
+            return self.env.simulate_state(states, actions)
         return self.env.simulate(states, actions)
 
     def predict_n_steps(self, *, start_observations, start_states, policy, horizon):

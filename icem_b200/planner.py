@@ -199,9 +199,12 @@ class Planner:
         check(self._lib.icem_plan_batch(self._h, dptr(st), st.shape[1], st.shape[0], dptr(out)))
         return out
 
+    active_problem = 0
+
     def set_active_problem(self, i):
         """Which problem mean() / std() / elites() / iteration_record() / costs() / actions() read."""
         check(self._lib.icem_set_active_problem(self._h, int(i)))
+        self.active_problem = int(i)
 
     def plan_async(self, state):
         """Launch a plan step without waiting for it (icem_plan_async); pair with plan_finish()."""
