@@ -85,3 +85,40 @@ class MlpModel:
                 obs = self.step(obs, np.asarray(actions[:, t], np.float32).astype(np.float64))
                 obs = obs.astype(np.float32).astype(np.float64)      # the device keeps the state in fp32
         return out
+
+
+class MlpModelF32:
+    """The same MLP WITHOUT any reduced-precision restatement: float32 weights, activations and accumulation, exact
+    tanh -- what a PyTorch fp32 `nn.Sequential(Linear, Tanh, Linear, Tanh, Linear)` computes (checked against torch
+    in tests/test_oracle_mlp.py) and what a learned model driven through the reference's
+    `ForwardModelWithDefaults.predict_n_steps` (models/abstract_models.py:31-53) would feed the controller.  This is
+    the precision reference for the tensor-core path: the device kernel rounds operands to bfloat16, this model does
+    not, and scripts/mlp_precision_report.py measures what that costs the planner (elite overlap, executed action)."""
+
+    def __init__(self, weights, biases):
+        self.w = [np.asarray(w, np.float32) for w in weights]
+        self.b = [np.asarray(b, np.float32) for b in biases]
+        self.obs_dim = self.w[2].shape[0]
+        self.act_dim = self.w[0].shape[1] - self.obs_dim
+        self.state_dim = self.obs_dim
+
+    def step(self, obs, act):
+        x = np.concatenate([np.asarray(obs, np.float32), np.asarray(act, np.float32)], axis=-1)
+        h1 = np.tanh(x @ self.w[0].T + self.b[0])
+        h2 = np.tanh(h1 @ self.w[1].T + self.b[1])
+        return (np.asarray(obs, np.float32) + h2 @ self.w[2].T + self.b[2]).astype(np.float64)
+
+    def observe(self, state):
+        return np.asarray(state, dtype=np.float64)
+
+    def rollout(self, start_state, actions, chunk=16384):
+        p, h, _ = actions.shape
+        out = np.empty((p, h, self.obs_dim))
+        for lo in range(0, p, chunk):
+            hi = min(p, lo + chunk)
+            obs = np.broadcast_to(np.asarray(start_state, np.float32), (hi - lo, self.obs_dim)).copy()
+            for t in range(h):
+                out[lo:hi, t] = obs
+                if t + 1 < h:
+                    obs = self.step(obs, actions[lo:hi, t]).astype(np.float32)
+        return out

@@ -147,3 +147,20 @@ def test_series_sampler_inside_the_plan_step():
     assert abs(np.mean(z[:, :, 0] * z[:, :, 1]) / np.mean(z * z)) < 0.05
     assert abs(np.mean(z[1:, :, 0] * z[:-1, :, 0]) / np.mean(z * z)) < 0.05
     p.close()
+
+
+def test_bf16_tensor_core_plan_against_the_fp32_plan():
+    """The precision reference of the tensor-core path is the fp32 model (oracle/dynamics_np.py::MlpModelF32 == a
+    torch fp32 nn.Sequential), NOT the oracle that restates the kernel's bf16 roundings: plan 6 closed-loop steps with
+    both on identical draws (scripts/mlp_precision_report.py) and require that the bf16 plan picks essentially the same
+    elites and executes essentially the same action.  Full-size numbers (N = 65536, 20 steps) are in
+    profiles/r2_mlp_bf16_vs_fp32.json."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from mlp_precision_report import run
+    rep = run(4096, 6, quiet=True)
+    # iteration 0 samples from the identical distribution in both planners: pure effect of the operand precision
+    assert rep["elite_overlap_first_iteration"]["mean"] >= 0.8, rep["elite_overlap_first_iteration"]
+    assert rep["elite_overlap_last_iteration"]["mean"] >= 0.6, rep["elite_overlap_last_iteration"]
+    assert rep["executed_action_abs_diff"]["median"] <= 0.1 * rep["executed_action_abs_diff"]["action_range"]
