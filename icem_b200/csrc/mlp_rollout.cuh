@@ -10,10 +10,10 @@
 // barrier inside the rollout): epilogue thread (q, lane, g), warp = 4 g + q, owns trajectory row r = 32 q + lane
 // (TMEM lane r; a warp may only touch the lane quarter warp % 4) and the 16 columns g*16.. of every 64-column
 // STAGE of a hidden layer; the fp32 observation is replicated in the 4 threads of a row.  The three weight matrices
-// stay RESIDENT in shared memory as bf16 in the tcgen05 K-major no-swizzle core-matrix layout
+// stay RESIDENT in shared memory as fp16 in the tcgen05 K-major no-swizzle core-matrix layout
 // ([n/8][k/8][n%8][k%8], 128-byte core matrices) for the whole kernel.  Per control step:
-//     X[128 x 32] (bf16, smem) --2 MMAs M128 N=H K=16--> D1[128 x H] fp32 in TMEM (columns 0..H)
-//     epilogue 1, stage by stage: tcgen05.ld 32x32b.x16 -> +bias, tanh.approx -> bf16 -> smem; as soon as a stage
+//     X[128 x 32] (fp16, smem) --2 MMAs M128 N=H K=16--> D1[128 x H] fp32 in TMEM (columns 0..H)
+//     epilogue 1, stage by stage: tcgen05.ld 32x32b.x16 -> +bias, tanh.approx -> fp16 -> smem; as soon as a stage
 //       (64 columns = 4 K-steps of the next layer's A operand) is in shared memory its warps arrive on that stage's
 //       mbarrier and the issuer accumulates those K-steps into D2 (TMEM columns 256..256+H): the layer-2 MMAs run
 //       UNDER the layer-1 epilogue instead of after it
@@ -22,12 +22,19 @@
 // MMAs are issued by ONE thread and tracked with tcgen05.commit on mbarriers; accumulators never leave TMEM except
 // through the epilogue loads.  Actions come from the sampler kernel's HBM/L2 tiles, prefetched one step ahead.
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "rollout.cuh"
 
 namespace icem {
+
+// Tensor-core operand type: IEEE half (11 significand bits), fp32 accumulation in TMEM.  tcgen05 `kind::f16` runs fp16
+// and bf16 operands at the same rate; against the fp32 model (oracle MlpModelF32 == torch fp32 nn.Sequential) bf16's 8
+// bits cost the planner half of its elite set at N = 65536 (profiles/r2_mlp_bf16_vs_fp32.json), fp16 keeps it.  The
+// observations / actions / activations of these models are O(1..100): far inside the fp16 range.
+typedef __half mlp_op_t;
+__host__ __device__ inline mlp_op_t mlp_op_from_float(float v) { return __float2half_rn(v); }
 
 constexpr int kMlpTile = 128;     // trajectories per CTA tile (UMMA M)
 constexpr int kMlpColGroups = 4;  // threads per trajectory row: each takes 16 columns of every 64-column stage
@@ -42,9 +49,9 @@ constexpr int kMlpOutPad = 32;    // padded output width (obs <= 32)
 struct MlpParams {
   int obs_dim, act_dim, hidden;               // hidden in {64, 128, 256}
   int act_off;                                // input column of action 0: obs_dim rounded up to 8 (act_off + act_dim <= 32)
-  const __nv_bfloat16* w1;                    // packed [hidden x kMlpInPad], columns [obs | 0 | act | 0]
-  const __nv_bfloat16* w2;                    // packed [hidden x hidden]
-  const __nv_bfloat16* w3;                    // packed [kMlpOutPad x hidden]
+  const mlp_op_t* w1;                    // packed [hidden x kMlpInPad], columns [obs | 0 | act | 0]
+  const mlp_op_t* w2;                    // packed [hidden x hidden]
+  const mlp_op_t* w3;                    // packed [kMlpOutPad x hidden]
   const float* bias;                          // [hidden + hidden + kMlpOutPad]
 };
 
@@ -63,8 +70,8 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                :: "r"(smem_addr(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, fp16 x fp16 -> fp32
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -141,12 +148,13 @@ __device__ __forceinline__ uint64_t umma_desc(const void* smem, uint32_t lbo_byt
   d |= (uint64_t)1 << 46;                  // version = 1
   return d;                                // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
 }
-// instruction descriptor: D fp32, A/B bf16, both K-major, dense
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// instruction descriptor: D fp32 (bits 4-5 = 1), A / B format fp16 (bits 7-9 / 10-12 = 0; 1 would be bf16), both
+// K-major, dense
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// packed core-matrix index of element (row, k) of a [rows x K] K-major operand (bf16 elements)
+// packed core-matrix index of element (row, k) of a [rows x K] K-major operand (2-byte elements)
 __host__ __device__ inline size_t umma_pack_index(int row, int k, int K) {
   return (size_t)(row >> 3) * (size_t)(K >> 3) * 64 + (size_t)(k >> 3) * 64 + (size_t)(row & 7) * 8 + (size_t)(k & 7);
 }
@@ -172,10 +180,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1)
 mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int H = mp.hidden;
-  __nv_bfloat16* sW1 = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  __nv_bfloat16* sW2 = sW1 + (size_t)H * kMlpInPad;
-  __nv_bfloat16* sW3 = sW2 + (size_t)H * H;
-  __nv_bfloat16* sA = sW3 + (size_t)kMlpOutPad * H;                   // [128 x max(H, 32)] activations
+  mlp_op_t* sW1 = reinterpret_cast<mlp_op_t*>(smem_raw);
+  mlp_op_t* sW2 = sW1 + (size_t)H * kMlpInPad;
+  mlp_op_t* sW3 = sW2 + (size_t)H * H;
+  mlp_op_t* sA = sW3 + (size_t)kMlpOutPad * H;                   // [128 x max(H, 32)] activations
   float* sBias = reinterpret_cast<float*>(sA + (size_t)kMlpTile * H);
   uint64_t* bar_x = reinterpret_cast<uint64_t*>(sBias + 2 * H + kMlpOutPad);   // X operand in smem      (16 arrivals)
   uint64_t* bar_a = bar_x + 1;                // [4] activation stage s in smem: layer 1 / layer 2 alternate (16 arrivals)
@@ -215,8 +223,8 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_d2 = tmem_base + 256u;
 
-  const uint32_t idesc_h = umma_idesc_bf16(kMlpTile, H);
-  const uint32_t idesc_o = umma_idesc_bf16(kMlpTile, kMlpOutPad);
+  const uint32_t idesc_h = umma_idesc_f16(kMlpTile, H);
+  const uint32_t idesc_o = umma_idesc_f16(kMlpTile, kMlpOutPad);
   const uint32_t sbo_in = (kMlpInPad / 8) * 128, sbo_h = (uint32_t)(H / 8) * 128;
 
   const StepState ss = *a.ss;
@@ -238,7 +246,7 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
           tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < kMlpInPad / 16; ++ks)
-            tc_mma_bf16(tmem_base, umma_desc(pA + ks * 256, 128, sbo_in), umma_desc(pW1 + ks * 256, 128, sbo_in),
+            tc_mma_f16(tmem_base, umma_desc(pA + ks * 256, 128, sbo_in), umma_desc(pW1 + ks * 256, 128, sbo_in),
                         idesc_h, ks > 0);
           tc_commit(&bar_d[0]);
           // layer 2: H1 stages -> D2, accumulated as the stages land in shared memory
@@ -249,7 +257,7 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
 #pragma unroll
             for (int k4 = 0; k4 < kMlpStageCols / 16; ++k4) {
               const int ks = s * (kMlpStageCols / 16) + k4;
-              tc_mma_bf16(tmem_d2, umma_desc(pA + ks * 256, 128, sbo_h), umma_desc(pW2 + ks * 256, 128, sbo_h),
+              tc_mma_f16(tmem_d2, umma_desc(pA + ks * 256, 128, sbo_h), umma_desc(pW2 + ks * 256, 128, sbo_h),
                           idesc_h, ks > 0);
             }
           }
@@ -262,7 +270,7 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
 #pragma unroll
             for (int k4 = 0; k4 < kMlpStageCols / 16; ++k4) {
               const int ks = s * (kMlpStageCols / 16) + k4;
-              tc_mma_bf16(tmem_base, umma_desc(pA + ks * 256, 128, sbo_h), umma_desc(pW3 + ks * 256, 128, sbo_h),
+              tc_mma_f16(tmem_base, umma_desc(pA + ks * 256, 128, sbo_h), umma_desc(pW3 + ks * 256, 128, sbo_h),
                           idesc_o, ks > 0);
             }
           }
@@ -308,15 +316,15 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
 
       for (int t = 0; t < h; ++t) {
 
-        // ---- X row -> smem (bf16, K-major core matrices), layer 1: thread g writes 16-byte chunk g ----
+        // ---- X row -> smem (fp16, K-major core matrices), layer 1: thread g writes 16-byte chunk g ----
         const bool last = t + 1 == h;          // the final predicted state is never scored: no transition after it
 #pragma unroll
         for (int ch = 0; ch < kMlpInPad / 8; ++ch) {
           if (ch == g && !last) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(x[8 * ch], x[8 * ch + 1]);
-            __nv_bfloat162 p1 = __floats2bfloat162_rn(x[8 * ch + 2], x[8 * ch + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(x[8 * ch + 4], x[8 * ch + 5]);
-            __nv_bfloat162 p3 = __floats2bfloat162_rn(x[8 * ch + 6], x[8 * ch + 7]);
+            __half2 p0 = __floats2half2_rn(x[8 * ch], x[8 * ch + 1]);
+            __half2 p1 = __floats2half2_rn(x[8 * ch + 2], x[8 * ch + 3]);
+            __half2 p2 = __floats2half2_rn(x[8 * ch + 4], x[8 * ch + 5]);
+            __half2 p3 = __floats2half2_rn(x[8 * ch + 6], x[8 * ch + 7]);
             uint4 v;
             v.x = *reinterpret_cast<uint32_t*>(&p0); v.y = *reinterpret_cast<uint32_t*>(&p1);
             v.z = *reinterpret_cast<uint32_t*>(&p2); v.w = *reinterpret_cast<uint32_t*>(&p3);
@@ -354,7 +362,7 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
         }
         if (last) break;
 
-        // ---- hidden layers: epilogue stage by stage (bias + tanh -> bf16 A operand of the next MMA) ----
+        // ---- hidden layers: epilogue stage by stage (bias + tanh -> fp16 A operand of the next MMA) ----
 #pragma unroll 1
         for (int layer = 0; layer < 2; ++layer) {
           mbar_wait(&bar_d[layer], n & 1);
@@ -378,9 +386,9 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float4 b = b4[j];
-                __nv_bfloat162 lo2 = __floats2bfloat162_rn(tanh_approx(__uint_as_float(rv[4 * j]) + b.x),
+                __half2 lo2 = __floats2half2_rn(tanh_approx(__uint_as_float(rv[4 * j]) + b.x),
                                                            tanh_approx(__uint_as_float(rv[4 * j + 1]) + b.y));
-                __nv_bfloat162 hi2 = __floats2bfloat162_rn(tanh_approx(__uint_as_float(rv[4 * j + 2]) + b.z),
+                __half2 hi2 = __floats2half2_rn(tanh_approx(__uint_as_float(rv[4 * j + 2]) + b.z),
                                                            tanh_approx(__uint_as_float(rv[4 * j + 3]) + b.w));
                 pk[2 * j] = *reinterpret_cast<uint32_t*>(&lo2);
                 pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi2);
@@ -445,13 +453,13 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
 }
 
 // one transition of the same model for a single state (env.step on the device model / closed-loop bench):
-// same bf16 roundings as the tensor-core path, CUDA-core arithmetic
+// same fp16 operand roundings as the tensor-core path, CUDA-core arithmetic
 __global__ void mlp_advance_kernel(MlpParams mp, const float* state, const float* action, float* next_state,
                                    float* obs_out, int obs_dim_out) {
   __shared__ float xin[kMlpInPad];
   __shared__ float h1[256], h2[256];
   const int H = mp.hidden, od = mp.obs_dim, d = mp.act_dim, tid = threadIdx.x;
-  auto bf = [](float v) { return __bfloat162float(__float2bfloat16_rn(v)); };
+  auto bf = [](float v) { return __half2float(__float2half_rn(v)); };
   const int ao = mp.act_off;
   if (tid < kMlpInPad)
     xin[tid] = tid < od ? state[tid] : (action && tid >= ao && tid < ao + d ? action[tid - ao] : 0.f);
@@ -459,19 +467,19 @@ __global__ void mlp_advance_kernel(MlpParams mp, const float* state, const float
   if (action) {
     for (int n = tid; n < H; n += blockDim.x) {
       float acc = 0.f;
-      for (int k = 0; k < kMlpInPad; ++k) acc = fmaf(bf(xin[k]), __bfloat162float(mp.w1[umma_pack_index(n, k, kMlpInPad)]), acc);
+      for (int k = 0; k < kMlpInPad; ++k) acc = fmaf(bf(xin[k]), __half2float(mp.w1[umma_pack_index(n, k, kMlpInPad)]), acc);
       h1[n] = bf(tanh_approx(acc + mp.bias[n]));
     }
     __syncthreads();
     for (int n = tid; n < H; n += blockDim.x) {
       float acc = 0.f;
-      for (int k = 0; k < H; ++k) acc = fmaf(h1[k], __bfloat162float(mp.w2[umma_pack_index(n, k, H)]), acc);
+      for (int k = 0; k < H; ++k) acc = fmaf(h1[k], __half2float(mp.w2[umma_pack_index(n, k, H)]), acc);
       h2[n] = bf(tanh_approx(acc + mp.bias[H + n]));
     }
     __syncthreads();
     if (tid < od) {
       float acc = 0.f;
-      for (int k = 0; k < H; ++k) acc = fmaf(h2[k], __bfloat162float(mp.w3[umma_pack_index(tid, k, H)]), acc);
+      for (int k = 0; k < H; ++k) acc = fmaf(h2[k], __half2float(mp.w3[umma_pack_index(tid, k, H)]), acc);
       xin[tid] = xin[tid] + acc + mp.bias[2 * H + tid];
     }
     __syncthreads();

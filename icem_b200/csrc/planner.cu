@@ -20,7 +20,6 @@
 #include "dyn_articulated.cuh"
 #include "dyn_dense.cuh"
 #include "mlp_rollout.cuh"
-#include "mlp_rollout_2cta.cuh"
 #include "sampler.cuh"
 #include "rollout.cuh"
 #include "rollout_chain.cuh"
@@ -152,10 +151,7 @@ struct icem_planner {
   DevBuf<ChainModel> chain_model;
   ChainParams chain{};
   MlpParams mlp{};
-  DevBuf<__nv_bfloat16> mlp_w1, mlp_w2, mlp_w3;
-  DevBuf<__nv_bfloat16> mlp_half[2][3];  // per-CTA halves of the packed weights for the cta_group::2 kernel
-  MlpHalfParams mlp_halves{};
-  bool mlp_use_2cta = false;             // ICEM_B200_MLP_2CTA=1 at icem_create: the CTA-pair schedule (see launch_mlp)
+  DevBuf<mlp_op_t> mlp_w1, mlp_w2, mlp_w3;
   DevBuf<float> mlp_bias;
 
   // run state
@@ -339,21 +335,6 @@ static void launch_rollout(icem_planner* p, const RolloutArgs& a, const typename
 static void launch_mlp(icem_planner* p, const RolloutArgs& a, int rows_max) {
   const SamplerConst sc = sampler_const(p);
   const CostConst cc = cost_const(p);
-  // CTA-pair schedule (cta_group::2, two tiles per SM in flight; mlp_rollout_2cta.cuh): opt-in.  Measured on B200 it
-  // ties the single-CTA kernel (0.228 vs 0.223 ms per 65k trajectories): with half the weights per CTA both tiles
-  // fit, but the M=256 layer-2 MMAs run at ~190 cycles each next to the epilogue's shared-memory traffic and the 16
-  // N=32 output MMAs cost ~84 cycles each, so the tensor pipe (9.2 k cycles per step for two tiles) is as long as the
-  // MUFU work (8.8 k) and the remaining gaps (3-4 k) do not close without a deeper software pipeline.
-  if (p->mlp_use_2cta && p->cfg.cost_along_trajectory == ICEM_REDUCE_SUM) {
-    const size_t smem = mlp2_smem_bytes(p->mlp.hidden);
-    ensure_dynamic_smem(mlp_rollout_2cta_kernel, smem, p->cfg.device);
-    const int super_tiles = (rows_max + kMlp2SuperTile - 1) / kMlp2SuperTile;
-    const int clusters = std::max(1, std::min(super_tiles, p->sm_count / 2));
-    mlp_rollout_2cta_kernel<<<2 * clusters, kMlpThreads, smem, p->stream>>>(a, sc, cc, p->mlp, p->mlp_halves);
-    ICEM_CUDA(cudaGetLastError());
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return;
-  }
   const size_t smem = mlp_smem_bytes(p->mlp.hidden);
   ensure_dynamic_smem(mlp_rollout_kernel, smem, p->cfg.device);
   const int tiles = (rows_max + kMlpTile - 1) / kMlpTile;
@@ -845,7 +826,6 @@ int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
   }
   p->white = cem_std || rnd || !(cfg->noise_beta > 0);
   { const char* e = getenv("ICEM_B200_WARP_SAMPLER"); p->force_warp_sampler = e && e[0] == '1'; }
-  { const char* e = getenv("ICEM_B200_MLP_2CTA"); p->mlp_use_2cta = e && e[0] == '1'; }
   { const char* e = getenv("ICEM_B200_ENGINE"); p->force_warp_engine = e && strcmp(e, "warp") == 0; }
   p->low.assign(cfg->action_low, cfg->action_low + p->d);
   p->high.assign(cfg->action_high, cfg->action_high + p->d);
@@ -1118,12 +1098,12 @@ int icem_set_mlp_model(icem_planner_t* p, int32_t n_layers, const int32_t* dims,
   for (int l = 0; l < 3; ++l)
     if (!weights[l] || !biases[l]) throw InvalidArg("null layer parameters");
   ICEM_CUDA(cudaSetDevice(p->cfg.device));
-  auto pack = [](const float* w, int rows, int cols, int rows_pad, int K, DevBuf<__nv_bfloat16>& dst) {
-    std::vector<__nv_bfloat16> h((size_t)rows_pad * K, __float2bfloat16_rn(0.f));
+  auto pack = [](const float* w, int rows, int cols, int rows_pad, int K, DevBuf<mlp_op_t>& dst) {
+    std::vector<mlp_op_t> h((size_t)rows_pad * K, mlp_op_from_float(0.f));
     for (int n = 0; n < rows; ++n)
-      for (int k = 0; k < cols; ++k) h[umma_pack_index(n, k, K)] = __float2bfloat16_rn(w[(size_t)n * cols + k]);
+      for (int k = 0; k < cols; ++k) h[umma_pack_index(n, k, K)] = mlp_op_from_float(w[(size_t)n * cols + k]);
     dst.alloc(h.size());
-    ICEM_CUDA(cudaMemcpy(dst.p, h.data(), h.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    ICEM_CUDA(cudaMemcpy(dst.p, h.data(), h.size() * sizeof(mlp_op_t), cudaMemcpyHostToDevice));
   };
   // layer-1 input columns: [obs | 0 | act at act_off | 0], act_off = obs width rounded up to 8 (the kernel
   // indexes its register state statically per 8-column chunk)
@@ -1141,24 +1121,6 @@ int icem_set_mlp_model(icem_planner_t* p, int32_t n_layers, const int32_t* dims,
   p->mlp.act_off = act_off;
   pack(weights[1], H, H, H, H, p->mlp_w2);
   pack(weights[2], out, H, kMlpOutPad, H, p->mlp_w3);
-  // cta_group::2 kernel: CTA v of a pair holds output rows [v * N/2, (v + 1) * N/2) of every layer (B operand split in N)
-  {
-    std::vector<float> w1p((size_t)H * kMlpInPad, 0.f), w3p((size_t)kMlpOutPad * H, 0.f);
-    for (int n = 0; n < H; ++n) {
-      for (int k = 0; k < out; ++k) w1p[(size_t)n * kMlpInPad + k] = weights[0][(size_t)n * in + k];
-      for (int m = 0; m < p->d; ++m) w1p[(size_t)n * kMlpInPad + act_off + m] = weights[0][(size_t)n * in + out + m];
-    }
-    for (int n = 0; n < out; ++n)
-      for (int k = 0; k < H; ++k) w3p[(size_t)n * H + k] = weights[2][(size_t)n * H + k];
-    for (int v = 0; v < 2; ++v) {
-      pack(w1p.data() + (size_t)v * (H / 2) * kMlpInPad, H / 2, kMlpInPad, H / 2, kMlpInPad, p->mlp_half[v][0]);
-      pack(weights[1] + (size_t)v * (H / 2) * H, H / 2, H, H / 2, H, p->mlp_half[v][1]);
-      pack(w3p.data() + (size_t)v * (kMlpOutPad / 2) * H, kMlpOutPad / 2, H, kMlpOutPad / 2, H, p->mlp_half[v][2]);
-      p->mlp_halves.w1[v] = p->mlp_half[v][0].p;
-      p->mlp_halves.w2[v] = p->mlp_half[v][1].p;
-      p->mlp_halves.w3[v] = p->mlp_half[v][2].p;
-    }
-  }
   std::vector<float> b((size_t)2 * H + kMlpOutPad, 0.f);
   for (int i = 0; i < H; ++i) { b[i] = biases[0][i]; b[H + i] = biases[1][i]; }
   for (int i = 0; i < out; ++i) b[2 * H + i] = biases[2][i];

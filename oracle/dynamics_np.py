@@ -52,24 +52,33 @@ def bf16_round(x):
     return r.astype(np.uint32).view(np.float32).astype(np.float64).reshape(a.shape)
 
 
+def f16_round(x):
+    """Round to the nearest IEEE half (ties to even), returned as float64."""
+    return np.asarray(x, dtype=np.float32).astype(np.float16).astype(np.float64)
+
+
 class MlpModel:
     """obs' = obs + W3 tanh(W2 tanh(W1 [obs, act] + b1) + b2) + b3 with the tensor-core path's operand roundings
-    restated: weights, the layer-1 input and both hidden activations are rounded to bfloat16 (what csrc/
-    mlp_rollout.cuh feeds tcgen05.mma), products accumulate in >= fp32, biases and the state stay fp32/f64.
-    Not restated: the accumulation order inside the tensor core and tanh.approx (rel. error ~5e-4), so agreement
-    is at bf16 resolution, not bit level (tests/test_gpu_mlp.py states the tolerance)."""
+    restated: weights, the layer-1 input and both hidden activations are rounded to the operand type of csrc/
+    mlp_rollout.cuh (`operand="f16"`, IEEE half, the shipped kernel; "bf16" = the round-1 kernel), products accumulate
+    in >= fp32, biases and the state stay fp32/f64.  Not restated: the accumulation order inside the tensor core and
+    tanh.approx (rel. error ~5e-4), so agreement is at operand resolution, not bit level (tests/test_gpu_mlp.py states
+    the tolerance).  The PRECISION reference of the path is MlpModelF32 below, not this class."""
 
-    def __init__(self, weights, biases):
-        self.w = [bf16_round(w) for w in weights]
+    def __init__(self, weights, biases, operand="f16"):
+        self._round = f16_round if operand == "f16" else bf16_round
+        bf16_round_ = self._round
+        self.w = [bf16_round_(w) for w in weights]
         self.b = [np.asarray(b, np.float32).astype(np.float64) for b in biases]
         self.obs_dim = self.w[2].shape[0]
         self.act_dim = self.w[0].shape[1] - self.obs_dim
         self.state_dim = self.obs_dim
 
     def step(self, obs, act):
-        x = bf16_round(np.concatenate([obs, act], axis=-1))
-        h1 = bf16_round(np.tanh(x @ self.w[0].T + self.b[0]))
-        h2 = bf16_round(np.tanh(h1 @ self.w[1].T + self.b[1]))
+        rnd = self._round
+        x = rnd(np.concatenate([obs, act], axis=-1))
+        h1 = rnd(np.tanh(x @ self.w[0].T + self.b[0]))
+        h2 = rnd(np.tanh(h1 @ self.w[1].T + self.b[1]))
         return obs + h2 @ self.w[2].T + self.b[2]
 
     def observe(self, state):

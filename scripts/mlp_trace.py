@@ -31,9 +31,6 @@ names2 = {0: "x", 1: "d1A", 2: "e1A", 3: "d1B", 4: "e1B", 5: "d2A", 6: "e2A", 7:
 names = {0: "x_arrive", 1: "d1_ready", 2: "e1s0", 3: "e1s1", 4: "e1s2", 5: "e1s3", 7: "d2_ready", 8: "e2s0", 9: "e2s1",
          10: "e2s2", 11: "e2s3", 13: "d3_ready", 14: "step_end", 16: "I:x", 17: "I:a0", 18: "I:a1", 19: "I:a2", 20: "I:a3",
          21: "I:b0", 22: "I:b1", 23: "I:b2", 24: "I:b3", 25: "I:commit3"}
-if os.environ.get("ICEM_B200_MLP_2CTA") == "1":
-    names = names2
-for step in (3, 4, 5):
     base = t[step, 0]
     ev = sorted((t[step, k] - base, v) for k, v in names.items() if t[step, k])
     print("step", step, " ".join(f"{v}@{c}" for c, v in ev), "| next x_arrive @", t[step + 1, 0] - base)

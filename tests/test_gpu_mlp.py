@@ -1,7 +1,8 @@
-"""GPU parity of the tensor-core MLP rollout (csrc/mlp_rollout.cuh: tcgen05.mma + TMEM, bf16 operands, fp32
-accumulation) against the NumPy oracle that restates the operand roundings (oracle/dynamics_np.py::MlpModel).
+"""GPU parity of the tensor-core MLP rollout (csrc/mlp_rollout.cuh: tcgen05.mma + TMEM, fp16 operands, fp32
+accumulation) against (a) the NumPy oracle that restates the operand roundings (oracle/dynamics_np.py::MlpModel) and
+(b) the fp32 model without any restatement (MlpModelF32 == torch fp32 nn.Sequential): the precision reference.
 
-Tolerance: bf16 resolution.  The oracle reproduces every bf16 rounding point but not the tensor core's accumulation
+Tolerance of (a): operand resolution (written for the round-1 bf16 kernel; the fp16 kernel sits well inside it).  The oracle reproduces every bf16 rounding point but not the tensor core's accumulation
 order nor tanh.approx (relative error ~5e-4); a value that lands within that error of a bf16 rounding boundary
 rounds the other way (1 bf16 ulp = 0.4 %), so per-step observations agree to ~1e-2 absolute after 11 steps of an
 O(1) state and h=12 costs to a few 1e-2, not to fp32 precision.  Elite SETS must agree except for candidates whose
@@ -48,13 +49,8 @@ def test_single_transition_matches_oracle(hidden):
     p.close()
 
 
-@pytest.mark.parametrize("two_cta", [False, True])
 @pytest.mark.parametrize("hidden,n", [(256, 1000), (128, 300), (64, 129)])
-def test_tensor_core_rollout_costs_match_oracle(hidden, n, two_cta, monkeypatch):
-    """Both tensor-core schedules: one 128-row tile per SM (mlp_rollout.cuh, default) and the CTA-pair kernel with
-    `tcgen05 cta_group::2` and two tiles per SM in flight (mlp_rollout_2cta.cuh, ICEM_B200_MLP_2CTA=1)."""
-    if two_cta:
-        monkeypatch.setenv("ICEM_B200_MLP_2CTA", "1")
+def test_tensor_core_rollout_costs_match_oracle(hidden, n):
     p, mod = _planner(hidden)
     rs = np.random.RandomState(1)
     acts = rs.uniform(-1, 1, (n, 12, 6)).astype(np.float32)

@@ -40,9 +40,12 @@ def test_register_budgets_of_the_hot_kernels(lib):
     k = _find(res, "colored_sampler_kernelILi16")
     assert k["reg"] <= 80 and k["stack"] == 0, k
     # tensor-core MLP rollout: 17 warps -> 96 registers at most (65536 / (5 warps * 32 lanes) per scheduler)
-    for name in ("mlp_rollout_kernel", "mlp_rollout_2cta_kernel"):
-        k = _find(res, name + "E")
-        assert k["reg"] <= 96, (name, k)
+    k = _find(res, "mlp_rollout_kernelE")
+    assert k["reg"] <= 96, k
+    # branch-parallel articulated engine: up to 12 warps per SM (384 threads) -> at most 170 registers, no spills
+    for g in (1, 2, 4):
+        k = _find(res, "chain_rollout_kernel", f"ILi{g}ELb1ELb1ELb0")
+        assert k["reg"] <= 170 and k["stack"] <= 64, k
     k = _find(res, "select_kernel")
     assert k["reg"] <= 64 and k["shared"] <= 16 * 1024, k
 
@@ -66,10 +69,10 @@ def test_sass_shows_the_blackwell_paths(lib):
     mlp = body("mlp_rollout_kernelE")
     for mnemonic in ("UTCHMMA", "LDTM", "UTCBAR", "MUFU.TANH", "SYNCS"):      # tcgen05.mma / .ld / .commit, mbarriers
         assert mnemonic in mlp, mnemonic
-    mlp2 = body("mlp_rollout_2cta_kernelE")
-    assert "UTCHMMA.2CTA" in mlp2
-    # cluster-scope release / acquire on the per-stage barriers would show up as these (measured 2x slower):
-    assert mlp2.count("MEMBAR.ALL.GPU") <= 2 and mlp2.count("CCTL.IVALL") <= 2
+    chain = body("chain_rollout_kernel", "ILi4ELb1ELb1ELb0")
+    assert "UBLKCP" in chain                                                  # TMA bulk store of the sampled tiles
+    assert "SHFL.BFLY" in chain                                               # junction sums inside a lane group
+    assert "MUFU.RCP" in chain and "LDS" in chain
     fused = body("rollout_kernel", "ArticulatedILi24EEELb1ELb1ELb0")
     assert "UBLKCP" in fused                                                  # TMA bulk store of the action tile
     assert "CALL.REL.NOINC" in fused or "CALL.ABS.NOINC" in fused             # the rollout is compiled out of line
