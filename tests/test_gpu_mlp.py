@@ -145,18 +145,17 @@ def test_series_sampler_inside_the_plan_step():
     p.close()
 
 
-def test_bf16_tensor_core_plan_against_the_fp32_plan():
-    """The precision reference of the tensor-core path is the fp32 model (oracle/dynamics_np.py::MlpModelF32 == a
-    torch fp32 nn.Sequential), NOT the oracle that restates the kernel's bf16 roundings: plan 6 closed-loop steps with
-    both on identical draws (scripts/mlp_precision_report.py) and require that the bf16 plan picks essentially the same
-    elites and executes essentially the same action.  Full-size numbers (N = 65536, 20 steps) are in
-    profiles/r2_mlp_bf16_vs_fp32.json."""
+def test_tensor_core_ranking_against_the_fp32_model():
+    """The precision reference of the tensor-core path is the fp32 model (oracle/dynamics_np.py::MlpModelF32 == a torch
+    fp32 nn.Sequential), NOT the oracle that restates the kernel's operand roundings: along 4 closed-loop steps of the
+    fp32 plan the device scores the same candidates at every CEM iteration (scripts/mlp_precision_report.py) and must
+    pick essentially the same elites and the same best candidate.  Full-size numbers (N = 65536, 20 steps) are in
+    profiles/r2_mlp_f16_vs_fp32.json."""
     import os
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
     from mlp_precision_report import run
-    rep = run(4096, 6, quiet=True)
-    # iteration 0 samples from the identical distribution in both planners: pure effect of the operand precision
-    assert rep["elite_overlap_first_iteration"]["mean"] >= 0.8, rep["elite_overlap_first_iteration"]
-    assert rep["elite_overlap_last_iteration"]["mean"] >= 0.6, rep["elite_overlap_last_iteration"]
-    assert rep["executed_action_abs_diff"]["median"] <= 0.1 * rep["executed_action_abs_diff"]["action_range"]
+    rep = run(4096, 4, quiet=True)
+    assert rep["cost_err_median"] <= 5e-3, rep["cost_err_median"]
+    assert rep["elite_overlap"]["mean"] >= 0.85, rep["elite_overlap"]
+    assert rep["executed_action_abs_diff"]["same_best_candidate_share"] >= 0.75, rep["executed_action_abs_diff"]
