@@ -254,8 +254,12 @@ struct ChainLane {
     return trunk ? shared_rec(M->s_dof + kChTrunkDofRec * M->d_rec[j])
                  : private_rec(M->p_dof + kChDofRec * M->d_rec[j]);
   }
+  // Node records: trunk nodes in the shared region; a limb's FIRST node is parked in the junction region (idle
+  // between the limb's start and the junction sums: 16 slots per lane of the group), its last node stays in
+  // registers, the ones in between (limbs of 3+ bodies) go to the lane-private region.
   __host__ __device__ __forceinline__ ChRef node_rec(bool trunk, int pos) const {
-    return trunk ? shared_rec(M->s_node + kChNodeRec * pos) : private_rec(M->p_node + kChNodeRec * pos);
+    if (trunk) return shared_rec(M->s_node + kChNodeRec * pos);
+    return pos == 0 ? shared_rec(M->s_frame + kChNodeRec * g) : private_rec(M->p_node + kChNodeRec * (pos - 1));
   }
   // node this lane visits at position i of its walk (trunk nodes, then its own limb); false = nothing to do
   __host__ __device__ __forceinline__ bool node_at(int i, int& node, bool& trunk, int& pos) const {
@@ -477,13 +481,16 @@ struct ChainLane {
       for (int k = 0; k < 3; ++k) p[k] = f[9 + k];
 #pragma unroll
       for (int k = 0; k < 6; ++k) v[k] = f[12 + k];
+    }
+    ctx->group_sync();      // every lane has its attach frame: the frame region may now park the limbs' first records
+    if (g < m.n_limbs) {
       const int nn = m.limb_nnodes[g];
       for (int i = 0; i < nn; ++i) {
         const int node = m.limb_node[g][i];
         walk_joints(node, false, false, R, p, v, O, q, qd, ctrl, dt);
         node_work(node, R, p, v, Oz, rec);
         if (i != nn - 1) {
-          const ChRef nr = private_rec(m.p_node + kChNodeRec * i);
+          const ChRef nr = node_rec(false, i);
 #pragma unroll
           for (int e = 0; e < kChNodeRec; ++e) nr[e] = rec[e];
         }
@@ -949,16 +956,21 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
   m.s_free = s; s += m.root_free ? kChFreeRec : 0;
   m.s_dof = s; s += kChTrunkDofRec * m.trunk_dofs;
   m.s_node = s; s += kChNodeRec * m.n_trunk;
-  // one region, three tenants in turn: junction frames (pass 1) -> junction sums (pass 2) -> junction accelerations
-  // (pass 3); the lanes are synchronised between the tenants (group sum / group_sync)
+  // one region, four tenants in turn: trunk frames (pass 1) -> the limbs' first node records (until their pass 2) ->
+  // junction sums (pass 2) -> junction accelerations (pass 3); the lanes are synchronised between the tenants
+  // (group_sync / group sum)
   m.s_frame = s; m.s_jun = s; m.s_acc = s;
-  s += kChJun * m.n_junctions > kChFrame * m.n_trunk ? kChJun * m.n_junctions : kChFrame * m.n_trunk;
+  {
+    int region = kChJun * m.n_junctions > kChFrame * m.n_trunk ? kChJun * m.n_junctions : kChFrame * m.n_trunk;
+    if (m.max_limb_nodes >= 2 && kChNodeRec * m.lanes > region) region = kChNodeRec * m.lanes;   // parked first records
+    s += region;
+  }
   m.s_rk = s; s += m.integrator == kChRK4 ? m.nq + 3 * m.nv : 0;
   m.s_end = s;
   int p = 0;
   m.p_dof = p; p += kChDofRec * m.max_limb_dofs;
-  // the last node of a walk keeps its record in registers (pass 1 -> pass 2)
-  m.p_node = p; p += kChNodeRec * (m.max_limb_nodes > 0 ? m.max_limb_nodes - 1 : 0);
+  // a limb's last node keeps its record in registers (pass 1 -> pass 2), its first one is parked in the junction region
+  m.p_node = p; p += kChNodeRec * (m.max_limb_nodes > 2 ? m.max_limb_nodes - 2 : 0);
   m.p_end = p;
   return true;
 }
