@@ -55,6 +55,15 @@ WORKLOADS = {
         settings=dict(_BLITZ, num_simulated_trajectories=16384, opt_iterations=3, noise_beta=2.0,
                       dynamics="humanoid_standup", cost="humanoid_standup", obs_dim=47, integrator="rk4"),
         act_dim=17, bound=0.4, env="HumanoidStandup", env_kwargs=dict(integrator="rk4")),
+    # the population of BASELINE configs[4] on ONE GPU (the strong-scaling base), Euler and Runge-Kutta
+    "humanoid_standup_gt_n262144": dict(
+        settings=dict(_BLITZ, num_simulated_trajectories=262144, opt_iterations=3, noise_beta=2.0,
+                      dynamics="humanoid_standup", cost="humanoid_standup", obs_dim=47),
+        act_dim=17, bound=0.4, env="HumanoidStandup"),
+    "humanoid_standup_gt_n262144_rk4": dict(
+        settings=dict(_BLITZ, num_simulated_trajectories=262144, opt_iterations=3, noise_beta=2.0,
+                      dynamics="humanoid_standup", cost="humanoid_standup", obs_dim=47, integrator="rk4"),
+        act_dim=17, bound=0.4, env="HumanoidStandup", env_kwargs=dict(integrator="rk4")),
     # one shard of BASELINE configs[4] (N=262144 over 8 GPUs): 32768 trajectories per GPU
     "humanoid_standup_gt_shard32768": dict(
         settings=dict(_BLITZ, num_simulated_trajectories=32768, opt_iterations=3, noise_beta=2.0,

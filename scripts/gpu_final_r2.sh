@@ -7,6 +7,7 @@ python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 python bench.py > gpurun_out/r2_bench_humanoid_gt_$TAG.json 2>gpurun_out/bench.err; cut -c1-300 gpurun_out/r2_bench_humanoid_gt_$TAG.json
 python bench.py --workload humanoid_standup_gt_n16384_rk4 --no-cpu-baseline > gpurun_out/r2_bench_humanoid_gt_rk4_$TAG.json 2>/dev/null; cut -c1-200 gpurun_out/r2_bench_humanoid_gt_rk4_$TAG.json
+python bench.py --workload humanoid_standup_gt_n262144_rk4 --no-cpu-baseline --steps 5 > gpurun_out/r2_bench_humanoid_gt_n262144_rk4_$TAG.json 2>/dev/null; cut -c1-200 gpurun_out/r2_bench_humanoid_gt_n262144_rk4_$TAG.json
 python bench.py --workload halfcheetah_gt_n4096 --no-cpu-baseline > gpurun_out/r2_bench_halfcheetah_gt_$TAG.json 2>/dev/null; cut -c1-200 gpurun_out/r2_bench_halfcheetah_gt_$TAG.json
 python bench.py --workload halfcheetah_gt_n4096_rk4 --no-cpu-baseline > gpurun_out/r2_bench_halfcheetah_gt_rk4_$TAG.json 2>/dev/null; cut -c1-200 gpurun_out/r2_bench_halfcheetah_gt_rk4_$TAG.json
 python bench.py --workload mlp_cheetah_n65536 --no-cpu-baseline > gpurun_out/r2_bench_mlp_$TAG.json 2>/dev/null; cut -c1-200 gpurun_out/r2_bench_mlp_$TAG.json
