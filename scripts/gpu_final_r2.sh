@@ -19,6 +19,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"chain_rollout_kernel" -s 3 -c 1 -f -o gpurun_out/r2_prof_chain_humanoid_$TAG python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-strong > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:"chain_rollout_kernel" -s 5 -c 1 -f -o gpurun_out/r2_prof_chain_cheetah_$TAG python bench.py --workload halfcheetah_gt_n4096 --steps 1 --warmup 3 --no-cpu-baseline --no-strong > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none -k regex:"mlp_rollout_kernel" -c 1 -f -o gpurun_out/r2_prof_mlp_$TAG python bench.py --workload mlp_cheetah_n65536 --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+# summaries here (the box has ncu); only the headline kernel's report travels back (64 MiB limit on gpurun_out)
+python scripts/ncu_summary.py gpurun_out/r2_prof_chain_humanoid_$TAG.ncu-rep > gpurun_out/r2_ncu_full_chain_rollout_humanoid_gt_n16384_$TAG.txt
+python scripts/ncu_summary.py gpurun_out/r2_prof_chain_cheetah_$TAG.ncu-rep > gpurun_out/r2_ncu_full_chain_rollout_halfcheetah_gt_n4096_$TAG.txt
+python scripts/ncu_summary.py gpurun_out/r2_prof_mlp_$TAG.ncu-rep > gpurun_out/r2_ncu_full_mlp_rollout_n65536_$TAG.txt
+rm -f gpurun_out/r2_prof_chain_cheetah_$TAG.ncu-rep gpurun_out/r2_prof_mlp_$TAG.ncu-rep
 timeout 200 compute-sanitizer --tool memcheck --print-limit 5 python scripts/sanitize.py cheetah humanoid > gpurun_out/r2_sanitize_memcheck_$TAG.log 2>&1; grep -E "ok$|ERROR SUMMARY" gpurun_out/r2_sanitize_memcheck_$TAG.log
 timeout 300 compute-sanitizer --tool synccheck --print-limit 5 python scripts/sanitize.py cheetah humanoid mlp > gpurun_out/r2_sanitize_synccheck_$TAG.log 2>&1; grep -E "ok$|ERROR SUMMARY" gpurun_out/r2_sanitize_synccheck_$TAG.log
 timeout 400 compute-sanitizer --tool racecheck --print-limit 5 python scripts/sanitize.py cheetah humanoid > gpurun_out/r2_sanitize_racecheck_$TAG.log 2>&1; grep -E "ok$|ERROR SUMMARY|RACECHECK SUMMARY" gpurun_out/r2_sanitize_racecheck_$TAG.log
