@@ -460,8 +460,11 @@ struct ChainLane {
       for (int k = 0; k < 6; ++k) f[12 + k] = v[k];
     }
     const float Oz = O[2];
+    // every lane wrote every frame (identical values), so a lane could read right behind its own stores; the barrier
+    // keeps the access pattern formally race-free (compute-sanitizer racecheck) at the price of one WARPSYNC
+    ctx->group_sync();
     for (int t = g; t < m.n_trunk; t += m.lanes) {
-      const ChRef f = shared_rec(m.s_frame + kChFrame * t);     // written by this very lane a moment ago
+      const ChRef f = shared_rec(m.s_frame + kChFrame * t);
 #pragma unroll
       for (int k = 0; k < 9; ++k) R[k] = f[k];
 #pragma unroll
@@ -518,6 +521,7 @@ struct ChainLane {
 #pragma unroll
           for (int e = 0; e < 9; ++e) x[6 + e] = w ? IA.B[e] : 0.f;
           ctx->group_sum(x);
+          if (js == 0) ctx->group_sync();      // the junction region changes tenant: parked limb records -> sums
           const ChRef jr = shared_rec(m.s_jun + kChJun * js);
 #pragma unroll
           for (int e = 0; e < kChJun; ++e) jr[e] = x[e];
@@ -603,6 +607,7 @@ struct ChainLane {
     for (int i = 0; i < n_seq; ++i) {
       int node, pos;
       bool trunk;
+      if (i == m.n_trunk) ctx->group_sync();     // the junction accelerations are complete in every lane's view
       if (!node_at(i, node, trunk, pos)) continue;
       if (!trunk && pos == 0) {
         const ChRef ar = shared_rec(m.s_acc + 6 * m.trunk_junction[m.limb_attach[g]]);
