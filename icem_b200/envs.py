@@ -304,13 +304,17 @@ class HalfCheetahMaybeWithPosition(_DeviceSimEnv):
 
 
 class HumanoidStandup(_DeviceSimEnv):
-    """Stand-in for environments/mujoco.py:228-277.  The reference observation is 378 wide but its cost reads only
-    obs[2] (= qpos[2], root height); this env exposes obs = qpos ++ qvel (47)."""
+    """Stand-in for environments/mujoco.py:228-277.  Same 378-wide observation layout as the reference
+    (mujoco.py:241-252: qpos(24) ++ qvel(23) ++ cinert(140) ++ cvel(84) ++ qfrc_actuator(23) ++ cfrc_ext(84)); the cost
+    reads only obs[2] (= qpos[2], root height), and the device model carries qpos / qvel only, so the four trailing
+    blocks (331 entries) are zeros -- consumers of `elite_samples["observations"]` see the reference's shape."""
     kind = "HumanoidStandup"
     dt = 0.015
+    obs_pad = 331
 
     def __init__(self, *, name="HumanoidStandup", device=0, **kwargs):
-        self.observation_space = Box(-np.inf * np.ones(47), np.inf * np.ones(47))
+        n = 47 + self.obs_pad
+        self.observation_space = Box(-np.inf * np.ones(n), np.inf * np.ones(n))
         super().__init__(name=name, device=device, **kwargs)
         self.store_init_arguments(locals())
 
@@ -324,7 +328,7 @@ class HumanoidStandup(_DeviceSimEnv):
         return humanoid_standup_cost_fn(observation, action, next_obs)
 
     def _obs(self):
-        return self._state.copy()
+        return np.concatenate([self._state, np.zeros(self.obs_pad)])
 
     def reset(self):
         c = 0.01

@@ -40,7 +40,7 @@ def test_cost_parameter_mapping():
 def test_standin_env_layouts_without_a_device():
     """Construction, reset, observation widths and cost specs need no GPU (the device model is created lazily)."""
     from icem_b200 import envs
-    widths = {"HalfCheetah": 17, "HumanoidStandup": 47, "Hopper": 12, "Ant": 113, "Humanoid": 378}
+    widths = {"HalfCheetah": 17, "HumanoidStandup": 378, "Hopper": 12, "Ant": 113, "Humanoid": 378}   # reference widths
     for name, w in widths.items():
         env = envs.make_env(name)
         env.seed(1)
