@@ -48,16 +48,19 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10 counter-based RNG (Salmon et al. 2011): one call -> 4 x uint32, no state.
+// Philox4x32-R counter-based RNG (Salmon et al., SC'11): one call -> 4 x uint32, no state.  R = 10 is the
+// authors' default; R = 7 is the smallest round count for which they report the generator Crush-resistant
+// (passes TestU01 BigCrush) and is what the stand-alone sampler uses.
 struct Philox4 {
   uint32_t x, y, z, w;
 };
 
-__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                           uint32_t k0, uint32_t k1) {
+template <int ROUNDS>
+__host__ __device__ __forceinline__ Philox4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                        uint32_t k0, uint32_t k1) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     const uint64_t p0 = (uint64_t)M0 * c0;
     const uint64_t p1 = (uint64_t)M1 * c2;
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -68,6 +71,11 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     k0 += W0; k1 += W1;
   }
   return Philox4{c0, c1, c2, c3};
+}
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                           uint32_t k0, uint32_t k1) {
+  return philox4x32<10>(c0, c1, c2, c3, k0, k1);
 }
 
 // two uniforms -> two standard normals (Box-Muller, fast intrinsics: sampling noise, not a parity path)

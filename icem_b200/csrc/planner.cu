@@ -110,6 +110,7 @@ struct icem_planner {
   size_t actions_per = 0, costs_per = 0;   // per-problem elements of `actions` / `costs`
   int sm_count = 148;
   bool white = false;
+  std::vector<float> G_host;         // host copy of G: the compile-time-shaped samplers take their table rows as kernel parameters
   bool force_warp_sampler = false;   // ICEM_B200_WARP_SAMPLER=1 at icem_create: A/B the two samplers (tests)
   std::vector<IterPlan> plan;
   cudaStream_t stream = nullptr;
@@ -350,27 +351,44 @@ static bool series_sampler_eligible(icem_planner* p) {
          p->d <= kSamplerThreads && !p->force_warp_sampler;
 }
 
-template <int KPAD>
+template <int KPAD, int H, int D>
 static void launch_series_sampler_k(icem_planner* p, const RolloutArgs& a, int rows_max) {
   const SamplerConst sc = sampler_const(p);
-  const int R = sampler_rows_per_batch(p->d, a.stride);
+  constexpr int threads = sampler_threads(KPAD, H, D);
+  const int R = sampler_rows_per_batch(p->d, a.stride, threads);
   const size_t smem = sampler_smem_bytes(p->h, p->d, KPAD, a.stride, R);
-  auto kern = colored_sampler_kernel<KPAD>;
+  auto kern = colored_sampler_kernel<KPAD, H, D>;
   ensure_dynamic_smem(kern, smem, p->cfg.device);
   int occ = 0;
-  ICEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSamplerThreads, smem));
+  ICEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
   if (occ < 1) throw InvalidArg("sampler kernel does not fit on an SM (shared memory)");
   const int batches = (rows_max + R - 1) / R;
   const int grid = std::max(1, std::min(batches, p->sm_count * occ));
-  kern<<<grid, kSamplerThreads, smem, p->stream>>>(a, sc, R);
+  SamplerTable<sampler_table_floats(KPAD, H, D)> tab{};
+  if constexpr (H > 0 && D > 0) {      // rows t = 0 .. h/4 of G: cosine side [t][KPAD], then sine side, zero padded
+    constexpr int rows = (H / 2) / 2 + 1;
+    const int K = p->K;
+    float* v = reinterpret_cast<float*>(tab.v2);
+    for (int t = 0; t < rows; ++t)
+      for (int k = 0; k < K; ++k) {
+        v[t * KPAD + k] = p->G_host[(size_t)t * 2 * K + k];
+        v[(rows + t) * KPAD + k] = p->G_host[(size_t)t * 2 * K + K + k];
+      }
+  }
+  kern<<<grid, threads, smem, p->stream>>>(a, sc, R, tab);
   ICEM_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
 static void launch_series_sampler(icem_planner* p, const RolloutArgs& a, int rows_max) {
-  if (p->K <= 8) launch_series_sampler_k<8>(p, a, rows_max);
-  else if (p->K <= 16) launch_series_sampler_k<16>(p, a, rows_max);
-  else launch_series_sampler_k<32>(p, a, rows_max);
+  // the shapes of BASELINE's configurations are compiled with horizon and action dim as constants
+  const bool packed = a.stride == ((p->h * p->d + 3) & ~3);
+  if (packed && p->h == 30 && p->d == 17) launch_series_sampler_k<16, 30, 17>(p, a, rows_max);
+  else if (packed && p->h == 30 && p->d == 6) launch_series_sampler_k<16, 30, 6>(p, a, rows_max);
+  else if (packed && p->h == 12 && p->d == 6) launch_series_sampler_k<8, 12, 6>(p, a, rows_max);
+  else if (p->K <= 8) launch_series_sampler_k<8, 0, 0>(p, a, rows_max);
+  else if (p->K <= 16) launch_series_sampler_k<16, 0, 0>(p, a, rows_max);
+  else launch_series_sampler_k<32, 0, 0>(p, a, rows_max);
 }
 
 constexpr size_t kMaxSmemPerCta = 227 * 1024;
@@ -846,8 +864,9 @@ int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
   p->ev_roll.resize(2 * p->iters);
   for (auto& e : p->ev_roll) ICEM_CUDA(cudaEventCreate(&e));
 
-  upload(p->G, p->white ? std::vector<float>(1, 0.f)
-                        : build_synthesis_matrix(p->h, cfg->noise_beta, cfg->colorednoise_v2 != 0));
+  p->G_host = p->white ? std::vector<float>(1, 0.f)
+                        : build_synthesis_matrix(p->h, cfg->noise_beta, cfg->colorednoise_v2 != 0);
+  upload(p->G, p->G_host);
   upload(p->d_low, p->low);
   upload(p->d_high, p->high);
   // icem.py:48-59: the bounds are float32 (gym Box) and the reference does this arithmetic on them

@@ -145,6 +145,60 @@ def test_series_sampler_inside_the_plan_step():
     p.close()
 
 
+@pytest.mark.parametrize("h,d,obs_dim,cost", [(30, 17, 8, "humanoid_standup"), (30, 6, 18, "halfcheetah"),
+                                              (12, 6, 18, "halfcheetah"), (20, 5, 18, "halfcheetah")])
+def test_production_normals_of_the_series_sampler(h, d, obs_dim, cost):
+    """The unit normals behind the production draws of csrc/sampler.cuh (Philox4x32-7, three Box-Muller pairs per call
+    from 21-bit fields, SFU approximations): undo the synthesis with an rfft and test the recovered per-bin real /
+    imaginary parts for what `np.random.normal` gives the reference (icem.py:73-75 via colorednoise): zero mean, equal
+    variance of real and imaginary parts, Gaussian shape (KS, kurtosis, 3- and 4-sigma tail mass), no correlation between
+    bins, between the two members of a Box-Muller pair, or between the series of one call group.  The first three
+    shapes run the compile-time-shaped kernels, the last one the run-time-shaped one."""
+    from scipy import stats
+    from icem_b200 import workloads
+    from icem_b200.planner import Planner, PlannerSettings
+    n = 8192
+    ws, bs = workloads.mlp_model_weights(obs_dim, d, 64, 3)
+    p = Planner(PlannerSettings(horizon=h, num_simulated_trajectories=n, action_low=-np.ones(d, np.float32),
+                                action_high=np.ones(d, np.float32), dynamics="mlp", cost=cost, obs_dim=obs_dim,
+                                noise_beta=1.0, init_std=0.02, opt_iterations=1, use_mean_actions=False, seed=11,
+                                keep_iteration_actions=True))
+    p.set_mlp_model(ws, bs)
+    p.begin_rollout()
+    p.plan(np.zeros(obs_dim))
+    y = p.actions(0, n).astype(np.float64) / 0.02          # [n, h, d]: nothing is clipped at 50 sigma
+    assert np.abs(y).max() < 40
+    Y = np.fft.rfft(y.transpose(0, 2, 1), axis=-1)          # [n, d, K]
+    K = h // 2 + 1
+    re, im = Y.real, Y.imag
+    assert np.abs(im[..., 0]).max() < 1e-3 and np.abs(im[..., -1]).max() < 1e-3
+    comps = [re[..., k] for k in range(K)] + [im[..., k] for k in range(1, K - 1)]      # the h normals of a series
+    z = np.stack([c / c.std() for c in comps], axis=-1)     # [n, d, h] unit normals up to the known per-bin scale
+    for k in range(1, K - 1):                               # real and imaginary parts carry the same scale
+        assert abs(re[..., k].std() / im[..., k].std() - 1) < 0.02
+    flat = z.reshape(-1)
+    assert abs(flat.mean()) < 4 / np.sqrt(flat.size)
+    assert abs(stats.kurtosis(flat)) < 0.03
+    assert abs(stats.skew(flat)) < 0.01
+    for thr, mass in ((3.0, 2.6998e-3), (4.0, 6.334e-5)):
+        got = np.mean(np.abs(flat) > thr)
+        assert abs(got - mass) < 5 * np.sqrt(mass / flat.size) + 0.02 * mass, (thr, got)
+    assert stats.kstest(flat[::7], "norm").pvalue > 1e-3
+    # independence: between bins, between the members of a pair (real / imaginary part of one bin), between the action
+    # dims of a trajectory and between neighbouring trajectories
+    c = np.corrcoef(z.reshape(-1, h), rowvar=False)
+    assert np.abs(c - np.eye(h)).max() < 5 / np.sqrt(n * d)
+    assert abs(np.mean(z[:, 0, :] * z[:, 1, :])) < 5 / np.sqrt(n * h)
+    assert abs(np.mean(z[1:, 0, :] * z[:-1, 0, :])) < 5 / np.sqrt(n * h)
+    # squared magnitudes of a pair are independent exponentials (radius and angle come from disjoint bit fields)
+    r2 = z[..., 1:K - 1] ** 2 + z[..., K:] ** 2
+    ang = np.arctan2(z[..., K:], z[..., 1:K - 1])
+    assert abs(np.corrcoef(r2.reshape(-1), np.cos(ang).reshape(-1))[0, 1]) < 5 / np.sqrt(r2.size)
+    assert stats.kstest(r2.reshape(-1)[::5] / 2, "expon").pvalue > 1e-3
+    assert stats.kstest((ang.reshape(-1)[::5] + np.pi) / (2 * np.pi), "uniform").pvalue > 1e-3
+    p.close()
+
+
 def test_tensor_core_ranking_against_the_fp32_model():
     """The precision reference of the tensor-core path is the fp32 model (oracle/dynamics_np.py::MlpModelF32 == a torch
     fp32 nn.Sequential), NOT the oracle that restates the kernel's operand roundings: along 4 closed-loop steps of the

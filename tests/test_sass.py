@@ -36,9 +36,13 @@ def test_register_budgets_of_the_hot_kernels(lib):
     for nv in (12, 24):
         k = _find(res, "rollout_kernel", f"ArticulatedILi{nv}EEELb1ELb1ELb0")
         assert k["reg"] <= 80 and k["stack"] <= 192, k
-    # stand-alone sampler: 3 CTAs per SM at K <= 16, no stack
-    k = _find(res, "colored_sampler_kernelILi16")
+    # stand-alone sampler: 3 CTAs per SM at K <= 16 (256 threads / 80 registers for the run-time-shaped kernel, 192
+    # threads / 96 for the compile-time-shaped ones), no stack
+    k = _find(res, "colored_sampler_kernelILi16ELi0ELi0E")
     assert k["reg"] <= 80 and k["stack"] == 0, k
+    for shape in ("ILi16ELi30ELi17E", "ILi16ELi30ELi6E", "ILi8ELi12ELi6E"):
+        k = _find(res, "colored_sampler_kernel" + shape)
+        assert k["reg"] <= 96 and k["stack"] == 0, k
     # tensor-core MLP rollout: 17 warps -> 96 registers at most (65536 / (5 warps * 32 lanes) per scheduler)
     k = _find(res, "mlp_rollout_kernelE")
     assert k["reg"] <= 96, k
@@ -80,7 +84,10 @@ def test_sass_shows_the_blackwell_paths(lib):
     assert "BAR.SYNC" in dense                                                # (cheap model: rollout inlined)
     loads = body("rollout_kernel", "ArticulatedILi24EEELb0ELb1ELb0")
     assert "UBLKCP" in loads and "SYNCS" in loads                             # TMA bulk loads on mbarriers
-    sampler = body("colored_sampler_kernelILi16")
+    sampler = body("colored_sampler_kernelILi16ELi0ELi0E")                    # run-time shape: table rows from smem
     assert "UBLKCP" in sampler and "MUFU.LG2" in sampler and "LDS.128" in sampler
+    sampler = body("colored_sampler_kernelILi16ELi30ELi17E")                  # BASELINE shape: packed-fp32 fold whose
+    assert "UBLKCP" in sampler and "FFMA2" in sampler and "LDCU" in sampler  # table operands are kernel-parameter constants
+    assert "LDS.128" not in sampler and "LDL" not in sampler and "STL" not in sampler
     select = body("select_kernel")
     assert "REDUX" in select or "CREDUX" in select                            # 64-bit warp minima by two REDUX.MIN
