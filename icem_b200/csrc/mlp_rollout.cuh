@@ -131,13 +131,6 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar)) : "memory");
 }
-// pre-activations (lo, hi) -> fp16 pair -> tanh on the pair in ONE MUFU instruction: the result is the packed operand
-__device__ __forceinline__ uint32_t tanh_f16x2(float lo, float hi) {
-  uint32_t h, y;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
-  asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(h));
-  return y;
-}
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -393,17 +386,12 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float4 b = b4[j];
-#ifdef ICEM_MLP_TANH_F16X2
-                pk[2 * j] = tanh_f16x2(__uint_as_float(rv[4 * j]) + b.x, __uint_as_float(rv[4 * j + 1]) + b.y);
-                pk[2 * j + 1] = tanh_f16x2(__uint_as_float(rv[4 * j + 2]) + b.z, __uint_as_float(rv[4 * j + 3]) + b.w);
-#else
                 __half2 lo2 = __floats2half2_rn(tanh_approx(__uint_as_float(rv[4 * j]) + b.x),
                                                            tanh_approx(__uint_as_float(rv[4 * j + 1]) + b.y));
                 __half2 hi2 = __floats2half2_rn(tanh_approx(__uint_as_float(rv[4 * j + 2]) + b.z),
                                                            tanh_approx(__uint_as_float(rv[4 * j + 3]) + b.w));
                 pk[2 * j] = *reinterpret_cast<uint32_t*>(&lo2);
                 pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi2);
-#endif
               }
               unsigned char* dst = dstH + (size_t)(c0 / 8) * 128;
               *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
