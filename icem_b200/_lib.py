@@ -7,7 +7,7 @@ import numpy as np
 LIB_PATH = os.environ.get("ICEM_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
                                                            "libicem_b200.so")
 
-ICEM_ABI_VERSION = 7
+ICEM_ABI_VERSION = 8
 INTEGRATOR = {"euler": 0, "rk4": 1}
 DYN = {"dense_tanh": 0, "halfcheetah": 1, "humanoid_standup": 2, "mlp": 3, "articulated": 4}
 COST = {"halfcheetah": 0, "humanoid_standup": 1, "locomotion": 2}
@@ -105,6 +105,14 @@ SIGNATURES = {
     "icem_op_topk": (C.c_int, [_H, C.c_int32, _F, C.c_int32, _I, _F]),
     "icem_comm_get_unique_id": (C.c_int, [C.c_char_p]),
     "icem_comm_init": (C.c_int, [_H, C.c_char_p]),
+    "icem_mlp_trainer_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_H)]),
+    "icem_mlp_trainer_destroy": (C.c_int, [_H]),
+    "icem_mlp_trainer_set_weights": (C.c_int, [_H, C.POINTER(_F), C.POINTER(_F), C.c_int32]),
+    "icem_mlp_trainer_get_weights": (C.c_int, [_H, C.POINTER(_F), C.POINTER(_F)]),
+    "icem_mlp_trainer_set_data": (C.c_int, [_H, C.c_int64, _F, _F]),
+    "icem_mlp_trainer_fit": (C.c_int, [_H, C.c_int32, C.c_int32, _I, C.c_float, C.c_float, C.c_float, C.c_float,
+                                       C.c_float, _F]),
+    "icem_mlp_trainer_predict": (C.c_int, [_H, C.c_int32, _F, _F]),
     "icem_bench_device": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, _F, _F, _I]),
     "icem_bench_op": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _F]),
 }

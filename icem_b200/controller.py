@@ -82,6 +82,7 @@ class MpcICemB200(*_Bases):
             self._planner.set_dense_model(*spec["dense"])
         if spec.get("mlp") is not None:
             self._planner.set_mlp_model(*spec["mlp"])
+        self._model_version = getattr(fm, "version", 0)
         if world_size > 1:
             from .distributed import init_planner_comm
             init_planner_comm(self._planner)
@@ -143,6 +144,12 @@ class MpcICemB200(*_Bases):
             self.forward_model_state = state
         else:
             self.forward_model_state = self.forward_model.reset(observation)
+        if getattr(self.forward_model, "version", 0) != self._model_version:
+            # the model was re-trained since the last rollout (main.py:209-210): the planner takes the new weights
+            spec = self.forward_model.cuda_spec()
+            if spec.get("mlp") is not None:
+                self._planner.set_mlp_model(*spec["mlp"])
+            self._model_version = self.forward_model.version
         self._planner.begin_rollout()
         self.was_reset = True
         self._elite_cache = None

@@ -24,6 +24,7 @@
 #include "rollout.cuh"
 #include "rollout_chain.cuh"
 #include "select_refit.cuh"
+#include "mlp_train.cuh"
 
 namespace icem {
 
@@ -768,6 +769,97 @@ static int rows_of(icem_planner* p, int i, bool first_step) {
 // ====================================================================================================
 // C ABI
 // ====================================================================================================
+// ---------------------------------------------------------------------------------------------------------------
+// MLP trainer (mlp_train.cuh): host side
+namespace icem {
+
+struct MlpTrainer {
+  int device = 0, in = 0, H = 0, out = 0;
+  cudaStream_t stream = nullptr;
+  // parameters: W1 [H][in], b1 [H], W2 [H][H], b2 [H], W3 [out][H], b3 [out]; Adam moments alongside
+  DevBuf<float> par[6], mom[6], var[6];
+  size_t par_n[6] = {0, 0, 0, 0, 0, 0};
+  long long adam_t = 0;
+  // data set and minibatch buffers
+  DevBuf<float> x, t;
+  size_t n_rows = 0;
+  DevBuf<int> idx;
+  DevBuf<float> xb, tb, a1, a2, y, dy, dz2, dz1, gw[3], gb[3], loss_part, losses;
+  int cap_batch = 0, splits = 1;
+
+  ~MlpTrainer() {
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+template <bool TA, bool TB, int EP>
+static void train_gemm(MlpTrainer* t, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+                       int ldc, const float* bias, const float* aux, int ldaux, int splits = 1) {
+  const int kchunk = ((K + splits - 1) / splits + kTrKT - 1) / kTrKT * kTrKT;
+  dim3 grid((N + kTrTile - 1) / kTrTile, (M + kTrTile - 1) / kTrTile, splits);
+  train_gemm_kernel<TA, TB, EP><<<grid, 256, 0, t->stream>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, aux, ldaux, kchunk);
+  ICEM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+static void trainer_reserve_batch(MlpTrainer* t, int batch) {
+  if (batch <= t->cap_batch) return;
+  const int H = t->H;
+  t->splits = std::max(1, std::min(16, batch / 256));
+  t->xb.alloc((size_t)batch * t->in); t->tb.alloc((size_t)batch * t->out);
+  t->a1.alloc((size_t)batch * H); t->a2.alloc((size_t)batch * H);
+  t->y.alloc((size_t)batch * t->out); t->dy.alloc((size_t)batch * t->out);
+  t->dz2.alloc((size_t)batch * H); t->dz1.alloc((size_t)batch * H);
+  for (int l = 0; l < 3; ++l) {
+    t->gw[l].alloc(t->par_n[2 * l] * 16);       // up to 16 batch splits
+    t->gb[l].alloc(t->par_n[2 * l + 1]);
+  }
+  t->loss_part.alloc(((size_t)batch * t->out + 255) / 256);
+  t->cap_batch = batch;
+}
+
+// one Adam step on the minibatch rows idx[0..batch) (device); the step's loss goes to loss_out (device, 1 float)
+static void trainer_step(MlpTrainer* t, const int* idx, int batch, float lr, float b1, float b2, float eps, float wd,
+                         float* loss_out) {
+  const int in = t->in, H = t->H, out = t->out;
+  float* W1 = t->par[0].p; float* B1 = t->par[1].p; float* W2 = t->par[2].p; float* B2 = t->par[3].p;
+  float* W3 = t->par[4].p; float* B3 = t->par[5].p;
+  train_gather_kernel<<<batch, 32, 0, t->stream>>>(batch, in, out, t->x.p, t->t.p, idx, t->xb.p, t->tb.p);
+  // forward
+  train_gemm<false, true, kTrEpBiasTanh>(t, batch, H, in, t->xb.p, in, W1, in, t->a1.p, H, B1, nullptr, 0);
+  train_gemm<false, true, kTrEpBiasTanh>(t, batch, H, H, t->a1.p, H, W2, H, t->a2.p, H, B2, nullptr, 0);
+  train_gemm<false, true, kTrEpBias>(t, batch, out, H, t->a2.p, H, W3, H, t->y.p, out, B3, nullptr, 0);
+  // loss and its gradient
+  const int count = batch * out, nblk = (count + 255) / 256;
+  train_loss_grad_kernel<<<nblk, 256, 0, t->stream>>>(count, t->y.p, t->tb.p, t->dy.p, t->loss_part.p);
+  train_loss_reduce_kernel<<<1, 256, 0, t->stream>>>(nblk, count, t->loss_part.p, loss_out);
+  // backward: data gradients through the tanh layers, weight gradients split over the batch, bias gradients
+  const int S = t->splits;
+  train_gemm<false, false, kTrEpTanhGrad>(t, batch, H, out, t->dy.p, out, W3, H, t->dz2.p, H, nullptr, t->a2.p, H);
+  train_gemm<false, false, kTrEpTanhGrad>(t, batch, H, H, t->dz2.p, H, W2, H, t->dz1.p, H, nullptr, t->a1.p, H);
+  train_gemm<true, false, kTrEpNone>(t, out, H, batch, t->dy.p, out, t->a2.p, H, t->gw[2].p, H, nullptr, nullptr, 0, S);
+  train_gemm<true, false, kTrEpNone>(t, H, H, batch, t->dz2.p, H, t->a1.p, H, t->gw[1].p, H, nullptr, nullptr, 0, S);
+  train_gemm<true, false, kTrEpNone>(t, H, in, batch, t->dz1.p, H, t->xb.p, in, t->gw[0].p, in, nullptr, nullptr, 0, S);
+  train_colsum_kernel<<<(out + 31) / 32, 256, 0, t->stream>>>(batch, out, t->dy.p, out, t->gb[2].p);
+  train_colsum_kernel<<<(H + 31) / 32, 256, 0, t->stream>>>(batch, H, t->dz2.p, H, t->gb[1].p);
+  train_colsum_kernel<<<(H + 31) / 32, 256, 0, t->stream>>>(batch, H, t->dz1.p, H, t->gb[0].p);
+  // Adam (torch.optim.Adam: step_size = lr / (1 - b1^t), denominator sqrt(v) / sqrt(1 - b2^t) + eps)
+  t->adam_t += 1;
+  const double bc1 = 1.0 - std::pow((double)b1, (double)t->adam_t), bc2 = 1.0 - std::pow((double)b2, (double)t->adam_t);
+  const float step_size = (float)(lr / bc1), inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
+  for (int q = 0; q < 6; ++q) {
+    const int n = (int)t->par_n[q];
+    const bool is_w = (q % 2) == 0;
+    const float* g = is_w ? t->gw[q / 2].p : t->gb[q / 2].p;
+    train_adam_kernel<<<(n + 255) / 256, 256, 0, t->stream>>>(n, t->par[q].p, g, is_w ? S : 1, t->par_n[q], t->mom[q].p,
+                                                              t->var[q].p, step_size, inv_sqrt_bc2, b1, b2, eps, wd);
+  }
+  ICEM_CUDA(cudaGetLastError());
+  g_launches.fetch_add(12, std::memory_order_relaxed);
+}
+
+}  // namespace icem
+
 #define ICEM_API_BEGIN try {
 #define ICEM_API_END                                                         \
   }                                                                          \
@@ -1746,6 +1838,136 @@ int icem_bench_op(icem_planner_t* p, int32_t op, int32_t n, int32_t reps, int32_
   *ms_avg = (float)(tot / reps);
   reset_distribution(p);
   ICEM_CUDA(cudaStreamSynchronize(p->stream));
+  ICEM_API_END
+}
+
+// ---- MLP trainer ------------------------------------------------------------------------------------------------
+int icem_mlp_trainer_create(int32_t device, int32_t in_dim, int32_t hidden, int32_t out_dim, icem_mlp_trainer_t** out) {
+  ICEM_API_BEGIN
+  if (!out) throw InvalidArg("null argument");
+  if (in_dim < 1 || hidden < 1 || out_dim < 1 || in_dim > 4096 || hidden > 4096 || out_dim > 4096)
+    throw InvalidArg("layer widths must be in [1, 4096]");
+  int count = 0;
+  ICEM_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) throw InvalidArg("no such CUDA device");
+  cudaDeviceProp prop{};
+  ICEM_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) throw Unsupported("icem_b200 needs an sm_100 device (no CPU or other-architecture fallback)");
+  ICEM_CUDA(cudaSetDevice(device));
+  std::unique_ptr<MlpTrainer> t(new MlpTrainer());
+  t->device = device; t->in = in_dim; t->H = hidden; t->out = out_dim;
+  ICEM_CUDA(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+  const size_t n[6] = {(size_t)hidden * in_dim, (size_t)hidden, (size_t)hidden * hidden, (size_t)hidden,
+                       (size_t)out_dim * hidden, (size_t)out_dim};
+  for (int q = 0; q < 6; ++q) {
+    t->par_n[q] = n[q];
+    t->par[q].alloc(n[q]); t->mom[q].alloc(n[q]); t->var[q].alloc(n[q]);
+  }
+  t->losses.alloc(1);
+  *out = reinterpret_cast<icem_mlp_trainer_t*>(t.release());
+  ICEM_API_END
+}
+
+int icem_mlp_trainer_destroy(icem_mlp_trainer_t* h) {
+  ICEM_API_BEGIN
+  MlpTrainer* t = reinterpret_cast<MlpTrainer*>(h);
+  if (t) {
+    cudaSetDevice(t->device);
+    if (t->stream) cudaStreamSynchronize(t->stream);
+    delete t;
+  }
+  ICEM_API_END
+}
+
+int icem_mlp_trainer_set_weights(icem_mlp_trainer_t* h, const float* const* weights, const float* const* biases,
+                                 int32_t reset_optimizer) {
+  ICEM_API_BEGIN
+  MlpTrainer* t = reinterpret_cast<MlpTrainer*>(h);
+  if (!t || !weights || !biases) throw InvalidArg("null argument");
+  ICEM_CUDA(cudaSetDevice(t->device));
+  for (int l = 0; l < 3; ++l) {
+    if (!weights[l] || !biases[l]) throw InvalidArg("null layer parameters");
+    ICEM_CUDA(cudaMemcpyAsync(t->par[2 * l].p, weights[l], t->par_n[2 * l] * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    ICEM_CUDA(cudaMemcpyAsync(t->par[2 * l + 1].p, biases[l], t->par_n[2 * l + 1] * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+  }
+  if (reset_optimizer) {
+    for (int q = 0; q < 6; ++q) {
+      ICEM_CUDA(cudaMemsetAsync(t->mom[q].p, 0, t->par_n[q] * sizeof(float), t->stream));
+      ICEM_CUDA(cudaMemsetAsync(t->var[q].p, 0, t->par_n[q] * sizeof(float), t->stream));
+    }
+    t->adam_t = 0;
+  }
+  ICEM_CUDA(cudaStreamSynchronize(t->stream));
+  ICEM_API_END
+}
+
+int icem_mlp_trainer_get_weights(icem_mlp_trainer_t* h, float* const* weights, float* const* biases) {
+  ICEM_API_BEGIN
+  MlpTrainer* t = reinterpret_cast<MlpTrainer*>(h);
+  if (!t || !weights || !biases) throw InvalidArg("null argument");
+  ICEM_CUDA(cudaSetDevice(t->device));
+  for (int l = 0; l < 3; ++l) {
+    if (!weights[l] || !biases[l]) throw InvalidArg("null layer parameters");
+    ICEM_CUDA(cudaMemcpyAsync(weights[l], t->par[2 * l].p, t->par_n[2 * l] * sizeof(float), cudaMemcpyDeviceToHost, t->stream));
+    ICEM_CUDA(cudaMemcpyAsync(biases[l], t->par[2 * l + 1].p, t->par_n[2 * l + 1] * sizeof(float), cudaMemcpyDeviceToHost, t->stream));
+  }
+  ICEM_CUDA(cudaStreamSynchronize(t->stream));
+  ICEM_API_END
+}
+
+int icem_mlp_trainer_set_data(icem_mlp_trainer_t* h, int64_t n, const float* inputs, const float* targets) {
+  ICEM_API_BEGIN
+  MlpTrainer* t = reinterpret_cast<MlpTrainer*>(h);
+  if (!t || !inputs || !targets) throw InvalidArg("null argument");
+  if (n < 1 || n > 0x7fffffffLL) throw InvalidArg("number of transitions out of range");
+  ICEM_CUDA(cudaSetDevice(t->device));
+  t->x.reserve((size_t)n * t->in);
+  t->t.reserve((size_t)n * t->out);
+  ICEM_CUDA(cudaMemcpyAsync(t->x.p, inputs, (size_t)n * t->in * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+  ICEM_CUDA(cudaMemcpyAsync(t->t.p, targets, (size_t)n * t->out * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+  ICEM_CUDA(cudaStreamSynchronize(t->stream));
+  t->n_rows = (size_t)n;
+  ICEM_API_END
+}
+
+int icem_mlp_trainer_fit(icem_mlp_trainer_t* h, int32_t n_steps, int32_t batch, const int32_t* indices, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, float* losses_out) {
+  ICEM_API_BEGIN
+  MlpTrainer* t = reinterpret_cast<MlpTrainer*>(h);
+  if (!t || !indices) throw InvalidArg("null argument");
+  if (t->n_rows == 0) throw StateError("icem_mlp_trainer_set_data() needs to be called before");
+  if (n_steps < 1 || batch < 1) throw InvalidArg("n_steps and batch must be positive");
+  if (!(lr > 0.f) || !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) || !(eps > 0.f))
+    throw InvalidArg("Adam hyper-parameters out of range");
+  const size_t total = (size_t)n_steps * batch;
+  for (size_t i = 0; i < total; ++i)
+    if (indices[i] < 0 || (size_t)indices[i] >= t->n_rows) throw InvalidArg("minibatch index outside the data set");
+  ICEM_CUDA(cudaSetDevice(t->device));
+  trainer_reserve_batch(t, batch);
+  t->idx.reserve(total);
+  t->losses.reserve((size_t)n_steps);
+  ICEM_CUDA(cudaMemcpyAsync(t->idx.p, indices, total * sizeof(int32_t), cudaMemcpyHostToDevice, t->stream));
+  for (int s = 0; s < n_steps; ++s)
+    trainer_step(t, t->idx.p + (size_t)s * batch, batch, lr, beta1, beta2, eps, weight_decay, t->losses.p + s);
+  if (losses_out)
+    ICEM_CUDA(cudaMemcpyAsync(losses_out, t->losses.p, (size_t)n_steps * sizeof(float), cudaMemcpyDeviceToHost, t->stream));
+  ICEM_CUDA(cudaStreamSynchronize(t->stream));
+  ICEM_API_END
+}
+
+int icem_mlp_trainer_predict(icem_mlp_trainer_t* h, int32_t n, const float* inputs, float* outputs) {
+  ICEM_API_BEGIN
+  MlpTrainer* t = reinterpret_cast<MlpTrainer*>(h);
+  if (!t || !inputs || !outputs) throw InvalidArg("null argument");
+  if (n < 1) throw InvalidArg("n must be positive");
+  ICEM_CUDA(cudaSetDevice(t->device));
+  trainer_reserve_batch(t, n);
+  ICEM_CUDA(cudaMemcpyAsync(t->xb.p, inputs, (size_t)n * t->in * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+  train_gemm<false, true, kTrEpBiasTanh>(t, n, t->H, t->in, t->xb.p, t->in, t->par[0].p, t->in, t->a1.p, t->H, t->par[1].p, nullptr, 0);
+  train_gemm<false, true, kTrEpBiasTanh>(t, n, t->H, t->H, t->a1.p, t->H, t->par[2].p, t->H, t->a2.p, t->H, t->par[3].p, nullptr, 0);
+  train_gemm<false, true, kTrEpBias>(t, n, t->out, t->H, t->a2.p, t->H, t->par[4].p, t->H, t->y.p, t->out, t->par[5].p, nullptr, 0);
+  ICEM_CUDA(cudaMemcpyAsync(outputs, t->y.p, (size_t)n * t->out * sizeof(float), cudaMemcpyDeviceToHost, t->stream));
+  ICEM_CUDA(cudaStreamSynchronize(t->stream));
   ICEM_API_END
 }
 

@@ -71,11 +71,42 @@ class CudaMlpModel(CudaDenseTanhModel):
     obs' = obs + W3 tanh(W2 tanh(W1 [obs, act] + b1) + b2) + b3.  The reference ships no learned model
     (icem/models/__init__.py:5-8); this is the hook `forward_model_from_string` would resolve for one."""
 
-    def __init__(self, *, env, weights, biases, **kwargs):
+    def __init__(self, *, env, weights=None, biases=None, hidden=256, train_params=None, init_seed=0, device=0,
+                 **kwargs):
         _FMBase.__init__(self, env=env, **kwargs)
+        if weights is None:       # untrained model: random initialisation, to be fitted by train()
+            from .workloads import mlp_model_weights
+            obs_dim, act_dim = env.observation_space.shape[0], env.action_space.shape[0]
+            weights, biases = mlp_model_weights(obs_dim, act_dim, hidden, init_seed)
         self.weights = [np.asarray(w, np.float32) for w in weights]
         self.biases = [np.asarray(b, np.float32) for b in biases]
         self.is_trained = True
+        # forward_model.train(rollout_buffer) (icem/main.py:209-210): Adam on the device, see trainer.py
+        self.train_params = dict(epochs=20, batch_size=256, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                                 seed=0)
+        self.train_params.update(train_params or {})
+        self.device = device
+        self.version = 0            # bumped by train(); the controller re-uploads the weights when it changed
+        self.train_losses = None
+        self._trainer = None
+
+    def train(self, buffer):
+        """Fit the model to every transition of `buffer` (the reference passes its whole RolloutBuffer each training
+        iteration, main.py:202-210) and keep the Adam moments across calls."""
+        from .trainer import MlpTrainer, epoch_indices, transitions_from_buffer
+        x, t = transitions_from_buffer(buffer)
+        tp = self.train_params
+        if self._trainer is None:
+            self._trainer = MlpTrainer(self.weights[0].shape[1], self.weights[0].shape[0], self.weights[2].shape[0],
+                                       device=self.device)
+            self._trainer.set_weights(self.weights, self.biases)
+        self._trainer.set_data(x, t)
+        idx = epoch_indices(x.shape[0], int(tp["batch_size"]), int(tp["epochs"]), int(tp["seed"]) + self.version)
+        self.train_losses = self._trainer.fit(idx, lr=tp["lr"], betas=tp["betas"], eps=tp["eps"],
+                                              weight_decay=tp["weight_decay"])
+        self.weights, self.biases = self._trainer.get_weights()
+        self.version += 1
+        return self.train_losses
 
     def cuda_spec(self):
         return dict(dynamics="mlp", dense=None, mlp=(self.weights, self.biases), obs_dim=self.weights[-1].shape[0])

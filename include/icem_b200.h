@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define ICEM_ABI_VERSION 7
+#define ICEM_ABI_VERSION 8
 
 /* status codes */
 enum { ICEM_OK = 0, ICEM_ERR_INVALID = 1, ICEM_ERR_CUDA = 2, ICEM_ERR_STATE = 3, ICEM_ERR_UNSUPPORTED = 4,
@@ -270,6 +270,29 @@ int icem_op_topk(icem_planner_t* p, int32_t n, const float* costs, int32_t k, in
 #define ICEM_UNIQUE_ID_BYTES 128
 int icem_comm_get_unique_id(char id_out[ICEM_UNIQUE_ID_BYTES]);
 int icem_comm_init(icem_planner_t* p, const char id[ICEM_UNIQUE_ID_BYTES]);
+
+/* ---- trainer of the dense MLP forward model ------------------------------------------------------------------ */
+/* Replaces the hook `forward_model.train(rollout_buffer)` (icem/main.py:209-210) for the MLP model the tensor-core
+ * rollout consumes: next_obs = obs + W3 tanh(W2 tanh(W1 [obs, act] + b1) + b2) + b3, fitted to transitions
+ * (inputs[n][in] = [obs, act], targets[n][out] = next_obs - obs) by minibatch Adam on the mean squared error, fp32,
+ * on the device.  The reference ships no trainable model (icem/models/__init__.py:5-8), so the semantics are those of
+ * torch.nn.MSELoss (mean) + torch.optim.Adam, which is also the oracle (oracle/mlp_train_torch.py).
+ * weights[l] is row-major [out_l][in_l] (torch.nn.Linear layout), l = 0..2; the handle owns device copies. */
+typedef struct icem_mlp_trainer icem_mlp_trainer_t;
+int icem_mlp_trainer_create(int32_t device, int32_t in_dim, int32_t hidden, int32_t out_dim, icem_mlp_trainer_t** out);
+int icem_mlp_trainer_destroy(icem_mlp_trainer_t* t);
+/* reset_optimizer != 0 also zeroes the Adam moments and the step count */
+int icem_mlp_trainer_set_weights(icem_mlp_trainer_t* t, const float* const* weights, const float* const* biases,
+                                 int32_t reset_optimizer);
+int icem_mlp_trainer_get_weights(icem_mlp_trainer_t* t, float* const* weights, float* const* biases);
+/* the whole data set goes to the device once (the reference keeps every rollout of a run in its RolloutBuffer) */
+int icem_mlp_trainer_set_data(icem_mlp_trainer_t* t, int64_t n, const float* inputs, const float* targets);
+/* n_steps Adam steps; step s trains on rows indices[s * batch .. (s + 1) * batch) of the data set;
+ * losses_out[n_steps] (may be NULL) = each step's minibatch loss BEFORE its update */
+int icem_mlp_trainer_fit(icem_mlp_trainer_t* t, int32_t n_steps, int32_t batch, const int32_t* indices, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, float* losses_out);
+/* outputs[n][out] = the network's delta prediction for inputs[n][in] (fp32 forward pass of the trainer) */
+int icem_mlp_trainer_predict(icem_mlp_trainer_t* t, int32_t n, const float* inputs, float* outputs);
 
 /* ---- bench helpers ------------------------------------------------------------------------------------- */
 /* Run `steps` device-resident closed-loop plan steps (plan_device + advance_state_device) after `warmup`,

@@ -88,3 +88,31 @@ def test_importing_the_package_does_not_shadow_the_reference():
             "bad = [m for m in sys.modules if m.split('.')[0] in ('environments', 'controllers', 'misc', 'models')]\n"
             "assert not bad, bad\n" % ROOT)
     subprocess.run([sys.executable, "-c", code], check=True)
+
+
+def test_trainer_minibatch_schedule_and_transition_extraction():
+    """Host side of forward_model.train(rollout_buffer) (icem/main.py:209-210): minibatch rows and the (input, target)
+    layout, no device involved."""
+    from icem_b200 import api
+    from icem_b200.trainer import epoch_indices, transitions_from_buffer
+    idx = epoch_indices(1000, 256, 3, seed=4)
+    assert idx.shape == (9, 256) and idx.dtype == np.int32
+    for e in range(3):                                 # inside an epoch no row repeats
+        assert np.unique(idx[3 * e:3 * e + 3]).size == 768
+    np.testing.assert_array_equal(idx, epoch_indices(1000, 256, 3, seed=4))
+    assert not np.array_equal(idx, epoch_indices(1000, 256, 3, seed=5))
+    small = epoch_indices(10, 64, 2, seed=0)           # fewer rows than a batch: drawn with replacement
+    assert small.shape == (2, 64) and small.min() >= 0 and small.max() < 10
+    full = epoch_indices(10, 4, 1, seed=0, drop_last=False)
+    assert full.shape == (3, 4) and set(full.ravel().tolist()) == set(range(10))
+    rs = np.random.RandomState(0)
+    rollouts = [api.EliteRollout(observations=rs.randn(5, 3), next_observations=rs.randn(5, 3), actions=rs.randn(5, 2),
+                                 rewards=np.zeros(5)) for _ in range(4)]
+    x, t = transitions_from_buffer(api.EliteBuffer(rollouts))
+    assert x.shape == (20, 5) and t.shape == (20, 3)
+    np.testing.assert_array_equal(x[5:10, :3], rollouts[1]["observations"])
+    np.testing.assert_array_equal(x[5:10, 3:], rollouts[1]["actions"])
+    np.testing.assert_array_equal(t[5:10], rollouts[1]["next_observations"] - rollouts[1]["observations"])
+    import pytest
+    with pytest.raises(ValueError):
+        transitions_from_buffer(api.EliteBuffer([]))
