@@ -106,7 +106,27 @@ class CudaMlpModel(CudaDenseTanhModel):
                                               weight_decay=tp["weight_decay"])
         self.weights, self.biases = self._trainer.get_weights()
         self.version += 1
+        k = max(1, len(self.train_losses) // 10)
+        print(f"CudaMlpModel.train: {x.shape[0]} transitions, {len(self.train_losses)} Adam steps on the device, "
+              f"loss {float(np.mean(self.train_losses[:k])):.3e} -> {float(np.mean(self.train_losses[-k:])):.3e}")
         return self.train_losses
+
+    # CheckpointManager.store_forward_model / load_forward_model (icem/misc/initialization.py:146-162)
+    def save(self, path):
+        np.savez(path if str(path).endswith(".npz") else str(path) + ".npz", version=self.version,
+                 **{f"w{l}": w for l, w in enumerate(self.weights)}, **{f"b{l}": b for l, b in enumerate(self.biases)})
+
+    def load(self, path):
+        import os
+        f = path if str(path).endswith(".npz") else str(path) + ".npz"
+        if not os.path.exists(f):
+            raise FileNotFoundError(f)
+        d = np.load(f)
+        self.weights = [np.asarray(d[f"w{l}"], np.float32) for l in range(3)]
+        self.biases = [np.asarray(d[f"b{l}"], np.float32) for l in range(3)]
+        self.version = int(d["version"]) + 1          # the controller re-uploads
+        if self._trainer is not None:
+            self._trainer.set_weights(self.weights, self.biases)
 
     def cuda_spec(self):
         return dict(dynamics="mlp", dense=None, mlp=(self.weights, self.biases), obs_dim=self.weights[-1].shape[0])

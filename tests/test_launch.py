@@ -180,3 +180,32 @@ def test_elite_samples_are_the_reference_rolloutbuffer_on_the_gpu(tmp_path):
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
     assert "reference RolloutBuffer OK" in res.stdout
+
+
+@pytest.mark.gpu
+def test_unchanged_main_trains_the_mlp_model_on_the_gpu(tmp_path):
+    """The reference's model-based loop (icem/main.py:193-210: collect rollouts with the controller, then
+    `forward_model.train(rollout_buffer)`) with the learned model on the device: CudaMlpModel starts from a random
+    initialisation, MpcICemB200 plans through it on the tensor cores, the REAL RolloutBuffer of the reference is handed
+    to train(), the Adam steps run on the GPU, the next iteration plans with the trained weights, and the checkpoint
+    holds the model."""
+    path = _settings(tmp_path, controller="mpc-icem-b200", forward_model="CudaMlpModel",
+                     forward_model_params={"hidden": 64, "train_params": {"epochs": 30, "batch_size": 32, "lr": 2e-3}},
+                     training_iterations=3, append_data=True)
+    cfg = json.load(open(path))
+    cfg["controller_params"]["num_simulated_trajectories"] = 128
+    cfg["controller_params"]["horizon"] = 12
+    cfg["controller_params"]["action_sampler_params"]["elites_size"] = 10
+    cfg["rollout_params"]["task_horizon"] = 40
+    json.dump(cfg, open(path, "w"))
+    res = subprocess.run([sys.executable, "-m", "icem_b200.launch", path, "--reference", ref_loader.REFERENCE_ROOT,
+                          "--shims", os.path.join(ROOT, "oracle", "shims")], cwd=str(tmp_path), capture_output=True,
+                         text=True, timeout=900, env=dict(os.environ, PYTHONPATH=ROOT))
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    lines = [l.strip("' ") for l in res.stdout.splitlines() if "CudaMlpModel.train:" in l]
+    assert len(lines) == 3, res.stdout[-3000:]
+    assert "40 transitions" in lines[0] and "80 transitions" in lines[1] and "120 transitions" in lines[2]
+    first, last = (float(lines[0].split("loss ")[1].split(" -> ")[0]), float(lines[-1].split(" -> ")[1]))
+    assert last < 0.5 * first, lines
+    ck = tmp_path / "results" / "checkpoints_latest"
+    assert ck.exists() and any(f.name.startswith("forward_model") for f in ck.iterdir())
