@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("ICEM_B200_LIB") or os.path.join(os.path.dirname(os.pa
 ICEM_ABI_VERSION = 8
 INTEGRATOR = {"euler": 0, "rk4": 1}
 DYN = {"dense_tanh": 0, "halfcheetah": 1, "humanoid_standup": 2, "mlp": 3, "articulated": 4}
-COST = {"halfcheetah": 0, "humanoid_standup": 1, "locomotion": 2}
+COST = {"halfcheetah": 0, "humanoid_standup": 1, "locomotion": 2, "reacher": 3}
 REDUCE = {"sum": 0, "best": 1, "final": 2}
 PLANNER = {"icem": 0, "cem_std": 1, "random": 2}
 UNIQUE_ID_BYTES = 128
@@ -32,7 +32,7 @@ class IcemConfig(C.Structure):
         ("fraction_elites_reused", C.c_double), ("noise_beta", C.c_double),
         ("cost_dt", C.c_double), ("cost_ctrl_weight", C.c_double), ("cost_unhealthy_weight", C.c_double),
         ("cost_z_lo", C.c_double), ("cost_z_hi", C.c_double), ("cost_state_bound", C.c_double),
-        ("cost_forward_weight", C.c_double),
+        ("cost_forward_weight", C.c_double), ("cost_reach", C.c_double * 4),
         ("seed", C.c_uint64),
         ("action_low", C.POINTER(C.c_float)), ("action_high", C.POINTER(C.c_float)),
     ]
@@ -69,6 +69,8 @@ _H = C.c_void_p
 SIGNATURES = {
     "icem_last_error": (C.c_char_p, []),
     "icem_abi_version": (C.c_int, []),
+    "icem_config_sizeof": (C.c_int, []),
+    "icem_articulated_model_sizeof": (C.c_int, []),
     "icem_kernel_launch_count": (C.c_uint64, []),
     "icem_create": (C.c_int, [C.POINTER(IcemConfig), C.POINTER(_H)]),
     "icem_destroy": (C.c_int, [_H]),
@@ -134,6 +136,10 @@ def load():
             fn.argtypes = args
         if lib.icem_abi_version() != ICEM_ABI_VERSION:
             raise ImportError("libicem_b200.so ABI version mismatch; rebuild")
+        if (lib.icem_config_sizeof() != C.sizeof(IcemConfig)
+                or lib.icem_articulated_model_sizeof() != C.sizeof(IcemArticulatedModel)):
+            raise ImportError("libicem_b200.so was built from another include/icem_b200.h (struct sizes differ); "
+                              "run `python -m icem_b200.build`")
         _lib = lib
     return _lib
 

@@ -270,7 +270,13 @@ class MpcICemB200(*_Bases):
         if self._elite_cache is None:
             acts, costs, _ = self._planner.elites()
             pad = int(getattr(self.env, "obs_pad", 0))     # observation entries the device model does not carry
-            obs = self._planner.rollout_observations(self._last_start, acts, self._obs_dim - pad)
+            if hasattr(self.env, "observation_from_state"):
+                # the env's observation is a function of the device state, not a slice of it (Reacher: cos / sin /
+                # fingertip - target, environments/mujoco.py:346-368)
+                states = self._planner.rollout_observations(self._last_start, acts, self._last_start.shape[-1])
+                obs = self.env.observation_from_state(states)
+            else:
+                obs = self._planner.rollout_observations(self._last_start, acts, self._obs_dim - pad)
             if pad:
                 obs = np.concatenate([obs, np.zeros(obs.shape[:-1] + (pad,))], axis=-1)
             rollouts = []

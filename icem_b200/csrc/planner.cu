@@ -270,6 +270,8 @@ static CostConst cost_const(icem_planner* p) {
     cc.z_hi = (float)p->cfg.cost_z_hi;
     cc.state_bound = (float)p->cfg.cost_state_bound;
     cc.z_strict = p->cfg.cost_z_strict;
+  } else if (p->cfg.cost == ICEM_COST_REACHER) {
+    for (int i = 0; i < 4; ++i) cc.reach[i] = (float)p->cfg.cost_reach[i];
   } else {
     cc.idx_a = 2;   // environments/mujoco.py:267 root z
     cc.idx_b = 0;
@@ -875,6 +877,8 @@ extern "C" {
 
 const char* icem_last_error(void) { return icem::g_last_error.c_str(); }
 int icem_abi_version(void) { return ICEM_ABI_VERSION; }
+int icem_config_sizeof(void) { return (int)sizeof(icem_config_t); }
+int icem_articulated_model_sizeof(void) { return (int)sizeof(icem_articulated_model_t); }
 uint64_t icem_kernel_launch_count(void) { return icem::g_launches.load(); }
 
 int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
@@ -912,6 +916,9 @@ int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
   if (cfg->cost == ICEM_COST_LOCOMOTION) {
     if (!(cfg->cost_dt > 0)) throw InvalidArg("cost_dt must be positive for ICEM_COST_LOCOMOTION");
     if (cfg->dynamics == ICEM_DYN_MLP) throw Unsupported("the locomotion cost is not available for the MLP rollout");
+  } else if (cfg->cost == ICEM_COST_REACHER) {
+    // the distance is formed from the arm's joint angles: only the articulated ground-truth model carries them
+    if (cfg->dynamics != ICEM_DYN_ARTICULATED) throw Unsupported("the reacher cost needs ICEM_DYN_ARTICULATED");
   } else if (cfg->cost != ICEM_COST_HALFCHEETAH && cfg->cost != ICEM_COST_HUMANOID_STANDUP) {
     throw Unsupported("unknown cost id");
   }

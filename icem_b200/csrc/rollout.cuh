@@ -47,7 +47,20 @@ struct CostConst {
   int z_strict;         // Hopper: z_lo < z < z_hi; Ant: z_lo <= z <= z_hi
   int vel_index;        // >= 0: x velocity = obs[vel_index] (Humanoid, mujoco.py:333; inv_dt is 0 then); -1: finite difference
   float w_fwd;          // weight of the velocity term
+  float reach[4];       // ICEM_COST_REACHER: link lengths l1, l2 and the target body's rest position (x, y)
 };
+
+// environments/mujoco.py:366-368 (Reacher): |fingertip - target| from the state (q0, q1 arm hinges about z; q2, q3 the
+// target's slide joints): fingertip = l1 (cos q0, sin q0) + l2 (cos(q0 + q1), sin(q0 + q1)), target = rest + (q2, q3);
+// both bodies sit at the same height, so the z difference gym's observation carries is zero.
+__device__ __forceinline__ float reacher_distance(const CostConst& cc, float q0, float q1, float q2, float q3) {
+  float s0, c0, s01, c01;
+  sincosf(q0, &s0, &c0);
+  sincosf(q0 + q1, &s01, &c01);
+  const float dx = fmaf(cc.reach[0], c0, cc.reach[1] * c01) - (cc.reach[2] + q2);
+  const float dy = fmaf(cc.reach[0], s0, cc.reach[1] * s01) - (cc.reach[3] + q3);
+  return sqrtf(fmaf(dx, dx, dy * dy));
+}
 
 struct RolloutArgs {
   int n_fresh_local;        // fresh rows this rank samples
@@ -87,6 +100,7 @@ __device__ __forceinline__ float step_cost(const CostConst& cc, const Dyn& dyn, 
     const float vel = cc.vel_index >= 0 ? cc.w_fwd * dyn.obs(cc.vel_index) : 0.f;
     return (healthy ? 0.f : cc.w_unhealthy) + cc.w_ctrl * a2 - vel;
   }
+  if (cc.kind == 3) return reacher_distance(cc, dyn.obs(0), dyn.obs(1), dyn.obs(2), dyn.obs(3));
   if (cc.kind == 0) {   // environments/mujoco.py:67-99
     const float ang = dyn.obs(cc.idx_a), vel = dyn.obs(cc.idx_b);
     float c = 0.f;

@@ -160,6 +160,7 @@ _ARTICULATED = {
     "Hopper": dict(dynamics="articulated", robot="hopper", nq=6, nv=6, act_dim=3, bound=1.0),
     "Ant": dict(dynamics="articulated", robot="ant", nq=15, nv=14, act_dim=8, bound=1.0),
     "Humanoid": dict(dynamics="articulated", robot="humanoid", nq=24, nv=23, act_dim=17, bound=0.4),
+    "Reacher": dict(dynamics="articulated", robot="reacher", nq=4, nv=4, act_dim=2, bound=1.0),
 }
 
 
@@ -441,7 +442,72 @@ class Humanoid(_LocomotionEnv):
         return self._obs()
 
 
+def reacher_cost_fn(observation, action, next_obs):
+    """environments/mujoco.py:366-368: |fingertip - target| = norm of the last three observation entries."""
+    return np.linalg.norm(np.asarray(observation)[..., -3:], axis=-1)
+
+
+class Reacher(_DeviceSimEnv):
+    """Stand-in for environments/mujoco.py:346-368 (gym Reacher-v2): 11-wide observation
+    [cos q0, cos q1, sin q0, sin q1, target x, target y, qvel0, qvel1, fingertip - target (3)]; state = [time, qpos(4),
+    qvel(4)] with qpos[2:4] the target's slide joints.  The device model carries the state; `observation_from_state`
+    rebuilds gym's layout from it (cost on the device: ICEM_COST_REACHER from the same forward kinematics)."""
+    kind = "Reacher"
+    dt = 0.02
+    reach = (0.1, 0.11, 0.0, 0.0)      # link lengths, target world position at q2 = q3 = 0 (robots.reacher)
+
+    def __init__(self, *, name="Reacher", device=0, frame_skip=None, **kwargs):
+        if frame_skip not in (None, 2):
+            raise NotImplementedError("the device Reacher model is compiled with gym's frame_skip = 2")
+        self.observation_space = Box(-np.inf * np.ones(11), np.inf * np.ones(11))
+        super().__init__(name=name, device=device, **kwargs)
+        self.store_init_arguments(locals())
+
+    def _qpos0(self):
+        return np.zeros(4)
+
+    def cuda_cost_spec(self):
+        return "reacher", False, dict(reach=self.reach)
+
+    def cost_fn(self, observation, action, next_obs):
+        return reacher_cost_fn(observation, action, next_obs)
+
+    @classmethod
+    def observation_from_state(cls, state):
+        """[..., 8] device states (qpos ++ qvel) -> [..., 11] observations in gym's layout (reacher.py::_get_obs)."""
+        st = np.asarray(state, np.float64)
+        q0, q1, tx, ty = st[..., 0], st[..., 1], st[..., 2], st[..., 3]
+        l1, l2, ox, oy = cls.reach
+        fx = l1 * np.cos(q0) + l2 * np.cos(q0 + q1)
+        fy = l1 * np.sin(q0) + l2 * np.sin(q0 + q1)
+        return np.stack([np.cos(q0), np.cos(q1), np.sin(q0), np.sin(q1), tx, ty, st[..., 4], st[..., 5],
+                         fx - (ox + tx), fy - (oy + ty), np.zeros_like(q0)], axis=-1)
+
+    def _obs(self):
+        return self.observation_from_state(self._state)
+
+    def set_state_from_observation(self, observation):      # environments/mujoco.py:359-364
+        o = np.asarray(observation, np.float64)
+        self._state = np.array([np.arctan2(o[2], o[0]), np.arctan2(o[3], o[1]), o[4], o[5], o[6], o[7], 0.0, 0.0])
+
+    def reset(self):
+        # gym reacher.py::reset_model: arm angles U(-0.1, 0.1), goal uniform in the disc of radius 0.2, arm velocities
+        # U(-0.005, 0.005), target at rest
+        q = self._rs.uniform(-0.1, 0.1, 4)
+        while True:
+            goal = self._rs.uniform(-0.2, 0.2, 2)
+            if np.linalg.norm(goal) < 0.2:
+                break
+        q[2:] = goal
+        qd = np.concatenate([self._rs.uniform(-0.005, 0.005, 2), np.zeros(2)])
+        self._state = np.concatenate([q, qd])
+        self._t = 0.0
+        return self._obs()
+
+
 def make_env(kind, device=0, **kwargs):
+    if kind == "Reacher":
+        return Reacher(name=kind, device=device, **kwargs)
     if kind == "Humanoid":
         return Humanoid(name=kind, device=device, **kwargs)
     if kind == "Hopper":

@@ -77,6 +77,7 @@ def register(override_mpc_icem=False, standin_envs=True):
         mod.Hopper = envs.Hopper
         mod.Ant = envs.Ant
         mod.Humanoid = envs.Humanoid
+        mod.Reacher = envs.Reacher
         mod.__doc__ = "device-simulated stand-ins registered by icem_b200.launch"
         sys.modules["environments.mujoco"] = mod
 

@@ -83,7 +83,8 @@ def _cost_fields(cp):
                 cost_z_lo=float(max(cp.get("z_lo", -inf), -inf)), cost_z_hi=float(min(cp.get("z_hi", inf), inf)),
                 cost_state_bound=float(cp.get("state_bound", 0.0)),
                 cost_velocity_index1=int(cp.get("velocity_index", -1)) + 1, cost_reserved=0,
-                cost_forward_weight=float(cp.get("forward_weight", 1.0)))
+                cost_forward_weight=float(cp.get("forward_weight", 1.0)),
+                cost_reach=(C.c_double * 4)(*[float(v) for v in cp.get("reach", (0.1, 0.11, 0.0, 0.0))]))
 
 
 class Planner:

@@ -88,6 +88,7 @@ class RobotDescription:
     friction_viscous: float = 150.0          # N s/m below the Coulomb cap
     limit_timeconst: float = 0.02            # spring-damper time constant of joint limits (MuJoCo solreflimit default)
     root_qpos0: Optional[Tuple[float, ...]] = None   # initial coordinates of the root joint(s) (default zeros / identity)
+    contacts: bool = True                    # False: no geom collides (MuJoCo contype = conaffinity = 0, reacher.xml)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -263,7 +264,34 @@ ROBOTS = {"halfcheetah": half_cheetah, "humanoid_standup": humanoid_standup, "ho
           "humanoid": humanoid}
 
 
+def reacher() -> RobotDescription:
+    """gym `reacher.xml` (Reacher-v2: timestep 0.01, frame_skip 2): a planar two-link arm on hinges about z (default
+    joint armature 1, damping 1; joint0 unlimited, joint1 in [-3, 3] rad; motors gear 200, ctrl in [-1, 1]), the
+    fingertip 0.11 beyond the second joint, and the target as its own body on two undriven slide joints (x, y) -- it
+    keeps whatever position the start state gives it.  No geom collides (contype = conaffinity = 0)."""
+    j = dict(armature=1.0, damping=1.0)
+    bodies = [
+        Body("body0", -1, (0, 0, 0.01), joints=[Joint("joint0", "hinge", axis=(0, 0, 1), **j)],
+             geoms=[Geom("link0", "capsule", 0.01, fromto=(0, 0, 0, 0.1, 0, 0))]),
+        Body("body1", 0, (0.1, 0, 0), joints=[Joint("joint1", "hinge", axis=(0, 0, 1), range=(-3.0, 3.0), **j)],
+             geoms=[Geom("link1", "capsule", 0.01, fromto=(0, 0, 0, 0.1, 0, 0)),
+                    Geom("fingertip", "sphere", 0.01, pos=(0.11, 0, 0))]),
+        # reacher.xml places the body at (.1, -.1, .01) and gives the slides ref = .1 / -.1: the joint coordinates ARE the
+        # target's world x, y.  The slides carry no force (no damping, no actuator, gravity is along z); armature 1
+        # instead of the XML's 0 keeps the 3-milligram body out of the fp32 factorisation -- its acceleration is 0 either way.
+        Body("target", -1, (0.0, 0.0, 0.01),
+             joints=[Joint("target_x", "slide", axis=(1, 0, 0), range=(-0.27, 0.27), armature=1.0),
+                     Joint("target_y", "slide", axis=(0, 1, 0), range=(-0.27, 0.27), armature=1.0)],
+             geoms=[Geom("target", "sphere", 0.009)]),
+    ]
+    return RobotDescription("reacher", bodies, [Actuator("joint0", 200.0), Actuator("joint1", 200.0)], timestep=0.01,
+                            frame_skip=2, ctrl_limit=1.0, contacts=False)
+
+
 # ---------------------------------------------------------------------------------------------------------------
+ROBOTS["reacher"] = reacher
+
+
 def _capsule_mass_inertia(radius, length, density):
     """Solid capsule along z about its centre: (mass, Ixx(=Iyy), Izz)."""
     r, L = radius, length
@@ -424,7 +452,8 @@ def compile_model(desc: RobotDescription) -> CompiledModel:
     for i, b in enumerate(desc.bodies):
         for g in b.geoms:
             for e in g.endpoints():
-                cb.append(i); cp.append(e); cr.append(g.size)
+                if desc.contacts:
+                    cb.append(i); cp.append(e); cr.append(g.size)
     nc = len(cb)
     assert nc <= MAX_CONTACTS, nc
 
@@ -447,7 +476,7 @@ def compile_model(desc: RobotDescription) -> CompiledModel:
         dof_lo=np.array([r["joint"].range[0] if r["joint"].range is not None else 0.0 for r in rows]),
         dof_hi=np.array([r["joint"].range[1] if r["joint"].range is not None else 0.0 for r in rows]),
         dof_klim=np.zeros(nv), dof_blim=np.zeros(nv), dof_gear=gear, dof_act=act,
-        con_body=np.array(cb, np.int64), con_pos=np.array(cp, float), con_radius=np.array(cr, float),
+        con_body=np.array(cb, np.int64), con_pos=np.array(cp, float).reshape(-1, 3), con_radius=np.array(cr, float),
         qpos0=np.array(qpos0, float))
     if desc.root_qpos0 is not None:
         m.qpos0[:len(desc.root_qpos0)] = desc.root_qpos0

@@ -42,11 +42,15 @@ enum {
 enum {
   ICEM_COST_HALFCHEETAH = 0,     /* environments/mujoco.py:67-99  */
   ICEM_COST_HUMANOID_STANDUP = 1,/* environments/mujoco.py:259-277 */
-  ICEM_COST_LOCOMOTION = 2       /* Ant (environments/mujoco.py:153-176), Hopper (:196-231), Humanoid (:314-343):
+  ICEM_COST_LOCOMOTION = 2,      /* Ant (environments/mujoco.py:153-176), Hopper (:196-231), Humanoid (:314-343):
                                     -w_fwd * x_velocity + w_unhealthy * unhealthy(obs) + w_ctrl * |a|^2 with
                                     x_velocity = (next_obs[0] - obs[0]) / dt (Ant, Hopper; reads next_obs, so all h
                                     steps are simulated) or obs[cost_velocity_index] (Humanoid); parameters in
                                     icem_config_t.cost_* */
+  ICEM_COST_REACHER = 3          /* Reacher (environments/mujoco.py:346-368): |fingertip - target|, the last three
+                                    entries of gym's observation.  On the device the observation is the state
+                                    (q0, q1 = arm hinges, q2, q3 = target slides), so the distance is formed from the
+                                    planar forward kinematics with the constants in icem_config_t.cost_reach */
 };
 
 /* action sampler / planner family */
@@ -109,6 +113,8 @@ typedef struct icem_config {
   double cost_z_lo, cost_z_hi;    /* LOCOMOTION: _healthy_z_range */
   double cost_state_bound;        /* LOCOMOTION: Hopper |states[..., 2:]| < bound (_healthy_state_range); <= 0: none */
   double cost_forward_weight;     /* LOCOMOTION: weight of the velocity term (Humanoid _forward_reward_weight 1.25); 0 = 1 */
+  double cost_reach[4];           /* REACHER: link 1 length, link 2 length to the fingertip, world x, y of the target at
+                                     q2 = q3 = 0 (gym reacher.xml: 0.1, 0.11, 0, 0 -- the slides' `ref` cancels the body offset) */
   uint64_t seed;                  /* Philox key (production noise) */
   const float* action_low;        /* [d] env.action_space.low  (float32 like gym.spaces.Box) */
   const float* action_high;       /* [d] */
@@ -118,6 +124,10 @@ typedef struct icem_planner icem_planner_t;
 
 const char* icem_last_error(void);
 int icem_abi_version(void);
+/* sizeof(icem_config_t) / sizeof(icem_articulated_model_t) as the library was compiled: a binding checks its own
+ * mirror of the structs against these before the first call (a stale library would read shifted fields) */
+int icem_config_sizeof(void);
+int icem_articulated_model_sizeof(void);
 /* number of kernels of this library launched by the calling process so far (bench `gpu_launches`) */
 uint64_t icem_kernel_launch_count(void);
 

@@ -70,3 +70,22 @@ def humanoid_cost(obs, act, next_obs=None, p=HUMANOID):
     unhealthy = 1 - np.isfinite(obs).all(axis=-1) * ((lo < z) * (z < hi))
     x_velocity = obs[..., p["nq"] - 2] if p["exclude_current_positions"] else obs[..., p["nq"]]
     return -p["forward_weight"] * x_velocity + 100 * unhealthy + p["ctrl_weight"] * np.sum(np.square(act), axis=-1)
+
+
+REACHER = dict(l1=0.1, l2=0.11, target0=(0.0, 0.0))      # gym reacher.xml link lengths; target world position at q2 = q3 = 0
+
+
+def reacher_cost(obs, act=None, next_obs=None):
+    """environments/mujoco.py:366-368: |fingertip - target| = norm of the last three observation entries."""
+    return np.linalg.norm(np.asarray(obs)[..., -3:], axis=-1)
+
+
+def reacher_observation(state, p=REACHER):
+    """gym reacher.py::_get_obs from the state (qpos(4) ++ qvel(4)): [cos q0, cos q1, sin q0, sin q1, target x, y,
+    qvel0, qvel1, fingertip - target (3)] with the fingertip from the planar forward kinematics."""
+    st = np.asarray(state, np.float64)
+    q0, q1, tx, ty = st[..., 0], st[..., 1], st[..., 2], st[..., 3]
+    fx = p["l1"] * np.cos(q0) + p["l2"] * np.cos(q0 + q1)
+    fy = p["l1"] * np.sin(q0) + p["l2"] * np.sin(q0 + q1)
+    return np.stack([np.cos(q0), np.cos(q1), np.sin(q0), np.sin(q1), tx, ty, st[..., 4], st[..., 5],
+                     fx - (p["target0"][0] + tx), fy - (p["target0"][1] + ty), np.zeros_like(q0)], axis=-1)

@@ -68,9 +68,23 @@ def reference_costs():
     return rm.Hopper.cost_fn(hs, ho.copy(), ha, hn), rm.Ant.cost_fn(as_, ao.copy(), aa, an)
 
 
+def reacher_inputs():
+    rs = np.random.RandomState(9)
+    return rs.randn(50, 7, 11), rs.uniform(-1, 1, (50, 7, 2))
+
+
+def reference_reacher_costs():
+    """environments/mujoco.py:366-368, called unbound (the method reads nothing from `self`)."""
+    ref_loader.load_reference()
+    import environments.mujoco as rm
+    o, a = reacher_inputs()
+    return rm.Reacher.cost_fn(None, o.copy(), a, o)
+
+
 def main():
     h, a = reference_costs()
     hu = reference_humanoid_costs()
+    np.savez_compressed(os.path.join(OUT, "costs_reacher.npz"), reacher=reference_reacher_costs())
     np.savez_compressed(os.path.join(OUT, "costs_locomotion.npz"), hopper=h, ant=a, humanoid=hu)
     print("humanoid", hu.shape, float(np.mean(hu > 50)))
     print("hopper", h.shape, float(np.nanmean(h > 100)), "ant", a.shape, float(np.mean(a > 50)))

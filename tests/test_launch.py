@@ -94,7 +94,7 @@ def test_register_adds_every_plugin_entry():
         "assert t['mpc-random-b200'][1] == 'MpcRandomB200' and t['mpc-icem'][0] == 'icem_b200.controller'\n"
         "assert t['mpc-random'][1] == 'MpcRandomB200'\n"
         "assert {'CudaGroundTruthModel', 'CudaDenseTanhModel', 'CudaMlpModel'} <= set(models.models_dict)\n"
-        "for n in ('HalfCheetahMaybeWithPosition', 'HumanoidStandup', 'Hopper', 'Ant', 'Humanoid'):\n"
+        "for n in ('HalfCheetahMaybeWithPosition', 'HumanoidStandup', 'Hopper', 'Ant', 'Humanoid', 'Reacher'):\n"
         "    assert hasattr(m, n), n\n"
         "cls = controllers.controller_from_string('mpc-random-b200')\n"
         "from controllers.abstract_controller import ModelBasedController\n"
