@@ -24,7 +24,7 @@ python scripts/ncu_summary.py gpurun_out/r2_prof_chain_humanoid_$TAG.ncu-rep > g
 python scripts/ncu_summary.py gpurun_out/r2_prof_chain_cheetah_$TAG.ncu-rep > gpurun_out/r2_ncu_full_chain_rollout_halfcheetah_gt_n4096_$TAG.txt
 python scripts/ncu_summary.py gpurun_out/r2_prof_mlp_$TAG.ncu-rep > gpurun_out/r2_ncu_full_mlp_rollout_n65536_$TAG.txt
 rm -f gpurun_out/r2_prof_chain_cheetah_$TAG.ncu-rep gpurun_out/r2_prof_mlp_$TAG.ncu-rep
-timeout 200 compute-sanitizer --tool memcheck --print-limit 5 python scripts/sanitize.py cheetah humanoid > gpurun_out/r2_sanitize_memcheck_$TAG.log 2>&1; grep -E "ok$|ERROR SUMMARY" gpurun_out/r2_sanitize_memcheck_$TAG.log
-timeout 300 compute-sanitizer --tool synccheck --print-limit 5 python scripts/sanitize.py cheetah humanoid mlp > gpurun_out/r2_sanitize_synccheck_$TAG.log 2>&1; grep -E "ok$|ERROR SUMMARY" gpurun_out/r2_sanitize_synccheck_$TAG.log
-timeout 400 compute-sanitizer --tool racecheck --print-limit 5 python scripts/sanitize.py cheetah humanoid > gpurun_out/r2_sanitize_racecheck_$TAG.log 2>&1; grep -E "ok$|ERROR SUMMARY|RACECHECK SUMMARY" gpurun_out/r2_sanitize_racecheck_$TAG.log
+timeout 200 compute-sanitizer --tool memcheck --print-limit 5 python scripts/sanitize.py cheetah humanoid sampler trainer reacher > gpurun_out/r2_sanitize_memcheck_$TAG.log 2>&1; grep -E "ok$|ERROR SUMMARY" gpurun_out/r2_sanitize_memcheck_$TAG.log
+timeout 300 compute-sanitizer --tool synccheck --print-limit 5 python scripts/sanitize.py cheetah humanoid mlp sampler trainer reacher > gpurun_out/r2_sanitize_synccheck_$TAG.log 2>&1; grep -E "ok$|ERROR SUMMARY" gpurun_out/r2_sanitize_synccheck_$TAG.log
+timeout 400 compute-sanitizer --tool racecheck --print-limit 5 python scripts/sanitize.py cheetah humanoid sampler trainer reacher > gpurun_out/r2_sanitize_racecheck_$TAG.log 2>&1; grep -E "ok$|ERROR SUMMARY|RACECHECK SUMMARY" gpurun_out/r2_sanitize_racecheck_$TAG.log
 ls -la gpurun_out | tail -12

@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 from icem_b200 import workloads  # noqa: E402
 from icem_b200.planner import Planner, PlannerSettings  # noqa: E402
 
-which = sys.argv[1:] or ["dense", "cheetah", "humanoid", "mlp", "cemstd", "random", "ops"]
+which = sys.argv[1:] or ["dense", "cheetah", "humanoid", "mlp", "cemstd", "random", "ops", "sampler", "trainer", "reacher"]
 if "dense" in which:
     name = "dense_tanh_cheetah_n4096"
     w = workloads.get_workload(name)
@@ -65,3 +65,39 @@ if "ops" in which:
     p.op_topk(rs.randn(5000).astype(np.float32), 10)
     p.close()
     print("ops ok")
+if "sampler" in which:
+    # stand-alone sampler, production noise: the three compile-time-shaped kernels and the run-time-shaped one, several
+    # row batches per CTA
+    for h, d in ((30, 17), (30, 6), (12, 6), (20, 5)):
+        p = Planner(PlannerSettings(horizon=h, num_simulated_trajectories=64, action_low=-np.ones(d),
+                                    action_high=np.ones(d), obs_dim=17, noise_beta=1.0))
+        p.set_dense_model(0.5 * np.eye(17), 0.1 * np.ones((17, d)))
+        p.begin_rollout()
+        p.plan(np.zeros(17))
+        p.bench_op("sample", 20011, reps=1, flush_l2=False)
+        p.close()
+    print("sampler ok")
+if "trainer" in which:
+    from icem_b200.trainer import MlpTrainer, epoch_indices
+    rs = np.random.RandomState(0)
+    ws, bs = workloads.mlp_model_weights(18, 6, 64, 1)
+    tr = MlpTrainer(24, 64, 18)
+    tr.set_weights(ws, bs)
+    tr.set_data(rs.randn(700, 24), rs.randn(700, 18))
+    tr.fit(epoch_indices(700, 300, 2, 0), lr=1e-3, weight_decay=1e-3)
+    tr.predict(rs.randn(33, 24))
+    tr.close()
+    print("trainer ok")
+if "reacher" in which:
+    from icem_b200.robots import get_model
+    m = get_model("reacher")
+    p = Planner(PlannerSettings(horizon=10, num_simulated_trajectories=64, action_low=-np.ones(2), action_high=np.ones(2),
+                                dynamics="articulated", articulated_model=m, obs_offset=0, cost="reacher",
+                                cost_params=dict(reach=(0.1, 0.11, 0.0, 0.0)), obs_dim=11, opt_iterations=2))
+    p.begin_rollout()
+    st = np.array([0.3, -0.5, 0.1, -0.1, 0.0, 0.0, 0.0, 0.0])
+    for _ in range(2):
+        p.plan(st)
+    p.sim_step(st, np.array([0.5, -0.5]))
+    p.close()
+    print("reacher ok")
