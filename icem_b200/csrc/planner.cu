@@ -787,7 +787,7 @@ struct MlpTrainer {
   size_t n_rows = 0;
   DevBuf<int> idx;
   DevBuf<float> xb, tb, a1, a2, y, dy, dz2, dz1, gw[3], gb[3], loss_part, losses;
-  int cap_batch = 0, splits = 1;
+  int cap_batch = 0;
 
   ~MlpTrainer() {
     if (stream) cudaStreamDestroy(stream);
@@ -807,7 +807,6 @@ static void train_gemm(MlpTrainer* t, int M, int N, int K, const float* A, int l
 static void trainer_reserve_batch(MlpTrainer* t, int batch) {
   if (batch <= t->cap_batch) return;
   const int H = t->H;
-  t->splits = std::max(1, std::min(16, batch / 256));
   t->xb.alloc((size_t)batch * t->in); t->tb.alloc((size_t)batch * t->out);
   t->a1.alloc((size_t)batch * H); t->a2.alloc((size_t)batch * H);
   t->y.alloc((size_t)batch * t->out); t->dy.alloc((size_t)batch * t->out);
@@ -836,7 +835,8 @@ static void trainer_step(MlpTrainer* t, const int* idx, int batch, float lr, flo
   train_loss_grad_kernel<<<nblk, 256, 0, t->stream>>>(count, t->y.p, t->tb.p, t->dy.p, t->loss_part.p);
   train_loss_reduce_kernel<<<1, 256, 0, t->stream>>>(nblk, count, t->loss_part.p, loss_out);
   // backward: data gradients through the tanh layers, weight gradients split over the batch, bias gradients
-  const int S = t->splits;
+  const int S = std::max(1, std::min(16, batch / 256));     // a function of the batch alone: results do not depend
+                                                            // on what the handle ran before
   train_gemm<false, false, kTrEpTanhGrad>(t, batch, H, out, t->dy.p, out, W3, H, t->dz2.p, H, nullptr, t->a2.p, H);
   train_gemm<false, false, kTrEpTanhGrad>(t, batch, H, H, t->dz2.p, H, W2, H, t->dz1.p, H, nullptr, t->a1.p, H);
   train_gemm<true, false, kTrEpNone>(t, out, H, batch, t->dy.p, out, t->a2.p, H, t->gw[2].p, H, nullptr, nullptr, 0, S);
