@@ -261,14 +261,19 @@ struct Articulated {
           p[0] = an[0] + rp[0]; p[1] = an[1] + rp[1]; p[2] = an[2] + rp[2];
         }
       }
-      if (depth == 0) {      // root: world frame; everything downstream is relative to O = root frame origin
-        O[0] = p[0]; O[1] = p[1]; O[2] = p[2];
-        p[0] = p[1] = p[2] = 0.f;
+      // world frame; everything downstream is relative to O = the origin of the FIRST root's frame (body 0; bodies are
+      // listed parent-before-child, so body 0 is a root).  A robot may have further roots (Reacher's target body):
+      // they are placed relative to the same O below, after the warp has seen it.
+      if (b == 0) { O[0] = p[0]; O[1] = p[1]; O[2] = p[2]; }
+    }
+    __syncwarp();
+    if (depth == 0) {
+      const int b = lane;
+      p[0] -= O[0]; p[1] -= O[1]; p[2] -= O[2];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) Rb[b * kSR + i] = R[i];
+      for (int i = 0; i < 9; ++i) Rb[b * kSR + i] = R[i];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) pb[b * kSP + i] = 0.f;
-      }
+      for (int i = 0; i < 3; ++i) pb[b * kSP + i] = p[i];
     }
     __syncwarp();
 
