@@ -96,10 +96,12 @@ colored_sampler_kernel(RolloutArgs a, SamplerConst sc, int rows_per_batch,
   float* s_tile = reinterpret_cast<float*>(s_ms + ((hd + 1) & ~1)); // [2][R][stride]
   const int batch_floats = R * stride;
 
-  for (int i = tid; i < (Q + 1) * KPAD; i += kThreads) {
-    const int t = i / KPAD, k = i - t * KPAD;
-    s_c[i] = k < K ? sc.G[(size_t)t * 2 * K + k] : 0.f;
-    s_s[i] = k < K ? sc.G[(size_t)t * 2 * K + K + k] : 0.f;
+  if constexpr (!kStatic) {       // the compile-time-shaped kernels take their table rows from the kernel parameters
+    for (int i = tid; i < (Q + 1) * KPAD; i += kThreads) {
+      const int t = i / KPAD, k = i - t * KPAD;
+      s_c[i] = k < K ? sc.G[(size_t)t * 2 * K + k] : 0.f;
+      s_s[i] = k < K ? sc.G[(size_t)t * 2 * K + K + k] : 0.f;
+    }
   }
   for (int i = tid; i < hd; i += kThreads) s_ms[i] = make_float2(a.mean[i], a.std[i]);
   for (int i = tid; i < 2 * batch_floats; i += kThreads) s_tile[i] = 0.f;   // also the row padding
