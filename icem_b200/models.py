@@ -93,14 +93,10 @@ class CudaMlpModel(CudaDenseTanhModel):
     def train(self, buffer):
         """Fit the model to every transition of `buffer` (the reference passes its whole RolloutBuffer each training
         iteration, main.py:202-210) and keep the Adam moments across calls."""
-        from .trainer import MlpTrainer, epoch_indices, transitions_from_buffer
+        from .trainer import epoch_indices, transitions_from_buffer
         x, t = transitions_from_buffer(buffer)
         tp = self.train_params
-        if self._trainer is None:
-            self._trainer = MlpTrainer(self.weights[0].shape[1], self.weights[0].shape[0], self.weights[2].shape[0],
-                                       device=self.device)
-            self._trainer.set_weights(self.weights, self.biases)
-        self._trainer.set_data(x, t)
+        self._device_net().set_data(x, t)
         idx = epoch_indices(x.shape[0], int(tp["batch_size"]), int(tp["epochs"]), int(tp["seed"]) + self.version)
         self.train_losses = self._trainer.fit(idx, lr=tp["lr"], betas=tp["betas"], eps=tp["eps"],
                                               weight_decay=tp["weight_decay"])
@@ -131,14 +127,26 @@ class CudaMlpModel(CudaDenseTanhModel):
     def cuda_spec(self):
         return dict(dynamics="mlp", dense=None, mlp=(self.weights, self.biases), obs_dim=self.weights[-1].shape[0])
 
+    def __getstate__(self):          # the device handle does not travel (copy / pickle): it is re-created on demand
+        d = dict(self.__dict__)
+        d["_trainer"] = None
+        return d
+
+    def _device_net(self):
+        if self._trainer is None:
+            from .trainer import MlpTrainer
+            self._trainer = MlpTrainer(self.weights[0].shape[1], self.weights[0].shape[0], self.weights[2].shape[0],
+                                       device=self.device)
+            self._trainer.set_weights(self.weights, self.biases)
+        return self._trainer
+
     def predict(self, *, observations, states, actions):
+        """One transition (or a batch) through the fp32 network ON THE DEVICE (icem_mlp_trainer_predict); the planner
+        itself rolls the model out on the tensor cores and never calls this."""
         o = np.asarray(observations, np.float64)
         x = np.concatenate([o, np.asarray(actions, np.float64)], axis=-1)
-        for l, (w, b) in enumerate(zip(self.weights, self.biases)):
-            x = x @ w.T.astype(np.float64) + b
-            if l + 1 < len(self.weights):
-                x = np.tanh(x)
-        return o + x, states, np.zeros(o.shape[:-1] + (1,))
+        delta = self._device_net().predict(x.reshape(-1, x.shape[-1])).astype(np.float64).reshape(o.shape)
+        return o + delta, states, np.zeros(o.shape[:-1] + (1,))
 
 
 class CudaGroundTruthModel(_GTBase):
