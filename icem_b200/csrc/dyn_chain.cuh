@@ -74,6 +74,8 @@ struct ChainModel {
   // scratch layout in slots (group-shared region: slot * (32 / G) + group; lane-private region: slot * 32 + lane)
   int s_state, s_free, s_dof, s_node, s_frame, s_acc, s_jun, s_rk, s_ctrl, s_end;
   int root_free;                                 // the root carries a free joint (handled as one 6-dof joint)
+  int planar;                                    // every body moves in the x-z plane and turns about y (HalfCheetah, Hopper):
+                                                 // the PLANAR instantiation of ChainLane may run this model
   int seq_last[kChMaxLimbs];                     // position of the last node of lane g's walk
   int p_dof, p_node, p_end;
   int trunk_node[kChMaxTrunk];
@@ -238,7 +240,12 @@ __host__ __device__ __forceinline__ void ch_solve_spd6(const ArtInertia& I, cons
 
 // One lane of a group.  Ctx provides: group_sum(float (&x)[N]) (sum over the G lanes, identical in all of them)
 // and group_sync() (barrier + memory ordering among the lanes of the warp / group).
-template <class Ctx, int STRIDE>
+//
+// PLANAR = true is the same algorithm with the structural zeros of a planar robot removed: a motion / force vector
+// [w; v] keeps (w_y, v_x, v_z) -- entries 1, 3, 5 of the same arrays and record slots --, a rotation is (cos, sin) in
+// R[0], R[2], the articulated inertia keeps A_yy, B_yx, B_yz, C_xx, C_zz, C_xz (A[1], B[3], B[5], C[0], C[2], C[4]).
+// A dynamics evaluation then costs about a third of the spatial one; only models flagged ChainModel::planar may use it.
+template <class Ctx, int STRIDE, bool PLANAR = false>
 struct ChainLane {
   typedef ChRefT<STRIDE> ChRef;
   const ChainModel* M;
@@ -277,6 +284,10 @@ struct ChainLane {
                                                        float (&v)[6], float (&O)[3], const ChRef& q, const ChRef& qd,
                                                        const ChRef& ctrl, float dt) {
     const ChainModel& m = *M;
+    if constexpr (PLANAR) {
+      walk_joints_planar(node, root, trunk, R, p, v, O, q, qd, ctrl, dt);
+      return;
+    }
     if (root) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) O[k] = m.n_pos[node][k];     // p stays 0: everything is relative to O
@@ -371,10 +382,110 @@ struct ChainLane {
     }
   }
 
+  // ---- planar twins of walk_joints / node_work (same formulas with the zero components dropped) --------------------
+  __host__ __device__ __forceinline__ void walk_joints_planar(int node, bool root, bool trunk, float (&R)[9],
+                                                              float (&p)[3], float (&v)[6], float (&O)[3],
+                                                              const ChRef& q, const ChRef& qd, const ChRef& ctrl,
+                                                              float dt) {
+    const ChainModel& m = *M;
+    if (root) {
+      O[0] = m.n_pos[node][0]; O[2] = m.n_pos[node][2];
+    } else {
+      p[0] += R[0] * m.n_pos[node][0] + R[2] * m.n_pos[node][2];
+      p[2] += R[0] * m.n_pos[node][2] - R[2] * m.n_pos[node][0];
+    }
+    const int j0 = m.n_dof_start[node], j1 = j0 + m.n_dof_count[node];
+    for (int j = j0; j < j1; ++j) {
+      const int t = m.d_type[j];
+      const float qj = q[m.d_qadr[j]], qdj = qd[j];
+      float Sw, Sx, Sz;
+      if (t == kSlide) {
+        const float ax = R[0] * m.d_axis[j][0] + R[2] * m.d_axis[j][2];
+        const float az = R[0] * m.d_axis[j][2] - R[2] * m.d_axis[j][0];
+        Sw = 0.f; Sx = ax; Sz = az;
+        float* dst = root ? O : p;           // root slides move the origin itself
+        dst[0] += ax * qj; dst[2] += az * qj;
+      } else {
+        const float sg = m.d_axis[j][1];     // +-1: hinge about +y or -y
+        const float anx = R[0] * m.d_anchor[j][0] + R[2] * m.d_anchor[j][2] + p[0];
+        const float anz = R[0] * m.d_anchor[j][2] - R[2] * m.d_anchor[j][0] + p[2];
+        Sw = sg; Sx = -anz * sg; Sz = anx * sg;      // [axis; anchor x axis]
+        float sn, cs;
+        ch::sincos_(qj, &sn, &cs);
+        sn *= sg;
+        const float c0 = R[0], s0 = R[2];
+        R[0] = cs * c0 - sn * s0;
+        R[2] = cs * s0 + sn * c0;
+        const float dx = p[0] - anx, dz = p[2] - anz;
+        p[0] = anx + (cs * dx + sn * dz);
+        p[2] = anz + (cs * dz - sn * dx);
+      }
+      // c = v xm S = [0; w x S_lin + v_lin x S_ang]
+      const float cx = v[1] * Sz - v[5] * Sw, cz = v[3] * Sw - v[1] * Sx;
+      float tau = 0.f;
+      const int act = m.d_act[j];
+      if (act >= 0) tau = m.d_gear[j] * fminf(fmaxf(ctrl[act], -m.ctrl_limit), m.ctrl_limit);
+      float keff = m.d_stiff[j], beff = m.d_damp[j];
+      tau -= keff * qj;
+      if (m.d_limited[j]) {
+        const bool below = qj < m.d_lo[j], above = qj > m.d_hi[j];
+        if (below) tau += m.d_klim[j] * (m.d_lo[j] - qj);
+        if (above) tau += m.d_klim[j] * (m.d_hi[j] - qj);
+        if (below || above) { keff += m.d_klim[j]; beff += m.d_blim[j]; }
+      }
+      const ChRef r = dof_rec(trunk, j);
+      r[1] = Sw; r[3] = Sx; r[5] = Sz;
+      r[9] = cx * qdj; r[11] = cz * qdj;
+      v[1] += Sw * qdj; v[3] += Sx * qdj; v[5] += Sz * qdj;
+      r[trunk ? 19 : 17] = tau - (beff + dt * keff) * qdj;
+      r[trunk ? 20 : 18] = m.d_arm[j] + dt * beff + dt * dt * keff;
+    }
+  }
+
+  __host__ __device__ __forceinline__ void node_work_planar(int node, const float (&R)[9], const float (&p)[3],
+                                                            const float (&v)[6], float Oz,
+                                                            float (&rec)[kChNodeRec]) const {
+    const ChainModel& m = *M;
+    const float mass = m.n_mass[node];
+    const float cx = R[0] * m.n_com[node][0] + R[2] * m.n_com[node][2] + p[0];
+    const float cz = R[0] * m.n_com[node][2] - R[2] * m.n_com[node][0] + p[2];
+    const float Io = m.n_inertia[node][1] + mass * (cx * cx + cz * cz);     // I_yy is invariant under turns about y
+    const float hx = mass * cx, hz = mass * cz;
+    const float wy = v[1], vx = v[3], vz = v[5];
+    // I v = [Io w + h x vl ; m vl - h x w],  bias = v x* (I v)
+    const float Iv1 = Io * wy + (hz * vx - hx * vz);
+    const float Iv3 = mass * vx + hz * wy;
+    const float Iv5 = mass * vz - hx * wy;
+    float f1 = vz * Iv3 - vx * Iv5, f3 = wy * Iv5, f5 = -wy * Iv3;
+    const int k0 = m.n_con_start[node], k1 = k0 + m.n_con_count[node];
+    for (int k = k0; k < k1; ++k) {
+      const float xz = R[0] * m.c_pos[k][2] - R[2] * m.c_pos[k][0] + p[2];
+      const float pen = m.c_radius[k] - (Oz + xz);
+      if (pen > 0.f) {
+        const float xx = R[0] * m.c_pos[k][0] + R[2] * m.c_pos[k][2] + p[0];
+        const float ux = wy * xz + vx, uz = vz - wy * xx;
+        const float spring = m.kc * pen;
+        const float damp = fminf(spring * m.cc, m.cdmax);
+        const float fn = fminf(fmaxf(spring - damp * uz, 0.f), 3.f * spring);
+        const float coef = fminf(m.kv, m.mu * fn * ch_rcp(fmaxf(fabsf(ux), 1e-6f)));
+        const float fcx = -coef * ux;
+        f1 -= xz * fcx - xx * fn;
+        f3 -= fcx;
+        f5 -= fn;
+      }
+    }
+    rec[0] = mass; rec[1] = hx; rec[3] = hz; rec[5] = Io;
+    rec[11] = f1; rec[13] = f3; rec[15] = f5;
+  }
+
   // Body-level work of one node given its frame and velocity: rigid inertia about O, bias force v x* I v minus the
   // floor-contact wrenches -> rec = (mass, h, Io, bias force).
   __host__ __device__ __forceinline__ void node_work(int node, const float (&R)[9], const float (&p)[3],
                                                      const float (&v)[6], float Oz, float (&rec)[kChNodeRec]) const {
+    if constexpr (PLANAR) {
+      node_work_planar(node, R, p, v, Oz, rec);
+      return;
+    }
     const ChainModel& m = *M;
     const float mass = m.n_mass[node];
     float c[3];
@@ -437,6 +548,29 @@ struct ChainLane {
     for (int e = 0; e < 6; ++e) { rec[4 + e] = Io[e]; rec[10 + e] = f[e]; }
   }
 
+  // frame (R, p, v) of a trunk body and node records (mass, h, Io, bias force) in shared memory: the planar engine
+  // moves only the entries it uses (same slots)
+  __host__ __device__ __forceinline__ void load_frame(const ChRef& f, float (&R)[9], float (&p)[3], float (&v)[6]) const {
+    if constexpr (PLANAR) {
+      R[0] = f[0]; R[2] = f[2]; p[0] = f[9]; p[2] = f[11]; v[1] = f[13]; v[3] = f[15]; v[5] = f[17];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) R[k] = f[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) p[k] = f[9 + k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v[k] = f[12 + k];
+    }
+  }
+  __host__ __device__ __forceinline__ void store_node_rec(const ChRef& nr, const float (&rec)[kChNodeRec]) const {
+    if constexpr (PLANAR) {
+      nr[0] = rec[0]; nr[1] = rec[1]; nr[3] = rec[3]; nr[5] = rec[5]; nr[11] = rec[11]; nr[13] = rec[13]; nr[15] = rec[15];
+    } else {
+#pragma unroll
+      for (int e = 0; e < kChNodeRec; ++e) nr[e] = rec[e];
+    }
+  }
+
   // `rec` returns the record of the LAST node of this lane's limb: pass 2 starts with that node, so its record never
   // goes through shared memory.  `implicit`: joint springs / dampers enter the system matrix (dt > 0 in the diagonal).
   //   1. every lane walks the trunk's joints (identical values in all lanes; frames -> shared memory);
@@ -452,38 +586,28 @@ struct ChainLane {
     for (int t = 0; t < m.n_trunk; ++t) {
       walk_joints(m.trunk_node[t], t == 0, true, R, p, v, O, q, qd, ctrl, dt);
       const ChRef f = shared_rec(m.s_frame + kChFrame * t);
+      if constexpr (PLANAR) {
+        f[0] = R[0]; f[2] = R[2]; f[9] = p[0]; f[11] = p[2]; f[13] = v[1]; f[15] = v[3]; f[17] = v[5];
+      } else {
 #pragma unroll
-      for (int k = 0; k < 9; ++k) f[k] = R[k];
+        for (int k = 0; k < 9; ++k) f[k] = R[k];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) f[9 + k] = p[k];
+        for (int k = 0; k < 3; ++k) f[9 + k] = p[k];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) f[12 + k] = v[k];
+        for (int k = 0; k < 6; ++k) f[12 + k] = v[k];
+      }
     }
     const float Oz = O[2];
     // every lane wrote every frame (identical values), so a lane could read right behind its own stores; the barrier
     // keeps the access pattern formally race-free (compute-sanitizer racecheck) at the price of one WARPSYNC
     ctx->group_sync();
     for (int t = g; t < m.n_trunk; t += m.lanes) {
-      const ChRef f = shared_rec(m.s_frame + kChFrame * t);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) R[k] = f[k];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) p[k] = f[9 + k];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) v[k] = f[12 + k];
+      load_frame(shared_rec(m.s_frame + kChFrame * t), R, p, v);
       node_work(m.trunk_node[t], R, p, v, Oz, rec);
-      const ChRef nr = shared_rec(m.s_node + kChNodeRec * t);
-#pragma unroll
-      for (int e = 0; e < kChNodeRec; ++e) nr[e] = rec[e];
+      store_node_rec(shared_rec(m.s_node + kChNodeRec * t), rec);
     }
     if (g < m.n_limbs) {
-      const ChRef f = shared_rec(m.s_frame + kChFrame * m.limb_attach[g]);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) R[k] = f[k];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) p[k] = f[9 + k];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) v[k] = f[12 + k];
+      load_frame(shared_rec(m.s_frame + kChFrame * m.limb_attach[g]), R, p, v);
     }
     ctx->group_sync();      // every lane has its attach frame: the frame region may now park the limbs' first records
     if (g < m.n_limbs) {
@@ -492,17 +616,17 @@ struct ChainLane {
         const int node = m.limb_node[g][i];
         walk_joints(node, false, false, R, p, v, O, q, qd, ctrl, dt);
         node_work(node, R, p, v, Oz, rec);
-        if (i != nn - 1) {
-          const ChRef nr = node_rec(false, i);
-#pragma unroll
-          for (int e = 0; e < kChNodeRec; ++e) nr[e] = rec[e];
-        }
+        if (i != nn - 1) store_node_rec(node_rec(false, i), rec);
       }
     }
   }
 
   // ---- pass 2 ----------------------------------------------------------------------------------------------------
   __host__ __device__ void pass2(const float (&rec)[kChNodeRec]) {
+    if constexpr (PLANAR) {
+      pass2_planar(rec);
+      return;
+    }
     const ChainModel& m = *M;
     ArtInertia IA;
     float P[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -598,9 +722,109 @@ struct ChainLane {
     }
   }
 
+  // ---- planar pass 2 / pass 3: articulated inertia (Ayy, Byx, Byz, Cxx, Czz, Cxz), forces (n_y, f_x, f_z) -------------
+  __host__ __device__ void pass2_planar(const float (&rec)[kChNodeRec]) {
+    const ChainModel& m = *M;
+    float Ayy = 0.f, Byx = 0.f, Byz = 0.f, Cxx = 0.f, Czz = 0.f, Cxz = 0.f, P1 = 0.f, P3 = 0.f, P5 = 0.f;
+    const int n_seq = m.n_trunk + m.max_limb_nodes;
+    const int last = m.seq_last[g];
+    for (int i = n_seq - 1; i >= 0; --i) {
+      if (i == m.n_trunk - 1 && m.n_junctions > 0) {
+        const int mine = g < m.n_limbs ? m.trunk_junction[m.limb_attach[g]] : -1;
+        for (int js = 0; js < m.n_junctions; ++js) {
+          const bool w = mine == js;
+          float x[9] = {w ? Ayy : 0.f, w ? Byx : 0.f, w ? Byz : 0.f, w ? Cxx : 0.f, w ? Czz : 0.f, w ? Cxz : 0.f,
+                        w ? P1 : 0.f, w ? P3 : 0.f, w ? P5 : 0.f};
+          ctx->group_sum(x);
+          if (js == 0) ctx->group_sync();      // the junction region changes tenant: parked limb records -> sums
+          const ChRef jr = shared_rec(m.s_jun + kChJun * js);
+#pragma unroll
+          for (int e = 0; e < 9; ++e) jr[e] = x[e];
+        }
+        Ayy = Byx = Byz = Cxx = Czz = Cxz = P1 = P3 = P5 = 0.f;
+      }
+      if (i == m.n_trunk - 1) ctx->group_sync();      // the trunk's node records were written by different lanes
+      int node, pos;
+      bool trunk;
+      if (!node_at(i, node, trunk, pos)) continue;
+      {
+        float mass, hx, hz, Io, f1, f3, f5;
+        if (i == last) {
+          mass = rec[0]; hx = rec[1]; hz = rec[3]; Io = rec[5]; f1 = rec[11]; f3 = rec[13]; f5 = rec[15];
+        } else {
+          const ChRef nr = node_rec(trunk, pos);
+          mass = nr[0]; hx = nr[1]; hz = nr[3]; Io = nr[5]; f1 = nr[11]; f3 = nr[13]; f5 = nr[15];
+        }
+        P1 += f1; P3 += f3; P5 += f5;
+        Ayy += Io; Byx += hz; Byz -= hx; Cxx += mass; Czz += mass;       // ArtInertia::add_rigid
+      }
+      if (trunk && m.trunk_junction[i] >= 0) {
+        const ChRef jr = shared_rec(m.s_jun + kChJun * m.trunk_junction[i]);
+        Ayy += jr[0]; Byx += jr[1]; Byz += jr[2]; Cxx += jr[3]; Czz += jr[4]; Cxz += jr[5];
+        P1 += jr[6]; P3 += jr[7]; P5 += jr[8];
+      }
+      const int j0 = m.n_dof_start[node], j1 = j0 + m.n_dof_count[node];
+      for (int j = j1 - 1; j >= j0; --j) {
+        const ChRef r = dof_rec(trunk, j);
+        const float S1 = r[1], S3 = r[3], S5 = r[5], c3 = r[9], c5 = r[11];
+        // U = IA S
+        const float U1 = Ayy * S1 + Byx * S3 + Byz * S5;
+        const float U3 = Byx * S1 + Cxx * S3 + Cxz * S5;
+        const float U5 = Byz * S1 + Cxz * S3 + Czz * S5;
+        float D = r[trunk ? 20 : 18], u = r[trunk ? 19 : 17];
+        D += S1 * U1 + S3 * U3 + S5 * U5;
+        u -= S1 * P1 + S3 * P3 + S5 * P5;
+        const float invD = ch_rcp(D);
+        const float ud = u * invD;
+        const float Ud1 = U1 * invD, Ud3 = U3 * invD, Ud5 = U5 * invD;
+        r[13] = Ud1; r[15] = Ud3; r[17] = Ud5;
+        r[18] = ud;
+        // IA -= U Ud^T
+        Ayy -= U1 * Ud1; Byx -= U1 * Ud3; Byz -= U1 * Ud5; Cxx -= U3 * Ud3; Czz -= U5 * Ud5; Cxz -= U3 * Ud5;
+        // pA += IA c + U u / D   (c has no angular part)
+        P1 += Byx * c3 + Byz * c5 + U1 * ud;
+        P3 += Cxx * c3 + Cxz * c5 + U3 * ud;
+        P5 += Cxz * c3 + Czz * c5 + U5 * ud;
+      }
+    }
+  }
+
+  template <class Sink>
+  __host__ __device__ void pass3_planar(Sink&& sink) {
+    const ChainModel& m = *M;
+    float a1 = 0.f, a3 = 0.f, a5 = m.gravity;     // gravity as a fictitious base acceleration
+    const int n_seq = m.n_trunk + m.max_limb_nodes;
+    for (int i = 0; i < n_seq; ++i) {
+      int node, pos;
+      bool trunk;
+      if (i == m.n_trunk) ctx->group_sync();     // the junction accelerations are complete in every lane's view
+      if (!node_at(i, node, trunk, pos)) continue;
+      if (!trunk && pos == 0) {
+        const ChRef ar = shared_rec(m.s_acc + 6 * m.trunk_junction[m.limb_attach[g]]);
+        a1 = ar[1]; a3 = ar[3]; a5 = ar[5];
+      }
+      const int j0 = m.n_dof_start[node], j1 = j0 + m.n_dof_count[node];
+      for (int j = j0; j < j1; ++j) {
+        const ChRef r = dof_rec(trunk, j);
+        a3 += r[9]; a5 += r[11];
+        const float qacc = r[18] - (r[13] * a1 + r[15] * a3 + r[17] * a5);
+        a1 += r[1] * qacc; a3 += r[3] * qacc; a5 += r[5] * qacc;
+        sink(j, trunk, qacc);
+      }
+      if (trunk && m.trunk_junction[i] >= 0) {
+        const ChRef ar = shared_rec(m.s_acc + 6 * m.trunk_junction[i]);
+        ar[1] = a1; ar[3] = a3; ar[5] = a5;
+      }
+    }
+  }
+
   // ---- pass 3: accelerations; qacc_j is handed to `sink(j, trunk, qacc)` in dof order ------------------------------
   template <class Sink>
   __host__ __device__ void pass3(Sink&& sink) {
+    if constexpr (PLANAR) {
+      pass3_planar(sink);
+      return;
+    }
     const ChainModel& m = *M;
     float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, m.gravity};     // gravity as a fictitious base acceleration
     const int n_seq = m.n_trunk + m.max_limb_nodes;
@@ -977,6 +1201,19 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
   // a limb's last node keeps its record in registers (pass 1 -> pass 2), its first one is parked in the junction region
   m.p_node = p; p += kChNodeRec * (m.max_limb_nodes > 2 ? m.max_limb_nodes - 2 : 0);
   m.p_end = p;
+  // planar robots (HalfCheetah, Hopper): no free joint, slides inside the x-z plane, hinges about +-y, every offset /
+  // centre of mass / anchor / contact point at y = 0, no inertia product with y
+  m.planar = m.root_free ? 0 : 1;
+  for (int n = 0; n < m.n_nodes && m.planar; ++n)
+    if (m.n_pos[n][1] != 0.f || m.n_com[n][1] != 0.f || m.n_inertia[n][3] != 0.f || m.n_inertia[n][5] != 0.f) m.planar = 0;
+  for (int j = 0; j < m.nv && m.planar; ++j) {
+    if (m.d_type[j] == kSlide) { if (m.d_axis[j][1] != 0.f) m.planar = 0; }
+    else if (m.d_type[j] == kHinge) {
+      if (m.d_axis[j][0] != 0.f || m.d_axis[j][2] != 0.f || fabsf(m.d_axis[j][1]) != 1.f || m.d_anchor[j][1] != 0.f) m.planar = 0;
+    } else m.planar = 0;
+  }
+  for (int c = 0; c < n_con && m.planar; ++c)
+    if (m.c_pos[c][1] != 0.f) m.planar = 0;
   return true;
 }
 

@@ -396,7 +396,7 @@ static void launch_series_sampler(icem_planner* p, const RolloutArgs& a, int row
 
 constexpr size_t kMaxSmemPerCta = 227 * 1024;
 
-template <int G, bool kSample, bool kRollout, bool kNextObs>
+template <int G, bool kSample, bool kRollout, bool kNextObs, bool kPlanar>
 static void launch_chain_impl(icem_planner* p, const RolloutArgs& a, int rows_max) {
   const SamplerConst sc = sampler_const(p);
   const CostConst cc = cost_const(p);
@@ -416,7 +416,7 @@ static void launch_chain_impl(icem_planner* p, const RolloutArgs& a, int rows_ma
   { const char* e = getenv("ICEM_B200_CHAIN_WARPS"); if (e && atoi(e) > 0) warps = std::min(wmax, atoi(e)); }
   const size_t smem = chain_rollout_smem_bytes<kSample>(sc, dp, a.stride, warps);
   if (smem > kMaxSmemPerCta) throw InvalidArg("chain rollout kernel does not fit on an SM (shared memory)");
-  auto kern = chain_rollout_kernel<G, kSample, kRollout, kNextObs>;
+  auto kern = chain_rollout_kernel<G, kSample, kRollout, kNextObs, kPlanar>;
   ensure_dynamic_smem(kern, chain_rollout_smem_bytes<kSample>(sc, dp, a.stride, wmax), p->cfg.device);
   const int grid = std::max(1, std::min((trips + warps - 1) / warps, sms));
   kern<<<dim3(grid, nprob), warps * 32, smem, p->stream>>>(a, sc, cc, dp);
@@ -424,22 +424,28 @@ static void launch_chain_impl(icem_planner* p, const RolloutArgs& a, int rows_ma
   g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
-template <int G, bool kSample, bool kRollout>
+template <int G, bool kSample, bool kRollout, bool kPlanar>
 static void launch_chain_g(icem_planner* p, const RolloutArgs& a, int rows_max) {
   if (p->cfg.cost == ICEM_COST_LOCOMOTION) {
-    if constexpr (kRollout) launch_chain_impl<G, kSample, true, true>(p, a, rows_max);
-    else launch_chain_impl<G, kSample, false, false>(p, a, rows_max);
+    if constexpr (kRollout) launch_chain_impl<G, kSample, true, true, kPlanar>(p, a, rows_max);
+    else launch_chain_impl<G, kSample, false, false, kPlanar>(p, a, rows_max);
   } else {
-    launch_chain_impl<G, kSample, kRollout, false>(p, a, rows_max);
+    launch_chain_impl<G, kSample, kRollout, false, kPlanar>(p, a, rows_max);
   }
 }
 
 template <bool kSample, bool kRollout>
 static void launch_chain(icem_planner* p, const RolloutArgs& a, int rows_max) {
+  // planar robots (HalfCheetah: 2 lanes, Hopper: 1) run the planar instantiation of the engine
+  if (p->chain_host.planar && p->chain_host.lanes <= 2) {
+    if (p->chain_host.lanes == 1) launch_chain_g<1, kSample, kRollout, true>(p, a, rows_max);
+    else launch_chain_g<2, kSample, kRollout, true>(p, a, rows_max);
+    return;
+  }
   switch (p->chain_host.lanes) {
-    case 1: launch_chain_g<1, kSample, kRollout>(p, a, rows_max); break;
-    case 2: launch_chain_g<2, kSample, kRollout>(p, a, rows_max); break;
-    default: launch_chain_g<4, kSample, kRollout>(p, a, rows_max); break;
+    case 1: launch_chain_g<1, kSample, kRollout, false>(p, a, rows_max); break;
+    case 2: launch_chain_g<2, kSample, kRollout, false>(p, a, rows_max); break;
+    default: launch_chain_g<4, kSample, kRollout, false>(p, a, rows_max); break;
   }
 }
 
@@ -656,9 +662,12 @@ static void advance_dyn(icem_planner* p, float* state, const float* action, floa
           kern<<<batch, 32, smem, p->stream>>>(p->chain, state, action, next_state, obs_out, obs_dim, ab.state_stride,
                                                ab.action_stride, ab.obs_stride);
         };
-        if (p->chain_host.lanes == 1) launch(chain_advance_kernel<1>);
-        else if (p->chain_host.lanes == 2) launch(chain_advance_kernel<2>);
-        else launch(chain_advance_kernel<4>);
+        const bool planar = p->chain_host.planar && p->chain_host.lanes <= 2;
+        if (planar && p->chain_host.lanes == 1) launch(chain_advance_kernel<1, true>);
+        else if (planar) launch(chain_advance_kernel<2, true>);
+        else if (p->chain_host.lanes == 1) launch(chain_advance_kernel<1, false>);
+        else if (p->chain_host.lanes == 2) launch(chain_advance_kernel<2, false>);
+        else launch(chain_advance_kernel<4, false>);
         ICEM_CUDA(cudaGetLastError());
         g_launches.fetch_add(1, std::memory_order_relaxed);
       } else if (Articulated<12>::fits(p->art.nb, p->art.nv, p->art.nc))
@@ -1182,6 +1191,8 @@ int icem_set_articulated_model(icem_planner_t* p, const icem_articulated_model_t
     const char* why = "";
     p->chain_ok = !p->force_warp_engine && build_chain_model(chain_source(*a), p->d, p->chain_host, &why);
     if (p->chain_ok) {
+      // ICEM_B200_PLANAR=0: run a planar robot through the spatial instantiation of the engine (A/B, tests)
+      { const char* e = getenv("ICEM_B200_PLANAR"); if (e && e[0] == '0') p->chain_host.planar = 0; }
       p->chain_model.alloc(1);
       ICEM_CUDA(cudaMemcpy(p->chain_model.p, &p->chain_host, sizeof(ChainModel), cudaMemcpyHostToDevice));
       p->chain.model = p->chain_model.p;

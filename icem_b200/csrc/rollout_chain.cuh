@@ -46,12 +46,12 @@ struct ChainParams {
 
 constexpr int kChainPrefetch = 5;     // controls per lane fetched one step ahead (covers d <= 5 G)
 
-template <int G>
-using ChainWarpLane = ChainLane<WarpGroupCtx<G>, 32 / G>;
+template <int G, bool PLANAR = false>
+using ChainWarpLane = ChainLane<WarpGroupCtx<G>, 32 / G, PLANAR>;
 
 // lane-private scratch of lane g of a group: region g behind the group-shared region (see chain_warp_floats)
-template <int G>
-__device__ __forceinline__ void chain_bind_lane(ChainWarpLane<G>& L, const ChainModel& m, float* w_base, int lane,
+template <int G, bool PLANAR>
+__device__ __forceinline__ void chain_bind_lane(ChainWarpLane<G, PLANAR>& L, const ChainModel& m, float* w_base, int lane,
                                                 WarpGroupCtx<G>* ctx) {
   constexpr int NG = 32 / G;
   const int grp = lane / G;
@@ -62,9 +62,10 @@ __device__ __forceinline__ void chain_bind_lane(ChainWarpLane<G>& L, const Chain
   L.ctx = ctx;
 }
 
-template <int G>
-__device__ __forceinline__ float chain_step_cost_pre(const CostConst& cc, const ChainWarpLane<G>& L,
-                                                     const typename ChainWarpLane<G>::ChRef& act, int d, bool next_obs) {
+template <int G, bool PLANAR>
+__device__ __forceinline__ float chain_step_cost_pre(const CostConst& cc, const ChainWarpLane<G, PLANAR>& L,
+                                                     const typename ChainWarpLane<G, PLANAR>::ChRef& act, int d,
+                                                     bool next_obs) {
   const ChainModel& m = *L.M;
   float a2 = 0.f;
   for (int k = 0; k < d; ++k) a2 = fmaf(act[k], act[k], a2);
@@ -98,7 +99,7 @@ __device__ __forceinline__ float chain_step_cost_pre(const CostConst& cc, const 
 
 constexpr int kChainMaxWarps = 12;    // per CTA (one CTA per SM): 384 threads x 170 registers fill the register file
 
-template <int G, bool kSample, bool kRollout, bool kNextObs>
+template <int G, bool kSample, bool kRollout, bool kNextObs, bool PLANAR = false>
 __global__ void __launch_bounds__(kChainMaxWarps * 32, 1)
 chain_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, ChainParams dp) {
   extern __shared__ __align__(128) float smem[];
@@ -149,10 +150,10 @@ chain_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, ChainParams d
   const uint32_t tile_bytes = (uint32_t)tile_floats * 4u;
 
   WarpGroupCtx<G> ctx;
-  ChainWarpLane<G> L;
-  typedef typename ChainWarpLane<G>::ChRef ChRef;
+  ChainWarpLane<G, PLANAR> L;
+  typedef typename ChainWarpLane<G, PLANAR>::ChRef ChRef;
   const int grp = lane / G;
-  chain_bind_lane<G>(L, m, w_base, lane, &ctx);
+  chain_bind_lane<G, PLANAR>(L, m, w_base, lane, &ctx);
 
   for (int trip = wg; trip < n_trips; trip += n_wg) {
     const int row0 = trip * rpw;
@@ -202,7 +203,7 @@ chain_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, ChainParams d
           pre[u] = k < d ? __ldcg(arow + (t + 1) * d + k) : 0.f;
         }
       }
-      const float c = chain_step_cost_pre<G>(cc, L, act, d, kNextObs);
+      const float c = chain_step_cost_pre<G, PLANAR>(cc, L, act, d, kNextObs);
       if constexpr (!kNextObs) {
         if (cc.reduce == 0) total += c;
         else if (cc.reduce == 1) total = fminf(total, c);
@@ -248,7 +249,7 @@ inline size_t chain_rollout_smem_bytes(const SamplerConst& sc, const ChainParams
 
 // One transition (or just the observation) of a single state: env.step on the device model with the chain engine.
 // blockIdx.x = instance; one warp, every group computes the same thing, group 0 reports.
-template <int G>
+template <int G, bool PLANAR = false>
 __global__ void chain_advance_kernel(ChainParams dp, float* state, const float* action, float* next_state,
                                      float* obs_out, int obs_dim, int state_stride, int action_stride, int obs_stride) {
   extern __shared__ __align__(128) float smem[];
@@ -267,9 +268,9 @@ __global__ void chain_advance_kernel(ChainParams dp, float* state, const float* 
   const ChainModel& m = *reinterpret_cast<const ChainModel*>(s_model);
   const int lane = threadIdx.x & 31, grp = lane / G;
   WarpGroupCtx<G> ctx;
-  ChainWarpLane<G> L;
-  typedef typename ChainWarpLane<G>::ChRef ChRef;
-  chain_bind_lane<G>(L, m, w_base, lane, &ctx);
+  ChainWarpLane<G, PLANAR> L;
+  typedef typename ChainWarpLane<G, PLANAR>::ChRef ChRef;
+  chain_bind_lane<G, PLANAR>(L, m, w_base, lane, &ctx);
   const int ns = m.nq + m.nv;
   for (int i = L.g; i < ns; i += G) L.state(i) = state[i];
   if (action)

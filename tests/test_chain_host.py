@@ -84,3 +84,46 @@ def test_host_compiled_engine_matches_float64_oracle(host_lib, name, tol, integr
     for t in range(h):
         s = mod.step_state(s, acts[:, t].astype(np.float64))
     assert np.abs(s - states[:, h]).max() <= (5e-2 if name == "ant" else 5e-3)
+
+
+@pytest.mark.parametrize("integrator", ["euler", "rk4"])
+@pytest.mark.parametrize("name", ["halfcheetah", "hopper"])
+def test_planar_instantiation_matches_oracle_and_spatial_engine(host_lib, name, integrator):
+    """Planar robots run ChainLane<..., PLANAR = true> (3-vectors instead of 6-vectors): same tolerance against the
+    float64 oracle as the spatial instantiation, and the two instantiations agree to fp32 rounding on one step."""
+    m = robots.get_model(name, integrator=integrator)
+    st, keep = articulated_model_struct(m)
+    host_lib.chain_host_is_planar.restype = C.c_int
+    host_lib.chain_host_rollout_engine.restype = C.c_int
+    assert host_lib.chain_host_is_planar(C.byref(st), m.nu) == 1
+    for other in ("humanoid_standup", "ant", "humanoid"):
+        so, _k = articulated_model_struct(robots.get_model(other))
+        assert host_lib.chain_host_is_planar(C.byref(so), robots.get_model(other).nu) == 0
+    mod = make_model(name, obs_skip=0, integrator=integrator)
+    rs = np.random.RandomState(7)
+    n, h = 16, 12
+    start = np.concatenate([m.qpos0, 0.2 * rs.randn(m.nv)])
+    acts = rs.uniform(-1.3 * m.ctrl_limit, 1.3 * m.ctrl_limit, (n, h, m.nu)).astype(np.float32)
+    out = {}
+    for planar in (0, 1):
+        states = np.zeros((n, h + 1, m.nq + m.nv))
+        rc = host_lib.chain_host_rollout_engine(C.byref(st), m.nu, {"euler": 0, "rk4": 1}[integrator], planar, n, h,
+                                                start.ctypes.data_as(C.POINTER(C.c_double)), fptr(acts),
+                                                states.ctypes.data_as(C.POINTER(C.c_double)))
+        assert rc == 0
+        worst = 0.0
+        for t in range(h):
+            ref = mod.step_state(states[:, t], acts[:, t].astype(np.float64))
+            worst = max(worst, float(np.abs(ref - states[:, t + 1]).max()))
+        assert worst <= 2e-4, (planar, worst)
+        out[planar] = states
+    # first step from the identical start state: the two instantiations differ by fp32 rounding only
+    assert np.abs(out[0][:, 1] - out[1][:, 1]).max() <= 2e-5
+    # a non-planar robot is refused by the planar engine
+    so, _k = articulated_model_struct(robots.get_model("ant"))
+    ant = robots.get_model("ant")
+    rc = host_lib.chain_host_rollout_engine(C.byref(so), ant.nu, 0, 1, 1, 1,
+                                            np.zeros(ant.nq + ant.nv).ctypes.data_as(C.POINTER(C.c_double)),
+                                            fptr(np.zeros((1, 1, ant.nu), np.float32)),
+                                            np.zeros((1, 2, ant.nq + ant.nv)).ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc == 2
