@@ -87,7 +87,8 @@ struct ChainModel {
   int n_dof_start[kChMaxNodes], n_dof_count[kChMaxNodes], n_con_start[kChMaxNodes], n_con_count[kChMaxNodes];
   float n_pos[kChMaxNodes][3], n_mass[kChMaxNodes], n_com[kChMaxNodes][3], n_inertia[kChMaxNodes][6];
   int d_type[kChMaxDofs], d_qadr[kChMaxDofs], d_limited[kChMaxDofs], d_act[kChMaxDofs];
-  int d_rec[kChMaxDofs];                         // record slot of the dof inside its region (trunk / own limb)
+  int d_rec[kChMaxDofs];                         // record index of the dof inside its region (trunk / own limb)
+  int d_slot[kChMaxDofs];                        // first slot of that record: s_dof + 21 * d_rec (trunk), p_dof + 19 * d_rec (limb)
   float d_axis[kChMaxDofs][3], d_anchor[kChMaxDofs][3];
   float d_stiff[kChMaxDofs], d_damp[kChMaxDofs], d_arm[kChMaxDofs], d_lo[kChMaxDofs], d_hi[kChMaxDofs];
   float d_klim[kChMaxDofs], d_blim[kChMaxDofs], d_gear[kChMaxDofs];
@@ -258,8 +259,7 @@ struct ChainLane {
   __host__ __device__ __forceinline__ ChRef private_rec(int slot) const { return ChRef{pr + slot * STRIDE}; }
   __host__ __device__ __forceinline__ float& state(int i) const { return sh[(M->s_state + i) * STRIDE]; }
   __host__ __device__ __forceinline__ ChRef dof_rec(bool trunk, int j) const {
-    return trunk ? shared_rec(M->s_dof + kChTrunkDofRec * M->d_rec[j])
-                 : private_rec(M->p_dof + kChDofRec * M->d_rec[j]);
+    return ChRef{(trunk ? sh : pr) + M->d_slot[j] * STRIDE};      // one table read instead of base + stride * index
   }
   // Node records: trunk nodes in the shared region; a limb's FIRST node is parked in the junction region (idle
   // between the limb's start and the junction sums: 16 slots per lane of the group), its last node stays in
@@ -1201,6 +1201,15 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
   // a limb's last node keeps its record in registers (pass 1 -> pass 2), its first one is parked in the junction region
   m.p_node = p; p += kChNodeRec * (m.max_limb_nodes > 2 ? m.max_limb_nodes - 2 : 0);
   m.p_end = p;
+  {
+    bool is_trunk_dof[kChMaxDofs] = {false};
+    for (int t = 0; t < m.n_trunk; ++t) {
+      const int n = m.trunk_node[t];
+      for (int j = m.n_dof_start[n]; j < m.n_dof_start[n] + m.n_dof_count[n]; ++j) is_trunk_dof[j] = true;
+    }
+    for (int j = 0; j < m.nv; ++j)
+      m.d_slot[j] = is_trunk_dof[j] ? m.s_dof + kChTrunkDofRec * m.d_rec[j] : m.p_dof + kChDofRec * m.d_rec[j];
+  }
   // planar robots (HalfCheetah, Hopper): no free joint, slides inside the x-z plane, hinges about +-y, every offset /
   // centre of mass / anchor / contact point at y = 0, no inertia product with y
   m.planar = m.root_free ? 0 : 1;
