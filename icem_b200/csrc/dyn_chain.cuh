@@ -269,10 +269,10 @@ struct ChainLane {
     return pos == 0 ? shared_rec(M->s_frame + kChNodeRec * g) : private_rec(M->p_node + kChNodeRec * (pos - 1));
   }
   // node this lane visits at position i of its walk (trunk nodes, then its own limb); false = nothing to do
-  __host__ __device__ __forceinline__ bool node_at(int i, int& node, bool& trunk, int& pos) const {
+  __host__ __device__ __forceinline__ bool node_at(int i, int n_trunk, int& node, bool& trunk, int& pos) const {
     const ChainModel& m = *M;
-    trunk = i < m.n_trunk;
-    pos = trunk ? i : i - m.n_trunk;
+    trunk = i < n_trunk;
+    pos = trunk ? i : i - n_trunk;
     node = m.seq_node[g][i];
     return node >= 0;
   }
@@ -631,13 +631,16 @@ struct ChainLane {
     ArtInertia IA;
     float P[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     IA.zero();
-    const int n_seq = m.n_trunk + m.max_limb_nodes;
+    // loop-invariant scalars of the model are read ONCE: the model lives in shared memory, and the compiler must assume
+    // that the record stores of the loop alias it, so every `m.x` inside the loop is a dependent shared-memory read
+    const int n_trunk = m.n_trunk, n_junctions = m.n_junctions;
+    const int n_seq = n_trunk + m.max_limb_nodes;
     const int last = m.seq_last[g];
     for (int i = n_seq - 1; i >= 0; --i) {
-      if (i == m.n_trunk - 1 && m.n_junctions > 0) {
+      if (i == n_trunk - 1 && n_junctions > 0) {
         // the limbs are done: sum them where they join the trunk (every lane gets every junction's sum)
         const int mine = g < m.n_limbs ? m.trunk_junction[m.limb_attach[g]] : -1;
-        for (int js = 0; js < m.n_junctions; ++js) {
+        for (int js = 0; js < n_junctions; ++js) {
           const bool w = mine == js;
           float x[kChJun];
 #pragma unroll
@@ -654,10 +657,10 @@ struct ChainLane {
 #pragma unroll
         for (int e = 0; e < 6; ++e) P[e] = 0.f;
       }
-      if (i == m.n_trunk - 1) ctx->group_sync();      // the trunk's node records were written by different lanes
+      if (i == n_trunk - 1) ctx->group_sync();      // the trunk's node records were written by different lanes
       int node, pos;
       bool trunk;
-      if (!node_at(i, node, trunk, pos)) continue;
+      if (!node_at(i, n_trunk, node, trunk, pos)) continue;
       if (i == last) {
         const float h[3] = {rec[1], rec[2], rec[3]};
 #pragma unroll
@@ -726,12 +729,13 @@ struct ChainLane {
   __host__ __device__ void pass2_planar(const float (&rec)[kChNodeRec]) {
     const ChainModel& m = *M;
     float Ayy = 0.f, Byx = 0.f, Byz = 0.f, Cxx = 0.f, Czz = 0.f, Cxz = 0.f, P1 = 0.f, P3 = 0.f, P5 = 0.f;
-    const int n_seq = m.n_trunk + m.max_limb_nodes;
+    const int n_trunk = m.n_trunk, n_junctions = m.n_junctions;
+    const int n_seq = n_trunk + m.max_limb_nodes;
     const int last = m.seq_last[g];
     for (int i = n_seq - 1; i >= 0; --i) {
-      if (i == m.n_trunk - 1 && m.n_junctions > 0) {
+      if (i == n_trunk - 1 && n_junctions > 0) {
         const int mine = g < m.n_limbs ? m.trunk_junction[m.limb_attach[g]] : -1;
-        for (int js = 0; js < m.n_junctions; ++js) {
+        for (int js = 0; js < n_junctions; ++js) {
           const bool w = mine == js;
           float x[9] = {w ? Ayy : 0.f, w ? Byx : 0.f, w ? Byz : 0.f, w ? Cxx : 0.f, w ? Czz : 0.f, w ? Cxz : 0.f,
                         w ? P1 : 0.f, w ? P3 : 0.f, w ? P5 : 0.f};
@@ -743,10 +747,10 @@ struct ChainLane {
         }
         Ayy = Byx = Byz = Cxx = Czz = Cxz = P1 = P3 = P5 = 0.f;
       }
-      if (i == m.n_trunk - 1) ctx->group_sync();      // the trunk's node records were written by different lanes
+      if (i == n_trunk - 1) ctx->group_sync();      // the trunk's node records were written by different lanes
       int node, pos;
       bool trunk;
-      if (!node_at(i, node, trunk, pos)) continue;
+      if (!node_at(i, n_trunk, node, trunk, pos)) continue;
       {
         float mass, hx, hz, Io, f1, f3, f5;
         if (i == last) {
@@ -793,12 +797,13 @@ struct ChainLane {
   __host__ __device__ void pass3_planar(Sink&& sink) {
     const ChainModel& m = *M;
     float a1 = 0.f, a3 = 0.f, a5 = m.gravity;     // gravity as a fictitious base acceleration
-    const int n_seq = m.n_trunk + m.max_limb_nodes;
+    const int n_trunk = m.n_trunk;
+    const int n_seq = n_trunk + m.max_limb_nodes;
     for (int i = 0; i < n_seq; ++i) {
       int node, pos;
       bool trunk;
-      if (i == m.n_trunk) ctx->group_sync();     // the junction accelerations are complete in every lane's view
-      if (!node_at(i, node, trunk, pos)) continue;
+      if (i == n_trunk) ctx->group_sync();     // the junction accelerations are complete in every lane's view
+      if (!node_at(i, n_trunk, node, trunk, pos)) continue;
       if (!trunk && pos == 0) {
         const ChRef ar = shared_rec(m.s_acc + 6 * m.trunk_junction[m.limb_attach[g]]);
         a1 = ar[1]; a3 = ar[3]; a5 = ar[5];
@@ -827,12 +832,13 @@ struct ChainLane {
     }
     const ChainModel& m = *M;
     float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, m.gravity};     // gravity as a fictitious base acceleration
-    const int n_seq = m.n_trunk + m.max_limb_nodes;
+    const int n_trunk = m.n_trunk;
+    const int n_seq = n_trunk + m.max_limb_nodes;
     for (int i = 0; i < n_seq; ++i) {
       int node, pos;
       bool trunk;
-      if (i == m.n_trunk) ctx->group_sync();     // the junction accelerations are complete in every lane's view
-      if (!node_at(i, node, trunk, pos)) continue;
+      if (i == n_trunk) ctx->group_sync();     // the junction accelerations are complete in every lane's view
+      if (!node_at(i, n_trunk, node, trunk, pos)) continue;
       if (!trunk && pos == 0) {
         const ChRef ar = shared_rec(m.s_acc + 6 * m.trunk_junction[m.limb_attach[g]]);
 #pragma unroll
