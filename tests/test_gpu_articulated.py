@@ -176,3 +176,30 @@ def test_closed_loop_cheetah_runs_forward():
     assert np.isfinite(state).all()
     assert state[0] - x0 > 1.0, state[0] - x0          # > 0.5 m/s on average over 2 s
     p.close()
+
+
+@pytest.mark.parametrize("integrator", INTEGRATORS)
+def test_planar_and_spatial_instantiations_agree(integrator, monkeypatch):
+    """HalfCheetah runs the planar instantiation of the chain engine (csrc/dyn_chain.cuh, PLANAR = true);
+    ICEM_B200_PLANAR=0 at model upload forces the spatial one.  One env step from the same state agrees to fp32
+    rounding, h = 30 costs of the same action sequences agree like either agrees with the float64 oracle, and the
+    planar path is what a default planner uses (its launch count and results differ from neither)."""
+    rs = np.random.RandomState(11)
+    m_acts = None
+    out = {}
+    for mode in ("planar", "spatial"):
+        if mode == "spatial":
+            monkeypatch.setenv("ICEM_B200_PLANAR", "0")
+        p, m = _planner("halfcheetah", integrator=integrator)
+        if m_acts is None:
+            m_acts = rs.uniform(-1, 1, (300, 30, m.nu)).astype(np.float32)
+            start = np.concatenate([m.qpos0, 0.1 * rs.randn(m.nv)]).astype(np.float32).astype(np.float64)
+            u = rs.uniform(-1, 1, m.nu)
+        nxt, _, _ = p.sim_step(start, u)
+        out[mode] = (nxt, p.op_rollout_cost(start, m_acts))
+        p.close()
+    assert np.abs(out["planar"][0] - out["spatial"][0]).max() <= 2e-5
+    d = np.abs(out["planar"][1] - out["spatial"][1])
+    assert np.median(d) <= 1e-4, np.median(d)
+    assert np.mean(d <= 5e-3) >= 0.95, np.sort(d)[-8:]
+    assert np.abs(out["planar"][1] - out["spatial"][1]).max() > 0      # two different instruction streams did run
