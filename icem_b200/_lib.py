@@ -7,10 +7,10 @@ import numpy as np
 LIB_PATH = os.environ.get("ICEM_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
                                                            "libicem_b200.so")
 
-ICEM_ABI_VERSION = 8
+ICEM_ABI_VERSION = 9
 INTEGRATOR = {"euler": 0, "rk4": 1}
 DYN = {"dense_tanh": 0, "halfcheetah": 1, "humanoid_standup": 2, "mlp": 3, "articulated": 4}
-COST = {"halfcheetah": 0, "humanoid_standup": 1, "locomotion": 2, "reacher": 3}
+COST = {"halfcheetah": 0, "humanoid_standup": 1, "locomotion": 2, "reacher": 3, "goal_distance": 4}
 REDUCE = {"sum": 0, "best": 1, "final": 2}
 PLANNER = {"icem": 0, "cem_std": 1, "random": 2}
 UNIQUE_ID_BYTES = 128
@@ -28,11 +28,13 @@ class IcemConfig(C.Structure):
         ("bounds_like_levine", C.c_int32), ("action_change_frequency", C.c_int32),
         ("num_problems", C.c_int32), ("cost_z_index", C.c_int32), ("cost_z_strict", C.c_int32),
         ("cost_velocity_index1", C.c_int32), ("cost_reserved", C.c_int32),
+        ("cost_goal_index", C.c_int32), ("cost_achieved_index", C.c_int32), ("cost_goal_sparse", C.c_int32),
+        ("cost_goal_shaped", C.c_int32),
         ("factor_decrease_num", C.c_double), ("alpha", C.c_double), ("init_std", C.c_double),
         ("fraction_elites_reused", C.c_double), ("noise_beta", C.c_double),
         ("cost_dt", C.c_double), ("cost_ctrl_weight", C.c_double), ("cost_unhealthy_weight", C.c_double),
         ("cost_z_lo", C.c_double), ("cost_z_hi", C.c_double), ("cost_state_bound", C.c_double),
-        ("cost_forward_weight", C.c_double), ("cost_reach", C.c_double * 4),
+        ("cost_forward_weight", C.c_double), ("cost_goal_threshold", C.c_double), ("cost_reach", C.c_double * 4),
         ("seed", C.c_uint64),
         ("action_low", C.POINTER(C.c_float)), ("action_high", C.POINTER(C.c_float)),
     ]

@@ -176,6 +176,10 @@ __device__ long long g_mlp_trace[64 * 32];
 #endif
 
 // ---------------------------------------------------------------------------------------------------------------
+// kGoalCost: the goal-distance cost family (ICEM_COST_GOAL_DISTANCE) as its own instantiation -- it gathers up to six
+// observation entries at run-time indices from the register-resident state, which must not touch the register
+// allocation of the default kernel.
+template <bool kGoalCost>
 __global__ void __launch_bounds__(kMlpThreads, 1)
 mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -349,7 +353,21 @@ mlp_rollout_kernel(RolloutArgs a, SamplerConst sc, CostConst cc, MlpParams mp) {
             ob = (i == cc.idx_b) ? x[i] : ob;
           }
           float c;
-          if (cc.kind == 0) {
+          if constexpr (kGoalCost) {
+            float d2 = 0.f, e2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              float gk = 0.f, ak = 0.f;
+#pragma unroll
+              for (int i = 0; i < kMlpInPad; ++i) {
+                gk = (i == cc.goal_idx + k) ? x[i] : gk;
+                ak = (i == cc.ach_idx + k) ? x[i] : ak;
+              }
+              d2 = fmaf(gk - ak, gk - ak, d2);
+              e2 = fmaf(x[k] - x[3 + k], x[k] - x[3 + k], e2);
+            }
+            c = goal_distance_cost(cc, d2, e2);
+          } else if (cc.kind == 0) {
             c = 0.1f * a2 - ob;
             if (cc.penalise_flipping)
               c += (oa > 1.5707963267948966f ? 10.f : 0.f) + (oa < -1.5707963267948966f ? 10.f : 0.f);

@@ -272,6 +272,10 @@ static CostConst cost_const(icem_planner* p) {
     cc.z_strict = p->cfg.cost_z_strict;
   } else if (p->cfg.cost == ICEM_COST_REACHER) {
     for (int i = 0; i < 4; ++i) cc.reach[i] = (float)p->cfg.cost_reach[i];
+  } else if (p->cfg.cost == ICEM_COST_GOAL_DISTANCE) {
+    cc.goal_idx = p->cfg.cost_goal_index; cc.ach_idx = p->cfg.cost_achieved_index;
+    cc.goal_sparse = p->cfg.cost_goal_sparse; cc.goal_shaped = p->cfg.cost_goal_shaped;
+    cc.goal_threshold = (float)p->cfg.cost_goal_threshold;
   } else {
     cc.idx_a = 2;   // environments/mujoco.py:267 root z
     cc.idx_b = 0;
@@ -340,10 +344,11 @@ static void launch_mlp(icem_planner* p, const RolloutArgs& a, int rows_max) {
   const SamplerConst sc = sampler_const(p);
   const CostConst cc = cost_const(p);
   const size_t smem = mlp_smem_bytes(p->mlp.hidden);
-  ensure_dynamic_smem(mlp_rollout_kernel, smem, p->cfg.device);
+  auto kern = p->cfg.cost == ICEM_COST_GOAL_DISTANCE ? mlp_rollout_kernel<true> : mlp_rollout_kernel<false>;
+  ensure_dynamic_smem(kern, smem, p->cfg.device);
   const int tiles = (rows_max + kMlpTile - 1) / kMlpTile;
   const int grid = std::max(1, std::min(tiles, p->sm_count));     // one resident CTA per SM (weights fill smem)
-  mlp_rollout_kernel<<<grid, kMlpThreads, smem, p->stream>>>(a, sc, cc, p->mlp);
+  kern<<<grid, kMlpThreads, smem, p->stream>>>(a, sc, cc, p->mlp);
   ICEM_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
 }
@@ -928,6 +933,14 @@ int icem_create(const icem_config_t* cfg, icem_planner_t** out) {
   } else if (cfg->cost == ICEM_COST_REACHER) {
     // the distance is formed from the arm's joint angles: only the articulated ground-truth model carries them
     if (cfg->dynamics != ICEM_DYN_ARTICULATED) throw Unsupported("the reacher cost needs ICEM_DYN_ARTICULATED");
+  } else if (cfg->cost == ICEM_COST_GOAL_DISTANCE) {
+    if (cfg->dynamics != ICEM_DYN_MLP && cfg->dynamics != ICEM_DYN_DENSE_TANH)
+      throw Unsupported("the goal-distance cost reads observations of a batched model (ICEM_DYN_MLP / ICEM_DYN_DENSE_TANH)");
+    const int od = cfg->obs_dim;
+    if (cfg->cost_goal_index < 0 || cfg->cost_goal_index + 3 > od || cfg->cost_achieved_index < 0 ||
+        cfg->cost_achieved_index + 3 > od || (cfg->cost_goal_shaped && od < 6))
+      throw InvalidArg("goal / achieved-goal indices outside the observation");
+    if (!(cfg->cost_goal_threshold >= 0)) throw InvalidArg("cost_goal_threshold must be >= 0");
   } else if (cfg->cost != ICEM_COST_HALFCHEETAH && cfg->cost != ICEM_COST_HUMANOID_STANDUP) {
     throw Unsupported("unknown cost id");
   }

@@ -48,7 +48,16 @@ struct CostConst {
   int vel_index;        // >= 0: x velocity = obs[vel_index] (Humanoid, mujoco.py:333; inv_dt is 0 then); -1: finite difference
   float w_fwd;          // weight of the velocity term
   float reach[4];       // ICEM_COST_REACHER: link lengths l1, l2 and the target body's rest position (x, y)
+  int goal_idx, ach_idx, goal_sparse, goal_shaped;      // ICEM_COST_GOAL_DISTANCE (see include/icem_b200.h)
+  float goal_threshold;
 };
+
+// environments/abstract_environments.py:115-123 / environments/robotics.py:150-164 from the two squared distances
+__device__ __forceinline__ float goal_distance_cost(const CostConst& cc, float d2, float e2) {
+  const float d = sqrtf(d2), e = cc.goal_shaped ? sqrtf(e2) : 0.f;
+  if (cc.goal_sparse) return (d > cc.goal_threshold ? 1.f : 0.f) + ((cc.goal_shaped && e > cc.goal_threshold) ? 0.1f : 0.f);
+  return d + 0.1f * e;
+}
 
 // environments/mujoco.py:366-368 (Reacher): |fingertip - target| from the state (q0, q1 arm hinges about z; q2, q3 the
 // target's slide joints): fingertip = l1 (cos q0, sin q0) + l2 (cos(q0 + q1), sin(q0 + q1)), target = rest + (q2, q3);
@@ -101,6 +110,16 @@ __device__ __forceinline__ float step_cost(const CostConst& cc, const Dyn& dyn, 
     return (healthy ? 0.f : cc.w_unhealthy) + cc.w_ctrl * a2 - vel;
   }
   if (cc.kind == 3) return reacher_distance(cc, dyn.obs(0), dyn.obs(1), dyn.obs(2), dyn.obs(3));
+  if (cc.kind == 4) {
+    float d2 = 0.f, e2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float dk = dyn.obs(cc.goal_idx + k) - dyn.obs(cc.ach_idx + k);
+      d2 = fmaf(dk, dk, d2);
+      if (cc.goal_shaped) { const float ek = dyn.obs(k) - dyn.obs(3 + k); e2 = fmaf(ek, ek, e2); }
+    }
+    return goal_distance_cost(cc, d2, e2);
+  }
   if (cc.kind == 0) {   // environments/mujoco.py:67-99
     const float ang = dyn.obs(cc.idx_a), vel = dyn.obs(cc.idx_b);
     float c = 0.f;

@@ -85,6 +85,7 @@ __device__ __forceinline__ float chain_step_cost_pre(const CostConst& cc, const 
     return ((z_ok && ok) ? 0.f : cc.w_unhealthy) + cc.w_ctrl * a2 - vel;
   }
   if (cc.kind == 3) return reacher_distance(cc, L.state(0), L.state(1), L.state(2), L.state(3));
+  if (cc.kind == 4) return 0.f;      // goal-space costs read observations of the batched models only (refused at icem_create)
   if (cc.kind == 0) {   // environments/mujoco.py:67-99
     const float ang = L.state(cc.idx_a + oo), vel = L.state(cc.idx_b + oo);
     float c = 0.f;

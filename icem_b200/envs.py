@@ -74,13 +74,26 @@ def humanoid_standup_cost_fn(observation, action, next_obs=None):
     return -observation[..., 2] + 0.1 * np.square(action).sum(axis=-1)
 
 
+def goal_distance_cost_fn(observation, action, next_obs, *, goal_index, achieved_index, sparse=False, threshold=0.05,
+                          shaped=False):
+    """environments/abstract_environments.py:115-123 / environments/robotics.py:150-164: distance between the desired
+    goal and the achieved goal inside the observation (+ 0.1 x end effector to box when `shaped`), dense or thresholded."""
+    o = np.asarray(observation)
+    dist = np.linalg.norm(o[..., goal_index:goal_index + 3] - o[..., achieved_index:achieved_index + 3], axis=-1)
+    eff = np.linalg.norm(o[..., :3] - o[..., 3:6], axis=-1) if shaped else 0
+    if sparse:
+        return np.asarray(dist > threshold, dtype=np.float32) + np.asarray(eff > threshold, dtype=np.float32) * 0.1
+    return dist + eff * 0.1
+
+
 class DenseStandInEnv(_EnvBase):
     """Environment whose true dynamics IS the dense-tanh model (obs' = tanh(W_o obs + W_a a + b)); used for the
     memory-side workloads and the plumbing tests.  state == observation."""
 
     def __init__(self, *, name="dense", act_dim, bound, cost, obs_dim, penalise_flipping=False, weights=None,
-                 **kwargs):
+                 cost_params=None, **kwargs):
         super().__init__(name=name, **kwargs)
+        self.cost_params = cost_params      # cost="goal_distance": goal_index, achieved_index, sparse, threshold, shaped
         self.store_init_arguments(locals())
         self.action_space = Box(-bound * np.ones(act_dim), bound * np.ones(act_dim))
         self.observation_space = Box(-np.ones(obs_dim), np.ones(obs_dim))
@@ -91,9 +104,13 @@ class DenseStandInEnv(_EnvBase):
         self._rs = np.random.RandomState(0)
 
     def cuda_cost_spec(self):
+        if self.cost == "goal_distance":
+            return self.cost, False, dict(self.cost_params)
         return self.cost, self.penalise_flipping
 
     def cost_fn(self, observation, action, next_obs):
+        if self.cost == "goal_distance":
+            return goal_distance_cost_fn(observation, action, next_obs, **self.cost_params)
         if self.cost == "halfcheetah":
             return halfcheetah_cost_fn(observation, action, next_obs, self.penalise_flipping)
         return humanoid_standup_cost_fn(observation, action, next_obs)
@@ -133,9 +150,10 @@ class DenseStandInEnv(_EnvBase):
 class MlpStandInEnv(DenseStandInEnv):
     """Environment whose true dynamics IS the MLP forward model (float64 host evaluation of one transition)."""
 
-    def __init__(self, *, name="mlp", act_dim, bound, cost, obs_dim, penalise_flipping=False, mlp=None, **kwargs):
+    def __init__(self, *, name="mlp", act_dim, bound, cost, obs_dim, penalise_flipping=False, mlp=None,
+                 cost_params=None, **kwargs):
         super().__init__(name=name, act_dim=act_dim, bound=bound, cost=cost, obs_dim=obs_dim,
-                         penalise_flipping=penalise_flipping, **kwargs)
+                         penalise_flipping=penalise_flipping, cost_params=cost_params, **kwargs)
         self.mlp = mlp
 
     def step(self, action):

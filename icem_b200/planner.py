@@ -84,6 +84,9 @@ def _cost_fields(cp):
                 cost_state_bound=float(cp.get("state_bound", 0.0)),
                 cost_velocity_index1=int(cp.get("velocity_index", -1)) + 1, cost_reserved=0,
                 cost_forward_weight=float(cp.get("forward_weight", 1.0)),
+                cost_goal_index=int(cp.get("goal_index", 0)), cost_achieved_index=int(cp.get("achieved_index", 0)),
+                cost_goal_sparse=int(bool(cp.get("sparse", False))), cost_goal_shaped=int(bool(cp.get("shaped", False))),
+                cost_goal_threshold=float(cp.get("threshold", 0.0)),
                 cost_reach=(C.c_double * 4)(*[float(v) for v in cp.get("reach", (0.1, 0.11, 0.0, 0.0))]))
 
 

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define ICEM_ABI_VERSION 8
+#define ICEM_ABI_VERSION 9
 
 /* status codes */
 enum { ICEM_OK = 0, ICEM_ERR_INVALID = 1, ICEM_ERR_CUDA = 2, ICEM_ERR_STATE = 3, ICEM_ERR_UNSUPPORTED = 4,
@@ -47,10 +47,16 @@ enum {
                                     x_velocity = (next_obs[0] - obs[0]) / dt (Ant, Hopper; reads next_obs, so all h
                                     steps are simulated) or obs[cost_velocity_index] (Humanoid); parameters in
                                     icem_config_t.cost_* */
-  ICEM_COST_REACHER = 3          /* Reacher (environments/mujoco.py:346-368): |fingertip - target|, the last three
+  ICEM_COST_REACHER = 3,         /* Reacher (environments/mujoco.py:346-368): |fingertip - target|, the last three
                                     entries of gym's observation.  On the device the observation is the state
                                     (q0, q1 = arm hinges, q2, q3 = target slides), so the distance is formed from the
                                     planar forward kinematics with the constants in icem_config_t.cost_reach */
+  ICEM_COST_GOAL_DISTANCE = 4    /* goal-space envs (environments/abstract_environments.py:115-123
+                                    MaskedGoalSpaceEnvironmentInterface.cost_fn; environments/robotics.py:150-164
+                                    FetchPickAndPlace.cost_fn): d = |obs[goal..goal+3) - obs[achieved..achieved+3)|,
+                                    shaped: e = |obs[0..3) - obs[3..6)| (end effector to box);
+                                    dense: d + 0.1 e, sparse: [d > threshold] + 0.1 [e > threshold].  Reads the
+                                    observation only: for the batched models (ICEM_DYN_MLP, ICEM_DYN_DENSE_TANH) */
 };
 
 /* action sampler / planner family */
@@ -102,6 +108,10 @@ typedef struct icem_config {
   int32_t cost_velocity_index1;   /* LOCOMOTION: 0 = x velocity by finite difference of obs[0]; k > 0 = read obs[k - 1]
                                      (Humanoid: observation[nq], mujoco.py:333) */
   int32_t cost_reserved;          /* keeps the doubles 8-byte aligned; must be 0 */
+  int32_t cost_goal_index;        /* GOAL_DISTANCE: first observation index of the desired goal (goal_idx[0]) */
+  int32_t cost_achieved_index;    /* GOAL_DISTANCE: first observation index of the achieved goal (Fetch: 3 = box, FetchReach: 0) */
+  int32_t cost_goal_sparse;       /* GOAL_DISTANCE: 1 = thresholded 0/1 cost (env_params.sparse) */
+  int32_t cost_goal_shaped;       /* GOAL_DISTANCE: 1 = add 0.1 * end-effector-to-box term (FetchPickAndPlace shaped_reward) */
   double factor_decrease_num;     /* gamma */
   double alpha;
   double init_std;
@@ -113,6 +123,7 @@ typedef struct icem_config {
   double cost_z_lo, cost_z_hi;    /* LOCOMOTION: _healthy_z_range */
   double cost_state_bound;        /* LOCOMOTION: Hopper |states[..., 2:]| < bound (_healthy_state_range); <= 0: none */
   double cost_forward_weight;     /* LOCOMOTION: weight of the velocity term (Humanoid _forward_reward_weight 1.25); 0 = 1 */
+  double cost_goal_threshold;     /* GOAL_DISTANCE: env_params.threshold */
   double cost_reach[4];           /* REACHER: link 1 length, link 2 length to the fingertip, world x, y of the target at
                                      q2 = q3 = 0 (gym reacher.xml: 0.1, 0.11, 0, 0 -- the slides' `ref` cancels the body offset) */
   uint64_t seed;                  /* Philox key (production noise) */

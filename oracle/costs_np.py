@@ -89,3 +89,15 @@ def reacher_observation(state, p=REACHER):
     fy = p["l1"] * np.sin(q0) + p["l2"] * np.sin(q0 + q1)
     return np.stack([np.cos(q0), np.cos(q1), np.sin(q0), np.sin(q1), tx, ty, st[..., 4], st[..., 5],
                      fx - (p["target0"][0] + tx), fy - (p["target0"][1] + ty), np.zeros_like(q0)], axis=-1)
+
+
+def goal_distance_cost(obs, goal_idx, achieved_idx, sparse=False, threshold=0.05, shaped=False):
+    """environments/abstract_environments.py:115-123 (MaskedGoalSpaceEnvironmentInterface.cost_fn: FetchReach) and,
+    with `shaped`, environments/robotics.py:150-164 (FetchPickAndPlace.cost_fn, the sparse branch of which always adds
+    the end-effector term -- dist_end_eff_to_box is 0 there unless shaped_reward)."""
+    obs = np.asarray(obs)
+    dist = np.linalg.norm(np.take(obs, goal_idx, axis=-1) - np.take(obs, achieved_idx, axis=-1), axis=-1)
+    eff = np.linalg.norm(obs[..., :3] - obs[..., 3:6], axis=-1) if shaped else 0
+    if sparse:
+        return np.asarray(dist > threshold, dtype=np.float32) + np.asarray(eff > threshold, dtype=np.float32) * 0.1
+    return dist + eff * 0.1

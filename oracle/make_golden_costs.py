@@ -81,7 +81,38 @@ def reference_reacher_costs():
     return rm.Reacher.cost_fn(None, o.copy(), a, o)
 
 
+GOAL_CASES = [  # (name, reference class, goal_idx, achieved_idx, sparse, threshold, shaped)
+    ("fetch_pick_dense_shaped", "FetchPickAndPlace", list(range(25, 28)), [3, 4, 5], False, 0.05, True),
+    ("fetch_pick_dense", "FetchPickAndPlace", list(range(25, 28)), [3, 4, 5], False, 0.05, False),
+    ("fetch_pick_sparse_shaped", "FetchPickAndPlace", list(range(25, 28)), [3, 4, 5], True, 2.2, True),
+    ("fetch_reach_dense", "FetchReach", list(range(10, 13)), [0, 1, 2], False, 0.05, False),
+    ("fetch_reach_sparse", "FetchReach", list(range(10, 13)), [0, 1, 2], True, 2.2, False),
+]
+
+
+def goal_inputs(width):
+    return np.random.RandomState(10 + width).randn(40, 6, width)
+
+
+def reference_goal_costs():
+    """environments/robotics.py:150-164 (FetchPickAndPlace) and abstract_environments.py:115-123 (FetchReach inherits
+    MaskedGoalSpaceEnvironmentInterface.cost_fn), called unbound on a stub carrying the attributes they read."""
+    ref_loader.load_reference()
+    import environments.robotics as rr
+    out = {}
+    for name, cls_name, gi, ai, sparse, thr, shaped in GOAL_CASES:
+        cls = getattr(rr, cls_name)
+        st = types.SimpleNamespace(goal_idx=np.asarray(gi), achieved_goal_idx=ai, sparse=sparse, threshold=thr,
+                                   shaped_reward=shaped)
+        st.goal_from_observation = lambda o, st=st, cls=cls: cls.goal_from_observation(st, o)
+        st.achieved_goal_from_observation = lambda o, st=st, cls=cls: cls.achieved_goal_from_observation(st, o)
+        o = goal_inputs(gi[-1] + 1)
+        out[name] = np.asarray(cls.cost_fn(st, o.reshape(-1, o.shape[-1]).copy(), None, None)).reshape(o.shape[:-1])
+    return out
+
+
 def main():
+    np.savez_compressed(os.path.join(OUT, "costs_goal_distance.npz"), **reference_goal_costs())
     h, a = reference_costs()
     hu = reference_humanoid_costs()
     np.savez_compressed(os.path.join(OUT, "costs_reacher.npz"), reacher=reference_reacher_costs())

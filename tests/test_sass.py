@@ -44,7 +44,7 @@ def test_register_budgets_of_the_hot_kernels(lib):
         k = _find(res, "colored_sampler_kernel" + shape)
         assert k["reg"] <= 96 and k["stack"] == 0, k
     # tensor-core MLP rollout: 17 warps -> 96 registers at most (65536 / (5 warps * 32 lanes) per scheduler)
-    k = _find(res, "mlp_rollout_kernelE")
+    k = _find(res, "mlp_rollout_kernelILb0E")
     assert k["reg"] <= 96, k
     # branch-parallel articulated engine: up to 12 warps per SM (384 threads) -> at most 170 registers, no spills
     for g in (1, 2, 4):
@@ -73,7 +73,7 @@ def test_sass_shows_the_blackwell_paths(lib):
         hits = [k for k in funcs if all(p in k for p in parts)]
         assert len(hits) == 1, (parts, hits)
         return "\n".join(funcs[hits[0]])
-    mlp = body("mlp_rollout_kernelE")
+    mlp = body("mlp_rollout_kernelILb0E")
     for mnemonic in ("UTCHMMA", "LDTM", "UTCBAR", "MUFU.TANH", "SYNCS"):      # tcgen05.mma / .ld / .commit, mbarriers
         assert mnemonic in mlp, mnemonic
     chain = body("chain_rollout_kernel", "ILi4ELb1ELb1ELb0ELb0")
