@@ -298,7 +298,8 @@ struct ChainLane {
     }
     int j0 = m.n_dof_start[node];
     const int j1 = j0 + m.n_dof_count[node];
-    if (root && m.root_free) {
+    const int rf = m.root_free;          // q index of a slide / hinge dof j: j + 1 behind a free joint, else j
+    if (root && rf) {
       // free joint: 3 world translations + 3 body-frame rotation rates, handled as ONE 6-dof joint.  Its motion
       // subspace spans all of R^6, so pass 2 solves the root acceleration directly (floating base) and no per-dof
       // record is needed: only R and the velocity-product term  c_J = sum_k (v xm S_k) qd_k = [0; v_lin x w].
@@ -330,7 +331,7 @@ struct ChainLane {
       const int t = m.d_type[j];
       float ax[3], S[6], c[6];
       ch::matvec(R, m.d_axis[j], ax);
-      const float qj = q[m.d_qadr[j]], qdj = qd[j];
+      const float qj = q[j + rf], qdj = qd[j];
       if (t == kSlide) {
         S[0] = S[1] = S[2] = 0.f;
         S[3] = ax[0]; S[4] = ax[1]; S[5] = ax[2];
@@ -397,7 +398,7 @@ struct ChainLane {
     const int j0 = m.n_dof_start[node], j1 = j0 + m.n_dof_count[node];
     for (int j = j0; j < j1; ++j) {
       const int t = m.d_type[j];
-      const float qj = q[m.d_qadr[j]], qdj = qd[j];
+      const float qj = q[j], qdj = qd[j];          // no free joint in a planar model: q index == dof index
       float Sw, Sx, Sz;
       if (t == kSlide) {
         const float ax = R[0] * m.d_axis[j][0] + R[2] * m.d_axis[j][2];
@@ -873,18 +874,20 @@ struct ChainLane {
 
   // q (+)= step * rate for one dof.  The quaternion of a free joint moves when its last rotation dof comes by:
   // the caller collects the three body-frame rates in `w` (dof order) on the way.
-  __host__ __device__ __forceinline__ void advance_position(int j, const ChRef& qsrc, const ChRef& qdst, float rate,
-                                                            float (&w)[3], float step) const {
-    const ChainModel& m = *M;
-    const int t = m.d_type[j];
-    if (t != kFreeRot) {
-      const int qa = m.d_qadr[j];
+  // Coordinate addresses need no table: a free joint, if any, is the first joint of the root (build_chain_model), so
+  // dofs 0..2 are its translations (q 0..2), 3..5 its rotation rates (quaternion at q 3..6) and every later dof j has
+  // q index j + 1; without a free joint q index == dof index.  (`root_free` is read once per substep by the caller: as
+  // table reads, type and address were two dependent shared-memory loads in front of every state update.)
+  __host__ __device__ __forceinline__ void advance_position(int j, int root_free, const ChRef& qsrc, const ChRef& qdst,
+                                                            float rate, float (&w)[3], float step) const {
+    if (!(root_free && j >= 3 && j < 6)) {
+      const int qa = j + ((root_free && j >= 6) ? 1 : 0);
       qdst[qa] = qsrc[qa] + step * rate;
       return;
     }
     w[0] = w[1]; w[1] = w[2]; w[2] = rate;
-    if (j + 1 < m.nv && m.d_type[j + 1] == kFreeRot) return;
-    const int qa = m.d_qadr[j];
+    if (j < 5) return;
+    const int qa = 3;
     const float n = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
     const float half = 0.5f * step * n;
     float sn, cs;
@@ -909,7 +912,7 @@ struct ChainLane {
     pass2(rec);
     ctx->group_sync();       // the junction accelerations of pass 3 overwrite the junction sums pass 2 was reading
     const float dt = m.dt;
-    const int gg = g;
+    const int gg = g, rf = m.root_free;
     const ChainLane* self = this;
     float w[3] = {0.f, 0.f, 0.f};
     pass3([&](int j, bool trunk, float qacc) {
@@ -917,7 +920,7 @@ struct ChainLane {
       if (trunk && gg != 0) return;
       const float v = qd[j] + dt * qacc;
       qd[j] = v;
-      self->advance_position(j, q, q, v, w, dt);
+      self->advance_position(j, rf, q, q, v, w, dt);
     });
     ctx->group_sync();
   }
@@ -931,7 +934,7 @@ struct ChainLane {
     const ChRef qs = shared_rec(m.s_rk), vs = shared_rec(m.s_rk + m.nq);
     const ChRef vsum = shared_rec(m.s_rk + m.nq + m.nv), asum = shared_rec(m.s_rk + m.nq + 2 * m.nv);
     const float dt = m.dt;
-    const int gg = g;
+    const int gg = g, rf = m.root_free;
     const ChainLane* self = this;
     for (int stage = 0; stage < 4; ++stage) {
       float rec[kChNodeRec];
@@ -950,10 +953,10 @@ struct ChainLane {
         if (stage < 3) {
           vsum[j] = vw;
           asum[j] = aw;
-          self->advance_position(j, q0, qs, vcur, w, nxt);      // stage positions start from the substep's q0
+          self->advance_position(j, rf, q0, qs, vcur, w, nxt);      // stage positions start from the substep's q0
           vs[j] = v0[j] + nxt * qacc;
         } else {
-          self->advance_position(j, q0, q0, vw, w, dt);
+          self->advance_position(j, rf, q0, q0, vw, w, dt);
           v0[j] = v0[j] + dt * aw;
         }
       });
@@ -1207,6 +1210,12 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
   // a limb's last node keeps its record in registers (pass 1 -> pass 2), its first one is parked in the junction region
   m.p_node = p; p += kChNodeRec * (m.max_limb_nodes > 2 ? m.max_limb_nodes - 2 : 0);
   m.p_end = p;
+  // the engine addresses coordinates without a table (advance_position, walk_joints): q index == dof index, shifted by
+  // one behind a free joint (4 quaternion entries for 3 rotation dofs)
+  for (int j = 0; j < m.nv; ++j) {
+    const int want = m.d_type[j] == kFreeRot ? 3 : j + ((m.root_free && j >= 6) ? 1 : 0);
+    if (m.d_qadr[j] != want) { *why = "unexpected coordinate layout"; return false; }
+  }
   {
     bool is_trunk_dof[kChMaxDofs] = {false};
     for (int t = 0; t < m.n_trunk; ++t) {
