@@ -86,9 +86,13 @@ struct ChainModel {
   int seq_node[kChMaxLimbs][kChMaxTrunk + kChMaxLimbNodes];   // node lane g visits at position i of its walk, -1 = none
   int n_dof_start[kChMaxNodes], n_dof_count[kChMaxNodes], n_con_start[kChMaxNodes], n_con_count[kChMaxNodes];
   float n_pos[kChMaxNodes][3], n_mass[kChMaxNodes], n_com[kChMaxNodes][3], n_inertia[kChMaxNodes][6];
-  int d_type[kChMaxDofs], d_qadr[kChMaxDofs], d_limited[kChMaxDofs], d_act[kChMaxDofs];
-  int d_rec[kChMaxDofs];                         // record index of the dof inside its region (trunk / own limb)
-  int d_slot[kChMaxDofs];                        // first slot of that record: s_dof + 21 * d_rec (trunk), p_dof + 19 * d_rec (limb)
+  int d_type[kChMaxDofs], d_limited[kChMaxDofs], d_act[kChMaxDofs];
+  // A dof's record sits at s_dof + 21 * index (trunk) / p_dof + 19 * index (own limb), index = its rank in walk order.  The
+  // records of a node's (non-free) dofs are consecutive, so the walks address them from ONE table read per node:
+  int n_slot0[kChMaxNodes];                      // slot of the record of the node's first slide / hinge dof
+  // ... and passes 2 / 3 take the dof range of walk position i straight from per-lane tables (no node indirection):
+  int seq_j0[kChMaxLimbs][kChMaxTrunk + kChMaxLimbNodes], seq_j1[kChMaxLimbs][kChMaxTrunk + kChMaxLimbNodes];
+  int seq_slot0[kChMaxLimbs][kChMaxTrunk + kChMaxLimbNodes];
   float d_axis[kChMaxDofs][3], d_anchor[kChMaxDofs][3];
   float d_stiff[kChMaxDofs], d_damp[kChMaxDofs], d_arm[kChMaxDofs], d_lo[kChMaxDofs], d_hi[kChMaxDofs];
   float d_klim[kChMaxDofs], d_blim[kChMaxDofs], d_gear[kChMaxDofs];
@@ -258,8 +262,12 @@ struct ChainLane {
   __host__ __device__ __forceinline__ ChRef shared_rec(int slot) const { return ChRef{sh + slot * STRIDE}; }
   __host__ __device__ __forceinline__ ChRef private_rec(int slot) const { return ChRef{pr + slot * STRIDE}; }
   __host__ __device__ __forceinline__ float& state(int i) const { return sh[(M->s_state + i) * STRIDE]; }
-  __host__ __device__ __forceinline__ ChRef dof_rec(bool trunk, int j) const {
-    return ChRef{(trunk ? sh : pr) + M->d_slot[j] * STRIDE};      // one table read instead of base + stride * index
+  // first dof record of a node (slot from a per-node / per-walk-position table) and the distance between records
+  __host__ __device__ __forceinline__ float* rec_base(bool trunk, int slot0) const {
+    return (trunk ? sh : pr) + slot0 * STRIDE;
+  }
+  static __host__ __device__ __forceinline__ int rec_step(bool trunk) {
+    return (trunk ? kChTrunkDofRec : kChDofRec) * STRIDE;
   }
   // Node records: trunk nodes in the shared region; a limb's FIRST node is parked in the junction region (idle
   // between the limb's start and the junction sums: 16 slots per lane of the group), its last node stays in
@@ -303,7 +311,7 @@ struct ChainLane {
       // free joint: 3 world translations + 3 body-frame rotation rates, handled as ONE 6-dof joint.  Its motion
       // subspace spans all of R^6, so pass 2 solves the root acceleration directly (floating base) and no per-dof
       // record is needed: only R and the velocity-product term  c_J = sum_k (v xm S_k) qd_k = [0; v_lin x w].
-      const int qa = m.d_qadr[j0];
+      const int qa = 0;                  // the free joint is the first joint of the root: coordinates 0..6
       O[0] = q[qa]; O[1] = q[qa + 1]; O[2] = q[qa + 2];
       float qw = q[qa + 3], x = q[qa + 4], y = q[qa + 5], z = q[qa + 6];
       {   // rotation of the NORMALISED quaternion (a start state may carry reset noise on it): R must be orthonormal,
@@ -327,7 +335,9 @@ struct ChainLane {
       fr[9] = cl[0]; fr[10] = cl[1]; fr[11] = cl[2];
       j0 += 6;
     }
-    for (int j = j0; j < j1; ++j) {
+    float* rb = rec_base(trunk, m.n_slot0[node]);
+    const int rs = rec_step(trunk);
+    for (int j = j0; j < j1; ++j, rb += rs) {
       const int t = m.d_type[j];
       float ax[3], S[6], c[6];
       ch::matvec(R, m.d_axis[j], ax);
@@ -371,7 +381,7 @@ struct ChainLane {
         if (above) tau += m.d_klim[j] * (m.d_hi[j] - qj);
         if (below || above) { keff += m.d_klim[j]; beff += m.d_blim[j]; }
       }
-      const ChRef r = dof_rec(trunk, j);
+      const ChRef r{rb};
 #pragma unroll
       for (int e = 0; e < 6; ++e) {
         r[e] = S[e];
@@ -396,7 +406,9 @@ struct ChainLane {
       p[2] += R[0] * m.n_pos[node][2] - R[2] * m.n_pos[node][0];
     }
     const int j0 = m.n_dof_start[node], j1 = j0 + m.n_dof_count[node];
-    for (int j = j0; j < j1; ++j) {
+    float* rb = rec_base(trunk, m.n_slot0[node]);
+    const int rs = rec_step(trunk);
+    for (int j = j0; j < j1; ++j, rb += rs) {
       const int t = m.d_type[j];
       const float qj = q[j], qdj = qd[j];          // no free joint in a planar model: q index == dof index
       float Sw, Sx, Sz;
@@ -434,7 +446,7 @@ struct ChainLane {
         if (above) tau += m.d_klim[j] * (m.d_hi[j] - qj);
         if (below || above) { keff += m.d_klim[j]; beff += m.d_blim[j]; }
       }
-      const ChRef r = dof_rec(trunk, j);
+      const ChRef r{rb};
       r[1] = Sw; r[3] = Sx; r[5] = Sz;
       r[9] = cx * qdj; r[11] = cz * qdj;
       v[1] += Sw * qdj; v[3] += Sx * qdj; v[5] += Sz * qdj;
@@ -682,12 +694,14 @@ struct ChainLane {
 #pragma unroll
         for (int e = 0; e < 9; ++e) IA.B[e] += jr[6 + e];
       }
-      int j0 = m.n_dof_start[node];
-      const int j1 = j0 + m.n_dof_count[node];
+      int j0 = m.seq_j0[g][i];
+      const int j1 = m.seq_j1[g][i];
       const bool free_root = i == 0 && m.root_free;
       if (free_root) j0 += 6;
-      for (int j = j1 - 1; j >= j0; --j) {
-        const ChRef r = dof_rec(trunk, j);
+      const int rs = rec_step(trunk);
+      float* rb = rec_base(trunk, m.seq_slot0[g][i]) + (j1 - 1 - j0) * rs;
+      for (int j = j1 - 1; j >= j0; --j, rb -= rs) {
+        const ChRef r{rb};
         float S[6], c[6], U[6], Ud[6];
 #pragma unroll
         for (int e = 0; e < 6; ++e) { S[e] = r[e]; c[e] = r[6 + e]; }
@@ -768,9 +782,11 @@ struct ChainLane {
         Ayy += jr[0]; Byx += jr[1]; Byz += jr[2]; Cxx += jr[3]; Czz += jr[4]; Cxz += jr[5];
         P1 += jr[6]; P3 += jr[7]; P5 += jr[8];
       }
-      const int j0 = m.n_dof_start[node], j1 = j0 + m.n_dof_count[node];
-      for (int j = j1 - 1; j >= j0; --j) {
-        const ChRef r = dof_rec(trunk, j);
+      const int j0 = m.seq_j0[g][i], j1 = m.seq_j1[g][i];
+      const int rs = rec_step(trunk);
+      float* rb = rec_base(trunk, m.seq_slot0[g][i]) + (j1 - 1 - j0) * rs;
+      for (int j = j1 - 1; j >= j0; --j, rb -= rs) {
+        const ChRef r{rb};
         const float S1 = r[1], S3 = r[3], S5 = r[5], c3 = r[9], c5 = r[11];
         // U = IA S
         const float U1 = Ayy * S1 + Byx * S3 + Byz * S5;
@@ -809,9 +825,11 @@ struct ChainLane {
         const ChRef ar = shared_rec(m.s_acc + 6 * m.trunk_junction[m.limb_attach[g]]);
         a1 = ar[1]; a3 = ar[3]; a5 = ar[5];
       }
-      const int j0 = m.n_dof_start[node], j1 = j0 + m.n_dof_count[node];
-      for (int j = j0; j < j1; ++j) {
-        const ChRef r = dof_rec(trunk, j);
+      const int j0 = m.seq_j0[g][i], j1 = m.seq_j1[g][i];
+      float* rb = rec_base(trunk, m.seq_slot0[g][i]);
+      const int rs = rec_step(trunk);
+      for (int j = j0; j < j1; ++j, rb += rs) {
+        const ChRef r{rb};
         a3 += r[9]; a5 += r[11];
         const float qacc = r[18] - (r[13] * a1 + r[15] * a3 + r[17] * a5);
         a1 += r[1] * qacc; a3 += r[3] * qacc; a5 += r[5] * qacc;
@@ -845,8 +863,8 @@ struct ChainLane {
 #pragma unroll
         for (int e = 0; e < 6; ++e) a[e] = ar[e];
       }
-      int j0 = m.n_dof_start[node];
-      const int j1 = j0 + m.n_dof_count[node];
+      int j0 = m.seq_j0[g][i];
+      const int j1 = m.seq_j1[g][i];
       if (i == 0 && m.root_free) {
         const ChRef fr = shared_rec(m.s_free);
 #pragma unroll
@@ -855,8 +873,10 @@ struct ChainLane {
         for (int e = 0; e < 6; ++e) sink(j0 + e, true, fr[18 + e]);
         j0 += 6;
       }
-      for (int j = j0; j < j1; ++j) {
-        const ChRef r = dof_rec(trunk, j);
+      float* rb = rec_base(trunk, m.seq_slot0[g][i]);
+      const int rs = rec_step(trunk);
+      for (int j = j0; j < j1; ++j, rb += rs) {
+        const ChRef r{rb};
         float qacc = r[18];
 #pragma unroll
         for (int e = 0; e < 6; ++e) { a[e] += r[6 + e]; qacc -= r[12 + e] * a[e]; }
@@ -1010,6 +1030,7 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
   static const char* none = "";
   *why = none;
   memset(&m, 0, sizeof m);
+  int d_rec[kChMaxDofs] = {0}, d_slot[kChMaxDofs] = {0};     // record rank / first slot of every dof (host only)
   if (a.nb < 1 || a.nb > kChMaxNodes || a.nv > kChMaxDofs || a.nc > kChMaxCon) { *why = "too large"; return false; }
   if (a.body_dof_count[0] < 1) { *why = "root body without joints"; return false; }
   // ---- fuse jointless bodies into the node of their parent ---------------------------------------------------------
@@ -1129,7 +1150,7 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
     }
   // ---- dofs -----------------------------------------------------------------------------------------------------
   for (int j = 0; j < a.nv; ++j) {
-    m.d_type[j] = a.dof_type[j]; m.d_qadr[j] = a.dof_qadr[j]; m.d_limited[j] = a.dof_limited[j];
+    m.d_type[j] = a.dof_type[j]; m.d_limited[j] = a.dof_limited[j];
     m.d_act[j] = a.dof_act[j];
     if (m.d_act[j] >= act_dim) { *why = "actuator index out of range"; return false; }
     for (int k = 0; k < 3; ++k) { m.d_axis[j][k] = a.dof_axis[3 * j + k]; m.d_anchor[j][k] = a.dof_anchor[3 * j + k]; }
@@ -1150,9 +1171,9 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
           return false;
         }
         m.root_free = 1;
-        m.d_rec[j] = 0;
+        d_rec[j] = 0;
       } else {
-        m.d_rec[j] = m.trunk_dofs++;
+        d_rec[j] = m.trunk_dofs++;
       }
       if ((ty == kFreeTrans || ty == kFreeRot) && k != 0) { *why = "free joint below the root"; return false; }
       if (k == 0 && ty == kHinge) seen_hinge = true;
@@ -1176,7 +1197,7 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
       const int n = m.limb_node[l][k];
       for (int j = m.n_dof_start[n]; j < m.n_dof_start[n] + m.n_dof_count[n]; ++j) {
         if (m.d_type[j] != kSlide && m.d_type[j] != kHinge) { *why = "free joint on a limb"; return false; }
-        m.d_rec[j] = cnt++;
+        d_rec[j] = cnt++;
       }
     }
     m.max_limb_dofs = cnt > m.max_limb_dofs ? cnt : m.max_limb_dofs;
@@ -1214,7 +1235,7 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
   // one behind a free joint (4 quaternion entries for 3 rotation dofs)
   for (int j = 0; j < m.nv; ++j) {
     const int want = m.d_type[j] == kFreeRot ? 3 : j + ((m.root_free && j >= 6) ? 1 : 0);
-    if (m.d_qadr[j] != want) { *why = "unexpected coordinate layout"; return false; }
+    if (a.dof_qadr[j] != want) { *why = "unexpected coordinate layout"; return false; }
   }
   {
     bool is_trunk_dof[kChMaxDofs] = {false};
@@ -1223,7 +1244,24 @@ inline bool build_chain_model(const ChainSource& a, int act_dim, ChainModel& m, 
       for (int j = m.n_dof_start[n]; j < m.n_dof_start[n] + m.n_dof_count[n]; ++j) is_trunk_dof[j] = true;
     }
     for (int j = 0; j < m.nv; ++j)
-      m.d_slot[j] = is_trunk_dof[j] ? m.s_dof + kChTrunkDofRec * m.d_rec[j] : m.p_dof + kChDofRec * m.d_rec[j];
+      d_slot[j] = is_trunk_dof[j] ? m.s_dof + kChTrunkDofRec * d_rec[j] : m.p_dof + kChDofRec * d_rec[j];
+    for (int n = 0; n < m.n_nodes; ++n) {
+      const int j1 = m.n_dof_start[n] + m.n_dof_count[n];
+      const int jf = m.n_dof_start[n] + ((n == m.trunk_node[0] && m.root_free) ? 6 : 0);
+      m.n_slot0[n] = jf < j1 ? d_slot[jf] : 0;
+      for (int j = jf; j < j1; ++j)
+        if (d_slot[j] != m.n_slot0[n] + (j - jf) * (is_trunk_dof[j] ? kChTrunkDofRec : kChDofRec)) {
+          *why = "dof records of a node are not consecutive";
+          return false;
+        }
+    }
+    for (int g2 = 0; g2 < kChMaxLimbs; ++g2)
+      for (int i = 0; i < kChMaxTrunk + kChMaxLimbNodes; ++i) {
+        const int n = m.seq_node[g2][i];
+        m.seq_j0[g2][i] = n >= 0 ? m.n_dof_start[n] : 0;
+        m.seq_j1[g2][i] = n >= 0 ? m.n_dof_start[n] + m.n_dof_count[n] : 0;
+        m.seq_slot0[g2][i] = n >= 0 ? m.n_slot0[n] : 0;
+      }
   }
   // planar robots (HalfCheetah, Hopper): no free joint, slides inside the x-z plane, hinges about +-y, every offset /
   // centre of mass / anchor / contact point at y = 0, no inertia product with y
