@@ -127,3 +127,20 @@ def test_planar_instantiation_matches_oracle_and_spatial_engine(host_lib, name, 
                                             fptr(np.zeros((1, 1, ant.nu), np.float32)),
                                             np.zeros((1, 2, ant.nq + ant.nv)).ctypes.data_as(C.POINTER(C.c_double)))
     assert rc == 2
+
+
+def test_twelve_humanoid_warps_fit_in_shared_memory(host_lib):
+    """The launch of the fused kernel holds up to 12 warps per SM for HumanoidStandup (csrc/planner.cu::launch_chain_impl,
+    rollout_chain.cuh::chain_rollout_smem_bytes): model + sampler tables + 12 warp scratches must stay inside the 227 KB
+    a CTA may use -- a few hundred bytes of slack, so growing ChainModel or a record silently costs a warp (and a whole
+    round at N = 13107 rows per launch).  Same arithmetic as chain_rollout_smem_bytes<true> for h = 30, d = 17."""
+    rc, out, why = _describe(host_lib, "humanoid_standup")
+    assert rc == 0, why
+    warp_floats, model_bytes = out[6], out[7]
+    h, d, K = 30, 17, 16
+    gs = 2 * K + 1
+    fixed = ((model_bytes // 4 + 3) & ~3) + ((h * gs + 3) & ~3) + 2 * ((h * d + 3) & ~3) + 2 * ((d + 3) & ~3)
+    stride = (h * d + 3) & ~3
+    sample_floats = 2 * stride + ((d * gs + 3) & ~3)
+    per_warp = max(sample_floats, (warp_floats + 3) & ~3)
+    assert (fixed + 12 * per_warp) * 4 <= 227 * 1024, ((fixed + 12 * per_warp) * 4, model_bytes, warp_floats)
